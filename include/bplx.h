@@ -1,0 +1,180 @@
+/*
+ * bplx.h -- C ABI of the B200-native Dixon-Coles hot path for bpl-next.
+ *
+ * The reference (anguswilliams91/bpl-next) has no FFI: its hot path is the numpyro model callable
+ * handed to NUTS (bpl/dixon_coles.py:100, bpl/extended_dixon_coles.py:293,
+ * bpl/neutral_dixon_coles.py:330, bpl/neutral_dixon_coles_WC.py:281,
+ * bpl/dynamic_dixon_coles.py:279) and the eager predict_* methods (bpl/base.py:74-148).  These
+ * entry points are what a jax.ffi / ctypes binding for that path binds (INTEGRATION.md shows both).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, int return (0 = ok, <0 = bplx_status), no exceptions, no exit();
+ *     bplx_last_error() gives a thread-local message for the last failing call on this thread.
+ *   - device pointers are caller-owned and must stay valid until the enqueued work completes;
+ *     *_fwdbwd and bplx_score_grid are asynchronous: they enqueue on `stream` (a cudaStream_t
+ *     passed as void*; NULL = legacy default stream), never synchronise and never allocate.
+ *   - the *_host variants take HOST buffers, do the H2D/D2H copies themselves through pinned
+ *     staging owned by the handle and return after the results are in the host buffers.
+ *   - a bplx_problem is immutable after create and bound to the CUDA device that was current at
+ *     create time; calls may come from any host thread (one stream per concurrent caller).
+ *   - all floating point is IEEE binary32 (the reference runs JAX with x64 disabled); indices are
+ *     the reference's DTYPES (bpl/base.py:16-22): uint16 teams, uint8 goals / conferences / venue.
+ */
+#ifndef BPLX_H_
+#define BPLX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BPLX_VERSION 1
+
+typedef enum {
+  BPLX_OK = 0,
+  BPLX_E_INVALID = -1,     /* bad argument (null pointer, index out of range, ...) */
+  BPLX_E_UNSUPPORTED = -2, /* shape outside what the kernels were built for */
+  BPLX_E_CUDA = -3,        /* CUDA runtime error (message has the cudaError string) */
+  BPLX_E_NOMEM = -4,
+  BPLX_E_WORKSPACE = -5    /* workspace too small */
+} bplx_status;
+
+/* which bpl-next class the problem mirrors */
+typedef enum {
+  BPLX_DIXON_COLES = 0, /* bpl/dixon_coles.py:39-84          D = 5 + 2T            */
+  BPLX_EXTENDED = 1,    /* bpl/extended_dixon_coles.py:78-248 D = 7 + 2K + 3T       */
+  BPLX_NEUTRAL = 2,     /* bpl/neutral_dixon_coles.py:102-283 D = 13 + 2K + 6T      */
+  BPLX_NEUTRAL_WC = 3,  /* bpl/neutral_dixon_coles_WC.py:83-232 D = 13 + 2K + 6T + Cf */
+  BPLX_DYNAMIC = 4      /* bpl/dynamic_dixon_coles.py:63-247  D = 10G + 2 + 2K + 7GT */
+} bplx_model;
+
+/* memory layout of theta / grad */
+typedef enum {
+  BPLX_CHAIN_MAJOR = 0, /* theta[c * D + d]   -- what a vmapped jax.ffi call hands over ([C, D]) */
+  BPLX_CHAIN_MINOR = 1  /* theta[d * ld + c]  -- native, fully coalesced ([D, ld], ld >= C)      */
+} bplx_layout;
+
+#define BPLX_FLAG_DYNAMIC_AS_WRITTEN 1u /* reproduce dynamic_dixon_coles.py:192-218 literally */
+
+/*
+ * Static match data = the positional arguments of the reference `_model` after `fit`'s host prep
+ * (parse_teams, bpl/_util.py:115-135).  All arrays are HOST arrays of length num_matches unless
+ * stated; the library copies what it needs, the caller keeps ownership.
+ */
+typedef struct {
+  int32_t model;            /* bplx_model */
+  int32_t num_matches;      /* M */
+  int32_t num_teams;        /* T */
+  int32_t num_covariates;   /* K (0 = no team_covariates) */
+  int32_t num_conferences;  /* Cf (NEUTRAL_WC only, else 0) */
+  int32_t num_gameweeks;    /* G (DYNAMIC only, else 0) */
+  uint32_t flags;
+  const uint16_t* home_team;      /* [M] index into sorted team names */
+  const uint16_t* away_team;      /* [M] */
+  const uint8_t* home_goals;      /* [M] */
+  const uint8_t* away_goals;      /* [M] */
+  const uint8_t* neutral_venue;   /* [M] 1 = neutral; NULL = all 0 (required NULL-able for DC/EXT) */
+  const uint8_t* home_conf;       /* [M] NEUTRAL_WC, else NULL */
+  const uint8_t* away_conf;       /* [M] NEUTRAL_WC, else NULL */
+  const int32_t* gameweek;        /* [M] DYNAMIC (0-based, < G), else NULL */
+  const float* weights;           /* [M] match weights (time decay x game weights), NULL = unweighted
+                                     (the `to_event(1)` branch, extended_dixon_coles.py:216-227) */
+  const float* covariates;        /* [T*K] row-major STANDARDISED covariates
+                                     (extended_dixon_coles.py:124-127), NULL iff K == 0 */
+} bplx_problem_desc;
+
+typedef struct bplx_problem bplx_problem;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+int bplx_problem_create(const bplx_problem_desc* desc, bplx_problem** out);
+void bplx_problem_destroy(bplx_problem* p);
+
+/* number of unconstrained parameters D of the model (numpyro's flattened latent sites) */
+int bplx_num_params(const bplx_problem* p);
+
+/*
+ * Layout of the flat unconstrained vector, as "name:offset:count:transform;" records
+ * (transform in real|exp|sigmoid; names are numpyro's latent site names).  Pointer is owned by
+ * the handle.  Replaces numpyro's ravel of the latent-site dict for this path.
+ */
+const char* bplx_problem_layout(const bplx_problem* p);
+
+/* ---- log-density + gradient: replaces value_and_grad(potential_fn) per leapfrog ---------- */
+/* (numpyro potential_energy of `_model`; the returned lp is the log JOINT density, i.e. MINUS
+ * the potential energy, and grad is d lp / d theta.) */
+size_t bplx_logdensity_workspace_bytes(const bplx_problem* p, int num_chains);
+
+int bplx_logdensity_fwdbwd(const bplx_problem* p, int num_chains, int layout, int ld,
+                           const float* theta,   /* device, [C, D] or [D, ld] */
+                           float* lp,            /* device, [C] */
+                           float* grad,          /* device, same layout as theta */
+                           float* corr_coef,     /* device, [C] (deterministic site "corr_coef"), may be NULL */
+                           void* workspace, size_t workspace_bytes,
+                           void* stream);
+
+/* host-buffer variant (chain-major [C, D]); copies in/out inside the call, returns when done. */
+int bplx_logdensity_fwdbwd_host(bplx_problem* p, int num_chains,
+                                const float* theta, float* lp, float* grad, float* corr_coef);
+
+/* ---- posterior-predictive score grid: replaces predict_score_grid_proba/outcome_proba ---- */
+/*
+ * Posterior sample arrays are [S, T] row-major (the attributes `fit` stores,
+ * e.g. neutral_dixon_coles_WC.py:308-334), device pointers; unused ones NULL:
+ *   DIXON_COLES : attack, defence, home_advantage [S] (in `home_attack`), corr_coef
+ *   EXTENDED    : attack, defence, home_advantage [S,T] (in `home_attack`), corr_coef
+ *   NEUTRAL(_WC): attack, defence, home_attack, away_attack, home_defence, away_defence,
+ *                 (confederation_strength [S, Cf]), corr_coef
+ */
+typedef struct {
+  int32_t model;           /* bplx_model (DYNAMIC unsupported: reference predict is unusable) */
+  int32_t num_samples;     /* S (this rank's shard) */
+  int32_t num_teams;       /* T */
+  int32_t num_conferences; /* Cf */
+  const float* attack;
+  const float* defence;
+  const float* home_attack;
+  const float* away_attack;
+  const float* home_defence;
+  const float* away_defence;
+  const float* confederation_strength;
+  const float* corr_coef;  /* [S] */
+} bplx_samples;
+
+typedef struct {
+  int32_t num_fixtures;          /* F */
+  const uint16_t* home_team;     /* device [F] */
+  const uint16_t* away_team;     /* device [F] */
+  const uint8_t* home_conf;      /* device [F] or NULL */
+  const uint8_t* away_conf;      /* device [F] or NULL */
+  const uint8_t* neutral_venue;  /* device [F] or NULL */
+} bplx_fixtures;
+
+size_t bplx_score_grid_workspace_bytes(const bplx_samples* s, const bplx_fixtures* f, int max_goals);
+
+/*
+ * grid[f, hg, ag] = scale * sum_s tau * Pois(hg; lam_h) * Pois(ag; lam_a), 0 <= hg, ag <= max_goals.
+ * scale = 1/S for a single-rank call (the reference's mean over samples); a sample-sharded caller
+ * passes 1/S_total and all-reduces (sum) the grids.  outcome (optional, [F, 3] = home_win, draw,
+ * away_win) is summed from the SAME rank-local grid, so it is also additive across ranks.
+ */
+int bplx_score_grid(const bplx_samples* s, const bplx_fixtures* f, int max_goals, float scale,
+                    float* grid,     /* device [F, g, g], g = max_goals + 1 */
+                    float* outcome,  /* device [F, 3] or NULL */
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* host-buffer variant: every pointer in s / f / grid / outcome is a HOST pointer. */
+int bplx_score_grid_host(const bplx_samples* s, const bplx_fixtures* f, int max_goals, float scale,
+                         float* grid, float* outcome);
+
+/* ---- misc --------------------------------------------------------------------------------- */
+const char* bplx_last_error(void);
+int bplx_version(void);
+/* number of kernel launches this library has enqueued from this process (for bench accounting) */
+unsigned long long bplx_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BPLX_H_ */

@@ -1,0 +1,50 @@
+"""CPU: the static plan (product host code) evaluated in double == the oracle restatement."""
+import numpy as np
+import pytest
+
+from oracle import datasets, models as om
+from tests import helpers as H
+
+CASES = [
+    ("dixon_coles", dict()),
+    ("extended", dict(weighted=False)),
+    ("extended", dict(weighted=True, K=3)),
+    ("neutral", dict(K=2)),
+    ("neutral", dict(neutral_frac=0.0)),
+    ("neutral", dict(neutral_frac=1.0)),
+    ("neutral_wc", dict()),
+    ("neutral_wc", dict(multi_conf=True, K=2)),
+]
+
+
+@pytest.mark.parametrize("model,kw", CASES)
+@pytest.mark.parametrize("radius", [0.5, 2.0])
+def test_plan_matches_oracle(model, kw, radius):
+    arr = H.small_problem(model, seed=3, **kw)
+    d = H.to_oracle(arr)
+    D = om.num_params(model, arr.num_teams, arr.num_covariates, arr.num_conferences)
+    theta = H.random_theta(D, 6, seed=11, radius=radius)
+    lp_o, g_o, cc_o = om.log_density_and_grad(d, theta)
+    lp_p, g_p, cc_p = H.plancheck_eval(arr, theta)
+    # float32 weights/covariates are shared; everything else is double on both sides
+    np.testing.assert_allclose(lp_p, lp_o, rtol=1e-7)  # const_term, yexp are float32
+    np.testing.assert_allclose(cc_p, cc_o, rtol=1e-9, atol=1e-12)
+    scale = np.abs(g_o).max(axis=1, keepdims=True)
+    np.testing.assert_allclose(g_p / scale, g_o / scale, rtol=0, atol=2e-7)
+
+
+def test_plan_reference_fixtures():
+    for model, td, eps in [("dixon_coles", datasets.dummy_data(), None),
+                           ("extended", datasets.timed_dummy_data(), 1.0),
+                           ("neutral", datasets.neutral_dummy_data(), 0.5),
+                           ("neutral_wc", datasets.neutral_dummy_data(), 0.2)]:
+        arr = H.from_training_data(model, td, epsilon=eps)
+        d = H.to_oracle(arr)
+        D = om.num_params(model, arr.num_teams, arr.num_covariates, arr.num_conferences)
+        theta = H.random_theta(D, 3, seed=5, radius=1.0)
+        lp_o, g_o, cc_o = om.log_density_and_grad(d, theta)
+        lp_p, g_p, cc_p = H.plancheck_eval(arr, theta)
+        np.testing.assert_allclose(lp_p, lp_o, rtol=1e-7)
+        np.testing.assert_allclose(cc_p, cc_o, rtol=1e-9, atol=1e-12)
+        scale = np.abs(g_o).max(axis=1, keepdims=True)
+        np.testing.assert_allclose(g_p / scale, g_o / scale, rtol=0, atol=2e-7)
