@@ -1,0 +1,345 @@
+// api.cu -- the extern "C" surface declared in include/bplx.h.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <new>
+
+#include "common.cuh"
+#include "plan.h"
+#include "problem.h"
+#include "score_grid.h"
+
+namespace bplx {
+
+static thread_local char g_err[1024] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+void note_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+template <typename T>
+static int upload(bplx_problem* p, const std::vector<T>& h, const T** out) {
+  *out = nullptr;
+  if (h.empty()) return BPLX_OK;
+  void* d = nullptr;
+  BPLX_CUDA(cudaMalloc(&d, h.size() * sizeof(T)));
+  p->dev_allocs.push_back(d);
+  BPLX_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = static_cast<const T*>(d);
+  return BPLX_OK;
+}
+
+static size_t workspace_bytes(const KernelParams& kp, int C) {
+  if (kp.Cf <= 0) return 0;
+  const size_t Cpad = ((size_t)C + 31) / 32 * 32;
+  return (size_t)kp.V * Cpad * sizeof(float);
+}
+
+static int enqueue(const bplx_problem* p, int C, int layout, int ld, const float* theta, float* lp, float* grad,
+                   float* corr_coef, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  BPLX_REQUIRE(p != nullptr, BPLX_E_INVALID, "problem is NULL");
+  BPLX_REQUIRE(C > 0, BPLX_E_INVALID, "num_chains must be positive (got %d)", C);
+  BPLX_REQUIRE(theta && lp && grad, BPLX_E_INVALID, "theta, lp and grad must not be NULL");
+  KernelParams kp = p->kp;
+  if (layout == BPLX_CHAIN_MAJOR) {
+    kp.sd = 1;
+    kp.sc = ld > 0 ? ld : kp.D;
+    BPLX_REQUIRE(kp.sc >= kp.D, BPLX_E_INVALID, "chain-major ld (%d) < D (%d)", ld, kp.D);
+  } else if (layout == BPLX_CHAIN_MINOR) {
+    kp.sc = 1;
+    kp.sd = ld > 0 ? ld : C;
+    BPLX_REQUIRE(kp.sd >= C, BPLX_E_INVALID, "chain-minor ld (%d) < num_chains (%d)", ld, C);
+  } else {
+    BPLX_REQUIRE(false, BPLX_E_INVALID, "unknown layout %d", layout);
+  }
+  const size_t need = workspace_bytes(kp, C);
+  BPLX_REQUIRE(ws_bytes >= need && (need == 0 || ws != nullptr), BPLX_E_WORKSPACE,
+               "workspace too small: %zu bytes given, %zu needed", ws_bytes, need);
+  kp.C = C;
+  kp.Cpad = (C + 31) / 32 * 32;
+  kp.theta = theta;
+  kp.lp = lp;
+  kp.grad = grad;
+  kp.corr_coef = corr_coef;
+  kp.scratch = static_cast<float*>(ws);
+  return launch_logdensity(kp, stream);
+}
+
+}  // namespace bplx
+
+using namespace bplx;
+
+extern "C" {
+
+int bplx_problem_create(const bplx_problem_desc* desc, bplx_problem** out) {
+  BPLX_REQUIRE(desc && out, BPLX_E_INVALID, "desc / out is NULL");
+  *out = nullptr;
+  HostPlan hp;
+  std::string err;
+  int rc = build_plan(*desc, &hp, &err);
+  if (rc != BPLX_OK) {
+    set_error("%s", err.c_str());
+    return rc;
+  }
+  bplx_problem* p = new (std::nothrow) bplx_problem();
+  BPLX_REQUIRE(p, BPLX_E_NOMEM, "out of host memory");
+  auto fail = [&](int code) {
+    bplx_problem_destroy(p);
+    return code;
+  };
+  if (cudaGetDevice(&p->device) != cudaSuccess) {
+    set_error("cudaGetDevice failed: no usable CUDA device (bplx has no CPU fallback)");
+    return fail(BPLX_E_CUDA);
+  }
+  p->kp = hp.kp;
+  p->layout = hp.layout;
+  KernelParams& kp = p->kp;
+  const List *l1 = nullptr, *l2 = nullptr;
+  const Entry *e1 = nullptr, *e2 = nullptr;
+  const EntryClip* e1c = nullptr;
+#define UP(vec, ptr)                                 \
+  if ((rc = upload(p, hp.vec, &(ptr))) != BPLX_OK) return fail(rc)
+  UP(lists1, l1);
+  UP(lists2, l2);
+  UP(ent1, e1);
+  UP(ent1c, e1c);
+  UP(ent2, e2);
+  UP(warp_l1, kp.warp_l1);
+  UP(warp_l2, kp.warp_l2);
+  UP(team_vptr, kp.team_vptr);
+  UP(v_team, kp.v_team);
+  UP(v_conf, kp.v_conf);
+  UP(conf_vptr, kp.conf_vptr);
+  UP(conf_vlist, kp.conf_vlist);
+  UP(yexp, kp.yexp);
+  UP(Xs, kp.Xs);
+#undef UP
+  kp.lists1 = l1;
+  kp.lists2 = l2;
+  kp.ent1 = kp.clip ? static_cast<const void*>(e1c) : static_cast<const void*>(e1);
+  kp.ent2 = e2;
+  if ((rc = logdensity_set_attributes(kp)) != BPLX_OK) return fail(rc);
+  p->stats[0] = desc->num_matches;
+  p->stats[1] = hp.n1;
+  p->stats[2] = hp.n1_padded;
+  p->stats[3] = hp.n2;
+  p->stats[4] = hp.n2_padded;
+  p->stats[5] = kp.smem_total;
+  p->stats[6] = kp.nwarps;
+  p->stats[7] = kp.V;
+  *out = p;
+  return BPLX_OK;
+}
+
+void bplx_problem_destroy(bplx_problem* p) {
+  if (!p) return;
+  for (void* d : p->dev_allocs) cudaFree(d);
+  if (p->d_theta) cudaFree(p->d_theta);
+  if (p->d_out) cudaFree(p->d_out);
+  if (p->d_ws) cudaFree(p->d_ws);
+  if (p->host_stream) cudaStreamDestroy(p->host_stream);
+  delete p;
+}
+
+int bplx_num_params(const bplx_problem* p) { return p ? p->kp.D : BPLX_E_INVALID; }
+
+const char* bplx_problem_layout(const bplx_problem* p) { return p ? p->layout.c_str() : ""; }
+
+int bplx_problem_stats(const bplx_problem* p, long long* out, int n) {
+  BPLX_REQUIRE(p && out, BPLX_E_INVALID, "problem / out is NULL");
+  for (int i = 0; i < n && i < 8; i++) out[i] = p->stats[i];
+  return n < 8 ? n : 8;
+}
+
+size_t bplx_logdensity_workspace_bytes(const bplx_problem* p, int num_chains) {
+  if (!p || num_chains <= 0) return 0;
+  return workspace_bytes(p->kp, num_chains);
+}
+
+int bplx_logdensity_fwdbwd(const bplx_problem* p, int num_chains, int layout, int ld, const float* theta, float* lp,
+                           float* grad, float* corr_coef, void* workspace, size_t workspace_bytes, void* stream) {
+  return enqueue(p, num_chains, layout, ld, theta, lp, grad, corr_coef, workspace, workspace_bytes,
+                 static_cast<cudaStream_t>(stream));
+}
+
+int bplx_logdensity_fwdbwd_host(bplx_problem* p, int C, const float* theta, float* lp, float* grad, float* corr_coef) {
+  BPLX_REQUIRE(p != nullptr, BPLX_E_INVALID, "problem is NULL");
+  BPLX_REQUIRE(C > 0, BPLX_E_INVALID, "num_chains must be positive (got %d)", C);
+  BPLX_REQUIRE(theta && lp && grad, BPLX_E_INVALID, "theta, lp and grad must not be NULL");
+  std::lock_guard<std::mutex> lock(p->mu);
+  BPLX_CUDA(cudaSetDevice(p->device));
+  const size_t D = (size_t)p->kp.D;
+  if (!p->host_stream) BPLX_CUDA(cudaStreamCreateWithFlags(&p->host_stream, cudaStreamNonBlocking));
+  if (C > p->host_cap) {
+    if (p->d_theta) cudaFree(p->d_theta);
+    if (p->d_out) cudaFree(p->d_out);
+    if (p->d_ws) cudaFree(p->d_ws);
+    p->d_theta = p->d_out = nullptr;
+    p->d_ws = nullptr;
+    p->host_cap = 0;
+    BPLX_CUDA(cudaMalloc(&p->d_theta, (size_t)C * D * sizeof(float)));
+    BPLX_CUDA(cudaMalloc(&p->d_out, ((size_t)C * D + 2 * (size_t)C) * sizeof(float)));
+    p->d_ws_bytes = workspace_bytes(p->kp, C);
+    if (p->d_ws_bytes) BPLX_CUDA(cudaMalloc(&p->d_ws, p->d_ws_bytes));
+    p->host_cap = C;
+  }
+  cudaStream_t s = p->host_stream;
+  float* d_grad = p->d_out;
+  float* d_lp = p->d_out + (size_t)C * D;
+  float* d_cc = d_lp + C;
+  BPLX_CUDA(cudaMemcpyAsync(p->d_theta, theta, (size_t)C * D * sizeof(float), cudaMemcpyHostToDevice, s));
+  int rc = enqueue(p, C, BPLX_CHAIN_MAJOR, (int)D, p->d_theta, d_lp, d_grad, d_cc, p->d_ws, p->d_ws_bytes, s);
+  if (rc != BPLX_OK) return rc;
+  BPLX_CUDA(cudaMemcpyAsync(grad, d_grad, (size_t)C * D * sizeof(float), cudaMemcpyDeviceToHost, s));
+  BPLX_CUDA(cudaMemcpyAsync(lp, d_lp, (size_t)C * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (corr_coef) BPLX_CUDA(cudaMemcpyAsync(corr_coef, d_cc, (size_t)C * sizeof(float), cudaMemcpyDeviceToHost, s));
+  BPLX_CUDA(cudaStreamSynchronize(s));
+  return BPLX_OK;
+}
+
+// ---- score grid ------------------------------------------------------------------------------------------
+static int check_grid_args(const bplx_samples* s, const bplx_fixtures* f, int max_goals) {
+  BPLX_REQUIRE(s && f, BPLX_E_INVALID, "samples / fixtures is NULL");
+  BPLX_REQUIRE(s->model >= BPLX_DIXON_COLES && s->model <= BPLX_NEUTRAL_WC, BPLX_E_UNSUPPORTED,
+               "score grid: model %d unsupported (DYNAMIC predict is unusable in the reference)", s->model);
+  BPLX_REQUIRE(s->num_samples > 0 && s->num_teams > 0 && f->num_fixtures > 0, BPLX_E_INVALID,
+               "score grid: num_samples, num_teams and num_fixtures must be positive");
+  BPLX_REQUIRE(max_goals >= 1 && max_goals <= 63, BPLX_E_INVALID, "max_goals must be in [1, 63] (got %d)", max_goals);
+  BPLX_REQUIRE(s->attack && s->defence && s->corr_coef && f->home_team && f->away_team, BPLX_E_INVALID,
+               "score grid: attack, defence, corr_coef, home_team, away_team must not be NULL");
+  if (s->model != BPLX_DIXON_COLES || true)
+    BPLX_REQUIRE(s->home_attack, BPLX_E_INVALID, "score grid: home_attack (home advantage) must not be NULL");
+  if (s->model == BPLX_NEUTRAL || s->model == BPLX_NEUTRAL_WC)
+    BPLX_REQUIRE(s->away_attack && s->home_defence && s->away_defence, BPLX_E_INVALID,
+                 "score grid: neutral models need away_attack, home_defence, away_defence");
+  if (s->model == BPLX_NEUTRAL_WC)
+    BPLX_REQUIRE(s->confederation_strength && s->num_conferences > 0 && f->home_conf && f->away_conf, BPLX_E_INVALID,
+                 "score grid: NEUTRAL_WC needs confederation_strength, home_conf, away_conf");
+  return BPLX_OK;
+}
+
+size_t bplx_score_grid_workspace_bytes(const bplx_samples* s, const bplx_fixtures* f, int max_goals) {
+  if (!s || !f || max_goals < 1) return 0;
+  return score_grid_workspace(s->num_samples, f->num_fixtures, max_goals + 1, nullptr, nullptr);
+}
+
+int bplx_score_grid(const bplx_samples* s, const bplx_fixtures* f, int max_goals, float scale, float* grid,
+                    float* outcome, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_grid_args(s, f, max_goals);
+  if (rc != BPLX_OK) return rc;
+  BPLX_REQUIRE(grid != nullptr, BPLX_E_INVALID, "grid is NULL");
+  GridParams gp{};
+  gp.model = s->model;
+  gp.S = s->num_samples;
+  gp.T = s->num_teams;
+  gp.Cf = s->model == BPLX_NEUTRAL_WC ? s->num_conferences : 0;
+  gp.F = f->num_fixtures;
+  gp.g = max_goals + 1;
+  gp.scale = scale;
+  const size_t need = score_grid_workspace(gp.S, gp.F, gp.g, &gp.nsplit, &gp.samples_per_split);
+  BPLX_REQUIRE(workspace && workspace_bytes >= need, BPLX_E_WORKSPACE,
+               "workspace too small: %zu bytes given, %zu needed", workspace_bytes, need);
+  gp.attack = s->attack;
+  gp.defence = s->defence;
+  gp.ha = s->home_attack;
+  gp.aa = s->away_attack;
+  gp.hd = s->home_defence;
+  gp.ad = s->away_defence;
+  gp.conf = s->confederation_strength;
+  gp.corr = s->corr_coef;
+  gp.home = f->home_team;
+  gp.away = f->away_team;
+  gp.hconf = f->home_conf;
+  gp.aconf = f->away_conf;
+  gp.nv = f->neutral_venue;
+  gp.partial = static_cast<float*>(workspace);
+  gp.grid = grid;
+  gp.outcome = outcome;
+  return launch_score_grid(gp, static_cast<cudaStream_t>(stream));
+}
+
+int bplx_score_grid_host(const bplx_samples* s, const bplx_fixtures* f, int max_goals, float scale, float* grid,
+                         float* outcome) {
+  int rc = check_grid_args(s, f, max_goals);
+  if (rc != BPLX_OK) return rc;
+  BPLX_REQUIRE(grid != nullptr, BPLX_E_INVALID, "grid is NULL");
+  const size_t S = s->num_samples, T = s->num_teams, F = f->num_fixtures, g = max_goals + 1;
+  const size_t Cf = s->model == BPLX_NEUTRAL_WC ? s->num_conferences : 0;
+  std::vector<void*> allocs;
+  auto cleanup = [&]() {
+    for (void* d : allocs) cudaFree(d);
+  };
+  cudaStream_t st = nullptr;
+  if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
+    set_error("cudaStreamCreate failed: no usable CUDA device (bplx has no CPU fallback)");
+    return BPLX_E_CUDA;
+  }
+  rc = BPLX_OK;
+  auto up = [&](const void* h, size_t bytes) -> void* {
+    if (!h || rc != BPLX_OK) return nullptr;
+    void* d = nullptr;
+    if (cudaMalloc(&d, bytes) != cudaSuccess ||
+        cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+      set_error("score_grid_host: device allocation / copy of %zu bytes failed", bytes);
+      rc = BPLX_E_CUDA;
+      return nullptr;
+    }
+    allocs.push_back(d);
+    return d;
+  };
+  bplx_samples ds = *s;
+  bplx_fixtures df = *f;
+  const size_t ha_w = s->model == BPLX_DIXON_COLES ? 1 : T;
+  ds.attack = (const float*)up(s->attack, S * T * 4);
+  ds.defence = (const float*)up(s->defence, S * T * 4);
+  ds.home_attack = (const float*)up(s->home_attack, S * ha_w * 4);
+  const bool neu = s->model == BPLX_NEUTRAL || s->model == BPLX_NEUTRAL_WC;
+  ds.away_attack = neu ? (const float*)up(s->away_attack, S * T * 4) : nullptr;
+  ds.home_defence = neu ? (const float*)up(s->home_defence, S * T * 4) : nullptr;
+  ds.away_defence = neu ? (const float*)up(s->away_defence, S * T * 4) : nullptr;
+  ds.confederation_strength = Cf ? (const float*)up(s->confederation_strength, S * Cf * 4) : nullptr;
+  ds.corr_coef = (const float*)up(s->corr_coef, S * 4);
+  df.home_team = (const uint16_t*)up(f->home_team, F * 2);
+  df.away_team = (const uint16_t*)up(f->away_team, F * 2);
+  df.home_conf = Cf ? (const uint8_t*)up(f->home_conf, F) : nullptr;
+  df.away_conf = Cf ? (const uint8_t*)up(f->away_conf, F) : nullptr;
+  df.neutral_venue = (neu && f->neutral_venue) ? (const uint8_t*)up(f->neutral_venue, F) : nullptr;
+  const size_t ws_bytes = score_grid_workspace((int)S, (int)F, (int)g, nullptr, nullptr);
+  void *d_ws = nullptr, *d_grid = nullptr, *d_out = nullptr;
+  if (rc == BPLX_OK) {
+    if (cudaMalloc(&d_ws, ws_bytes) == cudaSuccess) allocs.push_back(d_ws); else rc = BPLX_E_NOMEM;
+    if (cudaMalloc(&d_grid, F * g * g * 4) == cudaSuccess) allocs.push_back(d_grid); else rc = BPLX_E_NOMEM;
+    if (outcome) {
+      if (cudaMalloc(&d_out, F * 3 * 4) == cudaSuccess) allocs.push_back(d_out); else rc = BPLX_E_NOMEM;
+    }
+    if (rc != BPLX_OK) set_error("score_grid_host: out of device memory");
+  }
+  if (rc == BPLX_OK)
+    rc = bplx_score_grid(&ds, &df, max_goals, scale, (float*)d_grid, (float*)d_out, d_ws, ws_bytes, st);
+  if (rc == BPLX_OK) {
+    cudaError_t e = cudaMemcpyAsync(grid, d_grid, F * g * g * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && outcome) e = cudaMemcpyAsync(outcome, d_out, F * 3 * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+      set_error("score_grid_host: %s", cudaGetErrorString(e));
+      rc = BPLX_E_CUDA;
+    }
+  } else {
+    cudaStreamSynchronize(st);
+  }
+  cleanup();
+  cudaStreamDestroy(st);
+  return rc;
+}
+
+const char* bplx_last_error(void) { return g_err; }
+int bplx_version(void) { return BPLX_VERSION; }
+unsigned long long bplx_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+}  // extern "C"

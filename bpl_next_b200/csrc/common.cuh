@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+
 #include <string>
 
 #include "../../include/bplx.h"
@@ -13,21 +14,21 @@ namespace bplx {
 void set_error(const char* fmt, ...);
 void note_launch(int n = 1);  // kernels enqueued by this library (bplx_launch_count)
 
-#define BPLX_CUDA(call)                                                                 \
-  do {                                                                                  \
-    cudaError_t e__ = (call);                                                           \
-    if (e__ != cudaSuccess) {                                                           \
+#define BPLX_CUDA(call)                                                                        \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
       ::bplx::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
-      return BPLX_E_CUDA;                                                               \
-    }                                                                                   \
+      return BPLX_E_CUDA;                                                                      \
+    }                                                                                          \
   } while (0)
 
-#define BPLX_REQUIRE(cond, code, ...)      \
-  do {                                     \
-    if (!(cond)) {                         \
-      ::bplx::set_error(__VA_ARGS__);      \
-      return (code);                       \
-    }                                      \
+#define BPLX_REQUIRE(cond, code, ...) \
+  do {                                \
+    if (!(cond)) {                    \
+      ::bplx::set_error(__VA_ARGS__); \
+      return (code);                  \
+    }                                 \
   } while (0)
 
 // ---- device helpers -----------------------------------------------------------------------
@@ -35,10 +36,23 @@ void note_launch(int n = 1);  // kernels enqueued by this library (bplx_launch_c
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+__device__ __forceinline__ float2 lds64(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, float x, float y) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 
 // mbarrier (shared::cta) -------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 __device__ __forceinline__ void fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -46,11 +60,10 @@ __device__ __forceinline__ void fence_mbar_init() {
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -59,22 +72,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "@p bra DONE_%=;\n"
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
+      "}\n" ::"r"(bar),
       "r"(parity)
       : "memory");
 }
 // TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
 // dst/src 16-byte aligned, bytes a multiple of 16.
-__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
+__device__ __forceinline__ void tma_load_1d(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+               "l"(gmem_src), "r"(bytes), "r"(bar)
+               : "memory");
 }
-
-__device__ __forceinline__ float ld_cg(const float* p) { return __ldcg(p); }
-__device__ __forceinline__ void st_cg(float* p, float v) { __stcg(p, v); }
 #endif  // __CUDACC__
 
 }  // namespace bplx

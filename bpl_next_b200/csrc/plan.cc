@@ -275,28 +275,39 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err) {
   for (auto& v : raw2) merge(v);
 
   // ---- assign virtual teams to warps (longest processing time first) ---------------------------
+  // All virtual teams of a team go to the same warp: the owner thread of (team, chain) is the only
+  // one that read-modify-writes that team's gradient entries inside a phase.
   auto assign = [&](const std::vector<std::vector<RawEntry>>& raw, double per_entry, double per_vteam,
                     std::vector<std::vector<int>>* by_warp) {
-    std::vector<double> cost(V, 0.0);
+    std::vector<double> cost(T, 0.0);
     for (int v = 0; v < V; v++) {
       size_t n = 0;
       for (int k = 0; k < 4; k++) n += raw[(size_t)v * 4 + k].size();
-      cost[v] = n ? per_vteam + per_entry * (double)n : 0.0;
+      if (n) cost[P.v_team[v]] += per_vteam + per_entry * (double)n;
     }
-    std::vector<int> order(V);
+    std::vector<int> order(T);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
     std::vector<double> load(W, 0.0);
-    by_warp->assign(W, {});
-    for (int v : order) {
-      if (cost[v] == 0.0) continue;
+    std::vector<std::vector<int>> teams(W);
+    for (int t : order) {
+      if (cost[t] == 0.0) continue;
       int best = 0;
       for (int w = 1; w < W; w++)
         if (load[w] < load[best]) best = w;
-      load[best] += cost[v];
-      (*by_warp)[best].push_back(v);
+      load[best] += cost[t];
+      teams[best].push_back(t);
     }
-    for (auto& l : *by_warp) std::sort(l.begin(), l.end());
+    by_warp->assign(W, {});
+    for (int w = 0; w < W; w++) {
+      std::sort(teams[w].begin(), teams[w].end());
+      for (int t : teams[w])
+        for (int v = P.team_vptr[t]; v < P.team_vptr[t + 1]; v++) {
+          size_t n = 0;
+          for (int k = 0; k < 4; k++) n += raw[(size_t)v * 4 + k].size();
+          if (n) (*by_warp)[w].push_back(v);
+        }
+    }
   };
   std::vector<std::vector<int>> w1, w2;
   assign(raw1, 1.0, 16.0, &w1);

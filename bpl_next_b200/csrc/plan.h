@@ -43,7 +43,7 @@ constexpr int kChains = 32;       // chains per CTA: one lane per chain
 constexpr int kRowBytes = 256;    // one table row: float2 x 32 lanes
 constexpr int kListMax = 128;     // entries per list piece (bounds the arg-max rescan)
 constexpr int kMaxCov = 8;        // covariates supported by the kernel
-constexpr int kMaxWarps = 20;
+constexpr int kMaxWarps = 16;
 constexpr int kRedRows = 8;       // per-warp rows in the reduction area
 
 enum Kind : uint8_t { kH1 = 0, kA1 = 1, kH0 = 2, kA0 = 3 };

@@ -11,8 +11,6 @@ struct bplx_problem {
   int device = 0;
   bplx::KernelParams kp{};  // static part filled at create; call arguments filled per launch
   std::string layout;
-  size_t smem_bytes = 0;
-  int nthreads = 0;
   std::vector<void*> dev_allocs;
   // host-variant staging (lazily grown, guarded by mu)
   std::mutex mu;
@@ -23,10 +21,10 @@ struct bplx_problem {
   size_t d_ws_bytes = 0;
   cudaStream_t host_stream = nullptr;
   // plan statistics (for DESIGN/bench reporting)
-  long long p1_entries = 0, p2_entries = 0, p1_padded = 0, p2_padded = 0;
+  long long stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 namespace bplx {
-int launch_logdensity(const bplx_problem* p, const KernelParams& kp, cudaStream_t stream);
-int logdensity_set_attributes(const bplx_problem* p);
+int launch_logdensity(const KernelParams& kp, cudaStream_t stream);
+int logdensity_set_attributes(const KernelParams& kp);
 }  // namespace bplx

@@ -101,6 +101,13 @@ int bplx_num_params(const bplx_problem* p);
  */
 const char* bplx_problem_layout(const bplx_problem* p);
 
+/*
+ * Plan statistics for benchmarks / DESIGN.md: out[0..7] = matches, phase-1 entries, padded phase-1
+ * entries, phase-2 (tau) entries, padded phase-2 entries, shared-memory bytes per CTA, warps per
+ * CTA, (team, confederation) pairs.  Returns the number of values written.
+ */
+int bplx_problem_stats(const bplx_problem* p, long long* out, int n);
+
 /* ---- log-density + gradient: replaces value_and_grad(potential_fn) per leapfrog ---------- */
 /* (numpyro potential_energy of `_model`; the returned lp is the log JOINT density, i.e. MINUS
  * the potential energy, and grad is d lp / d theta.) */

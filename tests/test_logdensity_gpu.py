@@ -1,0 +1,113 @@
+"""GPU parity: K1 (C ABI) vs the float64 oracle restatement of the reference models.
+
+Tolerances are BASELINE.json's: log-density 1e-5 relative, gradient 1e-4 relative (float32)."""
+import numpy as np
+import pytest
+
+from oracle import datasets, models as om
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+LP_RTOL = 1e-5
+GRAD_RTOL = 1e-4
+
+
+def _check(arr, theta64, lp, grad, cc):
+    d = H.to_oracle(arr)
+    lp_o, g_o, cc_o = om.log_density_and_grad(d, theta64)
+    np.testing.assert_allclose(lp, lp_o, rtol=LP_RTOL)
+    np.testing.assert_allclose(cc, cc_o, rtol=1e-4, atol=1e-6)
+    scale = np.abs(g_o).max(axis=1, keepdims=True)
+    err = np.abs(grad - g_o) / scale
+    assert err.max() < GRAD_RTOL, f"max scaled gradient error {err.max():.3e} at {np.unravel_index(err.argmax(), err.shape)}"
+
+
+CASES = [
+    ("dixon_coles", dict()),
+    ("extended", dict(weighted=False)),
+    ("extended", dict(weighted=True, K=3)),
+    ("neutral", dict(K=2)),
+    ("neutral", dict(neutral_frac=0.0)),
+    ("neutral", dict(neutral_frac=1.0)),
+    ("neutral_wc", dict()),
+    ("neutral_wc", dict(multi_conf=True, K=2, T=13, M=400)),
+]
+
+
+@pytest.mark.parametrize("model,kw", CASES)
+@pytest.mark.parametrize("radius", [0.5, 2.0])
+@pytest.mark.parametrize("chain_minor", [False, True])
+def test_small_problems(model, kw, radius, chain_minor):
+    import torch
+    from bpl_next_b200 import Problem
+
+    arr = H.small_problem(model, seed=3, **kw)
+    p = Problem(arr)
+    C = 45  # not a multiple of 32: exercises the ragged last CTA
+    theta = H.random_theta(p.D, C, seed=11, radius=radius, dtype=np.float32)
+    t = torch.from_numpy(theta).cuda()
+    if chain_minor:
+        t = t.t().contiguous()
+    lp, grad, cc = p.logdensity(t, chain_minor=chain_minor)
+    torch.cuda.synchronize()
+    g = grad.t().contiguous() if chain_minor else grad
+    _check(arr, theta.astype(np.float64), lp.cpu().numpy(), g.cpu().numpy(), cc.cpu().numpy())
+
+
+@pytest.mark.parametrize("model,eps", [("dixon_coles", None), ("extended", None), ("extended", 1.0),
+                                       ("neutral", 0.5), ("neutral_wc", 0.2)])
+def test_reference_fixtures_host_path(model, eps):
+    """The reference's own test data (tests/conftest.py) through the host-buffer entry point."""
+    from bpl_next_b200 import Problem
+
+    td = {"dixon_coles": datasets.dummy_data, "extended": datasets.timed_dummy_data,
+          "neutral": datasets.neutral_dummy_data, "neutral_wc": datasets.neutral_dummy_data}[model]()
+    arr = H.from_training_data(model, td, epsilon=eps)
+    p = Problem(arr)
+    theta = H.random_theta(p.D, 64, seed=5, radius=1.0, dtype=np.float32)
+    lp, grad, cc = p.logdensity_host(theta)
+    _check(arr, theta.astype(np.float64), lp, grad, cc)
+
+
+def test_survey_anchor():
+    """SURVEY.md Appendix E anchor: theta_i = 0.3 sin(1+i) on conftest.dummy_data."""
+    from bpl_next_b200 import Problem
+
+    arr = H.from_training_data("dixon_coles", datasets.dummy_data())
+    p = Problem(arr)
+    theta = (0.3 * np.sin(1.0 + np.arange(45)))[None, :].astype(np.float32)
+    lp, grad, cc = p.logdensity_host(theta)
+    assert abs(lp[0] - (-1689.4267185765793)) < 1e-5 * 1689.5
+    assert abs(cc[0] - 0.1544682575346078) < 1e-5
+    assert abs(np.linalg.norm(grad[0]) - 883.2262464523642) < 1e-4 * 883.3
+
+
+@pytest.mark.parametrize("cfg", ["config_2", "config_3"])
+def test_baseline_configs(cfg):
+    """BASELINE.json configs at full match count, a handful of chains against the oracle."""
+    import torch
+    from bpl_next_b200 import Problem
+
+    if cfg == "config_2":
+        arr = H.from_training_data("extended", datasets.config_2(), epsilon=0.01)
+    else:
+        arr = H.from_training_data("neutral_wc", datasets.config_3(), epsilon=0.1)
+    p = Problem(arr)
+    C = 40
+    for radius in (0.3, 2.0):
+        theta = H.random_theta(p.D, C, seed=21, radius=radius, dtype=np.float32)
+        lp, grad, cc = p.logdensity(torch.from_numpy(theta).cuda())
+        torch.cuda.synchronize()
+        _check(arr, theta.astype(np.float64), lp.cpu().numpy(), grad.cpu().numpy(), cc.cpu().numpy())
+
+
+def test_errors():
+    from bpl_next_b200 import Problem, _abi
+
+    arr = H.small_problem("dixon_coles")
+    arr.home_team = arr.home_team.copy()
+    arr.home_team[0] = 999
+    with pytest.raises(_abi.BplxError) as e:
+        Problem(arr)
+    assert e.value.status == _abi.E_INVALID
