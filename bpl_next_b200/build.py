@@ -36,5 +36,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return OUT
 
 
+BENCH_SRC = os.path.join(HERE, "..", "bench_kernels", "fp32_peak.cu")
+BENCH_OUT = os.path.join(HERE, "lib", "libbplx_bench.so")
+
+
+def build_bench(force: bool = False) -> str:
+    """Measurement helper for bench.py (FFMA / shared-memory peaks); not part of the product."""
+    if not force and os.path.exists(BENCH_OUT) and os.path.getmtime(BENCH_OUT) >= os.path.getmtime(BENCH_SRC):
+        return BENCH_OUT
+    os.makedirs(os.path.dirname(BENCH_OUT), exist_ok=True)
+    nvcc = os.environ.get("NVCC", "nvcc")
+    r = subprocess.run([nvcc] + NVCC_FLAGS + ["-o", BENCH_OUT, BENCH_SRC], capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed building libbplx_bench.so")
+    return BENCH_OUT
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_bench(force="--force" in sys.argv))

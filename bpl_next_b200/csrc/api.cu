@@ -112,6 +112,8 @@ int bplx_problem_create(const bplx_problem_desc* desc, bplx_problem** out) {
   UP(ent2, e2);
   UP(warp_l1, kp.warp_l1);
   UP(warp_l2, kp.warp_l2);
+  UP(warp_e1, kp.warp_e1);
+  UP(warp_e2, kp.warp_e2);
   UP(team_vptr, kp.team_vptr);
   UP(v_team, kp.v_team);
   UP(v_conf, kp.v_conf);

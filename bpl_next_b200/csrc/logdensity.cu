@@ -134,6 +134,82 @@ __device__ __forceinline__ List load_list(const List* p) {
   return L;
 }
 
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Per-warp TMA ring over a contiguous global byte stream (the warp's entries of one phase).
+// One elected lane issues cp.async.bulk copies of kStageBytes into the warp's private ring and
+// every lane waits on the stage's mbarrier before reading it; the same warp produces and
+// consumes, so a __syncwarp() is all that is needed before a slot is refilled.
+struct Stream {
+  uint32_t ring, bar;        // shared addresses: kStages * kStageBytes ring, kStages mbarriers
+  const unsigned char* src;  // current stream
+  uint32_t total, pos;       // bytes in / consumed from the current stream
+  uint32_t gs0, gs_next;     // ring-stage counter at the start of / after the current stream
+  int lane;
+
+  __device__ __forceinline__ void init(uint32_t ring_, uint32_t bar_, int lane_) {
+    ring = ring_; bar = bar_; lane = lane_;
+    total = pos = gs0 = gs_next = 0;
+    src = nullptr;
+    if (lane == 0) {
+#pragma unroll
+      for (int s = 0; s < kStages; s++) mbar_init(bar + 8 * s, 1);
+      fence_mbar_init();
+      fence_proxy_async();
+    }
+    __syncwarp();
+  }
+  __device__ __forceinline__ void issue(uint32_t k) {  // stage k of the current stream
+    const uint32_t b0 = k * kStageBytes;
+    if (lane == 0 && b0 < total) {
+      const uint32_t bytes = min((uint32_t)kStageBytes, total - b0);
+      const uint32_t slot = (gs0 + k) % kStages;
+      mbar_arrive_expect_tx(bar + 8 * slot, bytes);
+      tma_load_1d(ring + slot * kStageBytes, src + b0, bytes, bar + 8 * slot);
+    }
+  }
+  __device__ __forceinline__ void begin(const void* src_, uint32_t total_bytes) {
+    __syncwarp();  // every lane is done with the previous stream's stages
+    src = static_cast<const unsigned char*>(src_);
+    total = total_bytes;
+    pos = 0;
+    gs0 = gs_next;
+    gs_next = gs0 + (total_bytes + kStageBytes - 1) / kStageBytes;
+#pragma unroll
+    for (int s = 0; s < kStages; s++) issue(s);
+  }
+  // body(shared address of a 16-byte unit), for nbytes (multiple of 16) of the stream
+  template <typename F>
+  __device__ __forceinline__ void consume(uint32_t nbytes, F&& body) {
+    while (nbytes) {
+      const uint32_t in_stage = pos & (kStageBytes - 1);
+      const uint32_t k = pos / kStageBytes;
+      const uint32_t idx = gs0 + k;
+      const uint32_t slot = idx % kStages;
+      if (in_stage == 0) mbar_wait(bar + 8 * slot, (idx / kStages) & 1);
+      const uint32_t chunk = min(nbytes, (uint32_t)kStageBytes - in_stage);
+      const uint32_t a0 = ring + slot * kStageBytes + in_stage;
+#pragma unroll 4
+      for (uint32_t o = 0; o < chunk; o += 16) body(a0 + o);
+      pos += chunk;
+      nbytes -= chunk;
+      if ((pos & (kStageBytes - 1)) == 0) {
+        __syncwarp();
+        issue(k + kStages);
+      }
+    }
+  }
+};
+
 }  // namespace
 
 template <bool CLIP, int KMAX>
@@ -151,6 +227,14 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
   ln.active = chain_raw < kp.C;
   const uint32_t tab = smem_u32(smem) + lane * 8;  // + row byte offset
   float* red = reinterpret_cast<float*>(smem + kp.smem_red);
+  Stream stream;
+  stream.init(smem_u32(smem) + kp.smem_ring + warp * (kStages * kStageBytes),
+              smem_u32(smem) + kp.smem_bar + warp * (kStages * 8), lane);
+  {  // phase-1 entries start streaming in while the prologue runs
+    const int e0 = __ldg(kp.warp_e1 + warp), e1 = __ldg(kp.warp_e1 + warp + 1);
+    const uint32_t esz = CLIP ? (uint32_t)sizeof(EntryClip) : (uint32_t)sizeof(Entry);
+    stream.begin(static_cast<const unsigned char*>(kp.ent1) + (size_t)e0 * esz, (uint32_t)(e1 - e0) * esz);
+  }
 
   const bool dc = kp.model == BPLX_DIXON_COLES, ext = kp.model == BPLX_EXTENDED;
   const bool has_rho = !dc;
@@ -272,8 +356,10 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
     float g[6];
     const float zero4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     const int l0 = __ldg(kp.warp_l1 + warp), l1 = __ldg(kp.warp_l1 + warp + 1);
+    List Lnext = l0 < l1 ? load_list(kp.lists1 + l0) : List{};
     for (int li = l0; li < l1; li++) {
-      const List L = load_list(kp.lists1 + li);
+      const List L = Lnext;
+      if (li + 1 < l1) Lnext = load_list(kp.lists1 + li + 1);  // hide the header's latency behind this list
       if (L.flags & kListFirst) {
 #pragma unroll
         for (int e = 0; e < 6; e++) g[e] = 0.0f;
@@ -283,14 +369,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
       const bool home = (L.kind & 1) == 0;
       float gx, gy;
       if (!CLIP) {
-        const uint4* e4 = reinterpret_cast<const uint4*>(reinterpret_cast<const Entry*>(kp.ent1) + L.ent);
-        const uint32_t n2 = L.n >> 1;
         float ax0 = 0.0f, ay0 = 0.0f, ax1 = 0.0f, ay1 = 0.0f;
         if (home) {
           float m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
-#pragma unroll 4
-          for (uint32_t i = 0; i < n2; i++) {
-            const uint4 q = __ldg(e4 + i);
+          stream.consume(L.n * (uint32_t)sizeof(Entry), [&](uint32_t addr) {
+            const uint4 q = lds128u(addr);  // two entries
             const float2 a = lds64(tab + q.x), b = lds64(tab + q.z);
             const float wa = __uint_as_float(q.y), wb = __uint_as_float(q.w);
             ax0 = fmaf(wa, a.x, ax0); ay0 = fmaf(wa, a.y, ay0);
@@ -298,55 +381,65 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
             m1 = fmaxf(m1, fmaxf(a.x, b.x));
             m2 = fmaxf(m2, fmaxf(a.y, b.y));
             m3 = fmaxf(m3, fmaxf(a.x * a.y, b.x * b.y));
-          }
+          });
           const float v0 = own.x * m1, v1 = own.y * m2, v2 = (own.x * own.y) * m3;
           if (v0 > best[0]) { best[0] = v0; bestl[0] = li; }
           if (v1 > best[1]) { best[1] = v1; bestl[1] = li; }
           if (v2 > best[2]) { best[2] = v2; bestl[2] = li; }
         } else {
-#pragma unroll 4
-          for (uint32_t i = 0; i < n2; i++) {
-            const uint4 q = __ldg(e4 + i);
+          stream.consume(L.n * (uint32_t)sizeof(Entry), [&](uint32_t addr) {
+            const uint4 q = lds128u(addr);
             const float2 a = lds64(tab + q.x), b = lds64(tab + q.z);
             const float wa = __uint_as_float(q.y), wb = __uint_as_float(q.w);
             ax0 = fmaf(wa, a.x, ax0); ay0 = fmaf(wa, a.y, ay0);
             ax1 = fmaf(wb, b.x, ax1); ay1 = fmaf(wb, b.y, ay1);
-          }
+          });
         }
         const float SX = own.x * (ax0 + ax1), SY = own.y * (ay0 + ay1);
         acc.lp -= 0.5f * (SX + SY);  // every match is in two lists
         gx = -SX;
         gy = -SY;
       } else {
-        const uint4* e4 = reinterpret_cast<const uint4*>(reinterpret_cast<const EntryClip*>(kp.ent1) + L.ent);
         gx = gy = 0.0f;
-        float lpl = 0.0f, m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
-#pragma unroll 2
-        for (uint32_t i = 0; i < L.n; i++) {
-          const uint4 q = __ldg(e4 + i);
-          const float2 a = lds64(tab + q.x);
-          const float w = __uint_as_float(q.y), wyx = __uint_as_float(q.z), wyy = __uint_as_float(q.w);
-          const float X = own.x * a.x, Y = own.y * a.y;
-          const float Xc = fminf(X, 15.0f), Yc = fminf(Y, 15.0f);
-          if (home) {
-            lpl += wyx * __logf(Xc) - w * Xc + wyy * __logf(Yc) - w * Yc;
+        if (home) {
+          float lp2 = 0.0f, lpw = 0.0f, m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
+          stream.consume(L.n * (uint32_t)sizeof(EntryClip), [&](uint32_t addr) {
+            const uint4 q = lds128u(addr);  // one entry: off, w, w*y_x, w*y_y
+            const float2 a = lds64(tab + q.x);
+            const float w = __uint_as_float(q.y), wyx = __uint_as_float(q.z), wyy = __uint_as_float(q.w);
+            const float X = own.x * a.x, Y = own.y * a.y;
+            const float Xc = fminf(X, 15.0f), Yc = fminf(Y, 15.0f);
+            lp2 = fmaf(wyx, lg2_approx(Xc), lp2);
+            lp2 = fmaf(wyy, lg2_approx(Yc), lp2);
+            lpw = fmaf(w, Xc + Yc, lpw);
             m1 = fmaxf(m1, Xc);
             m2 = fmaxf(m2, Yc);
             m3 = fmaxf(m3, Xc * Yc);
-          }
-          gx += X < 15.0f ? fmaf(-w, X, wyx) : 0.0f;
-          gy += Y < 15.0f ? fmaf(-w, Y, wyy) : 0.0f;
-        }
-        if (home) {
-          acc.lp += lpl;
+            gx += X < 15.0f ? fmaf(-w, X, wyx) : 0.0f;
+            gy += Y < 15.0f ? fmaf(-w, Y, wyy) : 0.0f;
+          });
+          acc.lp += fmaf(lp2, kLn2, -lpw);
           if (m1 > best[0]) { best[0] = m1; bestl[0] = li; }
           if (m2 > best[1]) { best[1] = m2; bestl[1] = li; }
           if (m3 > best[2]) { best[2] = m3; bestl[2] = li; }
+        } else {
+          stream.consume(L.n * (uint32_t)sizeof(EntryClip), [&](uint32_t addr) {
+            const uint4 q = lds128u(addr);
+            const float2 a = lds64(tab + q.x);
+            const float w = __uint_as_float(q.y), wyx = __uint_as_float(q.z), wyy = __uint_as_float(q.w);
+            const float X = own.x * a.x, Y = own.y * a.y;
+            gx += X < 15.0f ? fmaf(-w, X, wyx) : 0.0f;
+            gy += Y < 15.0f ? fmaf(-w, Y, wyy) : 0.0f;
+          });
         }
       }
       add_own(g, L.kind, gx, gy);
       if (L.flags & kListLast) apply_vteam<KMAX>(kp, hy, acc, ln, true, (int)L.vteam, g, false, false, 0.0f, 0.0f, zero4);
     }
+  }
+  {  // start fetching this warp's tau entries while the other warps finish phase 1
+    const int e0 = __ldg(kp.warp_e2 + warp), e1 = __ldg(kp.warp_e2 + warp + 1);
+    stream.begin(kp.ent2 + e0, (uint32_t)(e1 - e0) * (uint32_t)sizeof(Entry));
   }
   // ---- bounds (bpl/_util.py:17-31) ------------------------------------------------------------------
 #pragma unroll
@@ -381,8 +474,10 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
     float g[6];
     const float zero4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     const int l0 = __ldg(kp.warp_l2 + warp), l1 = __ldg(kp.warp_l2 + warp + 1);
+    List Lnext = l0 < l1 ? load_list(kp.lists2 + l0) : List{};
     for (int li = l0; li < l1; li++) {
-      const List L = load_list(kp.lists2 + li);
+      const List L = Lnext;
+      if (li + 1 < l1) Lnext = load_list(kp.lists2 + li + 1);
       if (L.flags & kListFirst) {
 #pragma unroll
         for (int e = 0; e < 6; e++) g[e] = 0.0f;
@@ -390,54 +485,48 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
       float2 own = lds64(tab + L.own_off);
       if (L.kind >= kH0) { const float s = own.x; own.x = own.y; own.y = s; }
       const bool home = (L.kind & 1) == 0;
-      const Entry* ep = kp.ent2 + L.ent;
       float uxy = 0.0f, ux = 0.0f, uy = 0.0f, lt = 0.0f;     // unmasked (d/d corr_coef)
       float sxy_x = 0.0f, sxy_y = 0.0f, sx = 0.0f, sy = 0.0f;  // masked by "rate not clipped"
-      // class XY: tau = 1 - c X Y
-#pragma unroll 2
-      for (uint32_t i = 0; i < L.n_xy; i++) {
-        const uint2 q = __ldg(reinterpret_cast<const uint2*>(ep + i));
-        const float2 a = lds64(tab + q.x);
-        const float w = __uint_as_float(q.y);
+      // one entry = (opponent row offset, w); the ring is read two entries (16 bytes) at a time
+      auto xy = [&](uint32_t off, float w) {  // tau = 1 - c X Y
+        const float2 a = lds64(tab + off);
         const float Xr = own.x * a.x, Yr = own.y * a.y;
         const float X = CLIP ? fminf(Xr, 15.0f) : Xr, Y = CLIP ? fminf(Yr, 15.0f) : Yr;
-        const float tau = fmaxf(1.0f - (cc * X) * Y, 0.0f);
-        const float val = w * (X * Y) * __frcp_rn(tau);
+        const float t = X * Y;
+        const float tau = fmaxf(fmaf(-cc, t, 1.0f), 0.0f);
+        const float val = (w * t) * rcp_approx(tau);
         uxy += val;
         if (CLIP) {
           sxy_x += Xr < 15.0f ? val : 0.0f;
           sxy_y += Yr < 15.0f ? val : 0.0f;
         }
-        if (home) lt = fmaf(w, __log2f(tau), lt);
-      }
-      ep += L.n_xy;
-#pragma unroll 2
-      for (uint32_t i = 0; i < L.n_x; i++) {
-        const uint2 q = __ldg(reinterpret_cast<const uint2*>(ep + i));
-        const float2 a = lds64(tab + q.x);
-        const float w = __uint_as_float(q.y);
-        const float Xr = own.x * a.x;
-        const float X = CLIP ? fminf(Xr, 15.0f) : Xr;
-        const float tau = fmaxf(fmaf(cc, X, 1.0f), 0.0f);
-        const float val = w * X * __frcp_rn(tau);
-        ux += val;
-        if (CLIP) sx += Xr < 15.0f ? val : 0.0f;
-        if (home) lt = fmaf(w, __log2f(tau), lt);
-      }
-      ep += L.n_x;
-#pragma unroll 2
-      for (uint32_t i = 0; i < L.n_y; i++) {
-        const uint2 q = __ldg(reinterpret_cast<const uint2*>(ep + i));
-        const float2 a = lds64(tab + q.x);
-        const float w = __uint_as_float(q.y);
-        const float Yr = own.y * a.y;
-        const float Y = CLIP ? fminf(Yr, 15.0f) : Yr;
-        const float tau = fmaxf(fmaf(cc, Y, 1.0f), 0.0f);
-        const float val = w * Y * __frcp_rn(tau);
-        uy += val;
-        if (CLIP) sy += Yr < 15.0f ? val : 0.0f;
-        if (home) lt = fmaf(w, __log2f(tau), lt);
-      }
+        if (home) lt = fmaf(w, lg2_approx(tau), lt);
+      };
+      auto one = [&](uint32_t off, float w, bool is_x, float& u, float& s) {  // tau = 1 + c X  (or Y)
+        const float2 a = lds64(tab + off);
+        const float Rr = is_x ? own.x * a.x : own.y * a.y;
+        const float R = CLIP ? fminf(Rr, 15.0f) : Rr;
+        const float tau = fmaxf(fmaf(cc, R, 1.0f), 0.0f);
+        const float val = (w * R) * rcp_approx(tau);
+        u += val;
+        if (CLIP) s += Rr < 15.0f ? val : 0.0f;
+        if (home) lt = fmaf(w, lg2_approx(tau), lt);
+      };
+      stream.consume((uint32_t)L.n_xy * (uint32_t)sizeof(Entry), [&](uint32_t addr) {
+        const uint4 q = lds128u(addr);
+        xy(q.x, __uint_as_float(q.y));
+        xy(q.z, __uint_as_float(q.w));
+      });
+      stream.consume((uint32_t)L.n_x * (uint32_t)sizeof(Entry), [&](uint32_t addr) {
+        const uint4 q = lds128u(addr);
+        one(q.x, __uint_as_float(q.y), true, ux, sx);
+        one(q.z, __uint_as_float(q.w), true, ux, sx);
+      });
+      stream.consume((uint32_t)L.n_y * (uint32_t)sizeof(Entry), [&](uint32_t addr) {
+        const uint4 q = lds128u(addr);
+        one(q.x, __uint_as_float(q.y), false, uy, sy);
+        one(q.z, __uint_as_float(q.w), false, uy, sy);
+      });
       if (!CLIP) { sxy_x = sxy_y = uxy; sx = ux; sy = uy; }
       if (home) {
         acc.lp = fmaf(lt, kLn2, acc.lp);

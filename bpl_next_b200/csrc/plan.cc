@@ -318,6 +318,8 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err) {
   P.n1 = P.n2 = 0;
   P.warp_l1.assign(W + 1, 0);
   P.warp_l2.assign(W + 1, 0);
+  P.warp_e1.assign(W + 1, 0);
+  P.warp_e2.assign(W + 1, 0);
   for (int w = 0; w < W; w++) {
     // phase 1
     for (int v : w1[w]) {
@@ -354,6 +356,7 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err) {
       }
     }
     P.warp_l1[w + 1] = (int32_t)P.lists1.size();
+    P.warp_e1[w + 1] = (int32_t)(kp.clip ? P.ent1c.size() : P.ent1.size());
     // phase 2
     for (int v : w2[w]) {
       size_t first = P.lists2.size();
@@ -392,6 +395,7 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err) {
       }
     }
     P.warp_l2[w + 1] = (int32_t)P.lists2.size();
+    P.warp_e2[w + 1] = (int32_t)P.ent2.size();
   }
   P.n1_padded = (long long)(kp.clip ? P.ent1c.size() : P.ent1.size());
   P.n2_padded = (long long)P.ent2.size();
@@ -399,8 +403,9 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err) {
   // ---- shared-memory carve-up --------------------------------------------------------------------
   uint32_t epi = (uint32_t)W * hyper_rows(K) * 128u;
   kp.tab_bytes = std::max(table_bytes, epi);
-  kp.smem_conf = kp.tab_bytes;
-  kp.smem_red = kp.smem_conf + (uint32_t)Cf * 128u;
+  kp.smem_ring = kp.tab_bytes;
+  kp.smem_bar = kp.smem_ring + (uint32_t)W * kStages * kStageBytes;
+  kp.smem_red = (kp.smem_bar + (uint32_t)W * kStages * 8u + 127u) / 128u * 128u;
   kp.smem_total = kp.smem_red + (uint32_t)W * kRedRows * 128u;
   if (kp.smem_total > 227u * 1024u)
     FAIL(BPLX_E_UNSUPPORTED, "problem needs %u bytes of shared memory per CTA (max %u): too many (team, confederation) pairs (%d)",

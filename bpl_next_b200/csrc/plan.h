@@ -45,6 +45,8 @@ constexpr int kListMax = 128;     // entries per list piece (bounds the arg-max 
 constexpr int kMaxCov = 8;        // covariates supported by the kernel
 constexpr int kMaxWarps = 16;
 constexpr int kRedRows = 8;       // per-warp rows in the reduction area
+constexpr int kStageBytes = 512;  // one TMA bulk copy of a warp's entry stream
+constexpr int kStages = 2;        // ring depth per warp
 
 enum Kind : uint8_t { kH1 = 0, kA1 = 1, kH0 = 2, kA0 = 3 };
 enum Exponent : int { eAh1 = 0, eBh1 = 1, eBa1 = 2, eAa1 = 3, eA0 = 4, eB0 = 5 };
@@ -98,7 +100,7 @@ struct KernelParams {
   int has1, has0;  // venue classes present
   uint32_t tabP1, tabQ1, tabP0;  // byte offsets of the tables (row V of each = zero row)
   uint32_t tab_bytes;
-  uint32_t smem_conf, smem_red, smem_total;  // carve-up (bytes)
+  uint32_t smem_ring, smem_bar, smem_red, smem_total;  // carve-up (bytes)
   ThetaOffsets off;
   const List* lists1;
   const List* lists2;
@@ -106,6 +108,8 @@ struct KernelParams {
   const Entry* ent2;
   const int32_t* warp_l1;  // [nwarps+1] list range of each warp, phase 1
   const int32_t* warp_l2;  // [nwarps+1]
+  const int32_t* warp_e1;  // [nwarps+1] entry range of each warp (contiguous stream), phase 1
+  const int32_t* warp_e2;  // [nwarps+1]
   const int32_t* team_vptr;   // [T+1] virtual teams of each team (CSR over v, v sorted by team)
   const uint16_t* v_team;     // [V]
   const uint8_t* v_conf;      // [V]
@@ -133,7 +137,7 @@ struct HostPlan {
   std::vector<List> lists1, lists2;
   std::vector<Entry> ent1, ent2;
   std::vector<EntryClip> ent1c;
-  std::vector<int32_t> warp_l1, warp_l2, team_vptr, conf_vptr, conf_vlist;
+  std::vector<int32_t> warp_l1, warp_l2, warp_e1, warp_e2, team_vptr, conf_vptr, conf_vlist;
   std::vector<uint16_t> v_team;
   std::vector<uint8_t> v_conf;
   std::vector<float> yexp, Xs;
