@@ -100,32 +100,23 @@ int bplx_problem_create(const bplx_problem_desc* desc, bplx_problem** out) {
   p->kp = hp.kp;
   p->layout = hp.layout;
   KernelParams& kp = p->kp;
-  const List *l1 = nullptr, *l2 = nullptr;
-  const Entry *e1 = nullptr, *e2 = nullptr;
-  const EntryClip* e1c = nullptr;
 #define UP(vec, ptr)                                 \
   if ((rc = upload(p, hp.vec, &(ptr))) != BPLX_OK) return fail(rc)
-  UP(lists1, l1);
-  UP(lists2, l2);
-  UP(ent1, e1);
-  UP(ent1c, e1c);
-  UP(ent2, e2);
-  UP(warp_l1, kp.warp_l1);
-  UP(warp_l2, kp.warp_l2);
-  UP(warp_e1, kp.warp_e1);
-  UP(warp_e2, kp.warp_e2);
+  UP(stream1, kp.stream1);
+  UP(stream2, kp.stream2);
+  UP(warp_b1, kp.warp_b1);
+  UP(warp_b2, kp.warp_b2);
   UP(team_vptr, kp.team_vptr);
+  UP(team_flags, kp.team_flags);
   UP(v_team, kp.v_team);
   UP(v_conf, kp.v_conf);
   UP(conf_vptr, kp.conf_vptr);
   UP(conf_vlist, kp.conf_vlist);
   UP(yexp, kp.yexp);
+  UP(yteam, kp.yteam);
+  UP(yconf, kp.yconf);
   UP(Xs, kp.Xs);
 #undef UP
-  kp.lists1 = l1;
-  kp.lists2 = l2;
-  kp.ent1 = kp.clip ? static_cast<const void*>(e1c) : static_cast<const void*>(e1);
-  kp.ent2 = e2;
   if ((rc = logdensity_set_attributes(kp)) != BPLX_OK) return fail(rc);
   p->stats[0] = desc->num_matches;
   p->stats[1] = hp.n1;

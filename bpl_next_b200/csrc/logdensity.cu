@@ -5,19 +5,21 @@
 // bpl/neutral_dixon_coles_WC.py:83-232) together with bpl/_util.py:17-93, for a batch of chains.
 //
 // CTA = 32 chains (lane = chain) x nwarps warps.  Flow (DESIGN.md "K1"):
-//   prologue  each warp takes teams t = warp, warp+W, ...: reads theta, adds the per-team priors,
-//             writes the rows (exp of the six exponents) of its virtual teams into the shared
-//             tables, and stores the prior + static (sum w*y) part of the gradient.
-//   phase 1   each warp walks its entry lists: acc += w * table[opp]; per list
+//   prologue  each warp takes teams t = warp, warp+W, ...: reads theta and writes the rows (exp of
+//             the six exponents) of its virtual teams into the shared tables; static sum(w y eta).
+//   phase 1   each warp walks its stream of lists: acc += w * table[opp]; per list
 //             sum_w_lambda = own * acc (both rates), running maxima of lambda_h, lambda_a,
-//             lambda_h*lambda_a with the list they came from (bpl/_util.py:23-30).
-//   bounds    maxima reduced over warps -> LB, UB, corr_coef.
-//   phase 2   tau lists (0-0, 1-0, 0-1 matches): log tau, d/d eta, d/d corr_coef.
-//   fix-up    the maxima's arg-max entries are found by rescanning one list per chain and the
-//             d corr_coef / d eta terms are added.
-//   epilogue  hyper-parameter chain rule, priors and Jacobians; lp, corr_coef.
-// Gradients of per-team parameters are accumulated by read-modify-write of the caller's grad
-// buffer by the single thread that owns (team, chain) in each stage: no atomics, deterministic.
+//             lambda_h*lambda_a with the list they came from (bpl/_util.py:23-30).  A team's
+//             gradient wrt its log-rate halves goes to its raw slots in the grad buffer.
+//   bounds    maxima reduced over warps -> LB, UB, corr_coef; every warp scans a slice of each
+//             chain's arg-max lists for the entry that attained the maximum.
+//   phase 2   tau lists (0-0, 1-0, 0-1 matches): log tau, d/d eta (added to the raw slots),
+//             d/d corr_coef.
+//   fix-up    d corr_coef / d eta of the arg-max matches is added.
+//   team pass raw slots -> parameter gradients: priors, chain rule, hyper-parameter sums.
+//   epilogue  cross-warp reduction, hyper priors + Jacobians, covariate coefficients; lp, corr_coef.
+// A raw slot is written by the one thread that owns (team, chain) in a phase and red.add'ed by one
+// thread per later stage, in program order: the result is deterministic.
 #include <float.h>
 
 #include "common.cuh"
@@ -28,17 +30,11 @@ namespace bplx {
 
 namespace {
 
-constexpr float kLogSqrt2Pi = 0.918938533204672742f;
 constexpr float kLn2 = 0.693147180559945309f;
+constexpr unsigned kFull = 0xffffffffu;
 
 struct Hyp {  // constrained hyper-parameters of this lane's chain
-  float mu_d, sig_a, sig_d, mu[4], sig[4], rho, inv_s2;
-};
-
-template <int KMAX>
-struct Acc {  // gradient accumulators wrt hyper-parameters (+ this thread's share of lp)
-  float lp, mu_d, ls_a, ls_d, mu[4], ls[4], rho;
-  float ba[KMAX > 0 ? KMAX : 1], bd[KMAX > 0 ? KMAX : 1];
+  float mu_d, sig_a, sig_d, mu[4], sig[4];
 };
 
 struct Lane {
@@ -48,6 +44,7 @@ struct Lane {
   long long sd;
   bool active;
   __device__ __forceinline__ float ld(int d) const { return __ldg(th + (long long)d * sd); }
+  __device__ __forceinline__ float* g(int d) const { return gr + (long long)d * sd; }
 };
 
 __device__ __forceinline__ float sigmoid_clipped(float x) {
@@ -55,85 +52,6 @@ __device__ __forceinline__ float sigmoid_clipped(float x) {
   float s = 1.0f / (1.0f + expf(-x));
   return fminf(fmaxf(s, FLT_MIN), 1.0f - FLT_EPSILON);
 }
-
-// exponent gradients g[6] of virtual team v -> raw parameter gradients.
-// `pred` masks everything (stores and accumulators); `init_t` / `init_v`: first touch of the
-// team's gradient entries / of the virtual team's scratch slot -> plain store of prior + value.
-template <int KMAX>
-__device__ __forceinline__ void apply_vteam(const KernelParams& kp, const Hyp& hy, Acc<KMAX>& acc, const Lane& ln,
-                                            bool pred, int v, const float (&g)[6], bool init_t, bool init_v,
-                                            float p_za, float p_zd, const float (&p_dec)[4]) {
-  const ThetaOffsets& o = kp.off;
-  const int t = kp.v_team[v];
-  const float gA = g[eAh1] + g[eAa1] + g[eA0];
-  const float gB = g[eBh1] + g[eBa1] + g[eB0];
-  const float g_att = pred ? gA : 0.0f, g_def = pred ? -gB : 0.0f;
-  const bool st = pred && ln.active;
-  if (kp.Cf > 0) {
-    float* s = ln.sc + (long long)v * kp.Cpad;
-    float old = init_v ? 0.0f : (st ? *s : 0.0f);
-    if (st) *s = old + (gA - gB);
-  }
-  {
-    const float za = ln.ld(o.za + t), zd = ln.ld(o.zd + t);
-    float* pa = ln.gr + (long long)(o.za + t) * ln.sd;
-    float* pd = ln.gr + (long long)(o.zd + t) * ln.sd;
-    float olda = init_t ? p_za : (st ? *pa : 0.0f);
-    float oldd = init_t ? p_zd : (st ? *pd : 0.0f);
-    if (st) {
-      *pa = fmaf(hy.sig_a, g_att, olda);
-      *pd = fmaf(hy.sig_d, g_def, oldd);
-    }
-    acc.ls_a = fmaf(hy.sig_a * za, g_att, acc.ls_a);
-    acc.ls_d = fmaf(hy.sig_d * zd, g_def, acc.ls_d);
-    acc.mu_d += g_def;
-  }
-  if (KMAX > 0) {
-#pragma unroll
-    for (int k = 0; k < KMAX; k++) {
-      if (k < kp.K) {
-        const float x = __ldg(kp.Xs + (size_t)t * kp.K + k);
-        acc.ba[k] = fmaf(x, g_att, acc.ba[k]);
-        acc.bd[k] = fmaf(x, g_def, acc.bd[k]);
-      }
-    }
-  }
-  const float gx[4] = {pred ? g[eAh1] : 0.0f, pred ? g[eAa1] : 0.0f, pred ? -g[eBh1] : 0.0f, pred ? -g[eBa1] : 0.0f};
-  if (kp.model == BPLX_DIXON_COLES) {
-    acc.mu[0] += gx[0];
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      if (i == 0 || kp.model != BPLX_EXTENDED) {
-        const float dec = ln.ld(o.dec[i] + t);
-        float* p = ln.gr + (long long)(o.dec[i] + t) * ln.sd;
-        float old = init_t ? p_dec[i] : (st ? *p : 0.0f);
-        if (st) *p = fmaf(hy.sig[i], gx[i], old);
-        acc.mu[i] += gx[i];
-        acc.ls[i] = fmaf(hy.sig[i] * dec, gx[i], acc.ls[i]);
-      }
-    }
-  }
-}
-
-__device__ __forceinline__ void add_own(float (&g)[6], int kind, float gx, float gy) {
-  switch (kind) {
-    case kH1: g[eAh1] += gx; g[eBh1] += gy; break;
-    case kA1: g[eBa1] += gx; g[eAa1] += gy; break;
-    default: g[eB0] += gx; g[eA0] += gy; break;
-  }
-}
-
-__device__ __forceinline__ List load_list(const List* p) {
-  const uint4* q = reinterpret_cast<const uint4*>(p);
-  uint4 a = __ldg(q), b = __ldg(q + 1);
-  List L;
-  L.ent = a.x; L.n = a.y; L.own_off = a.z; L.vteam = a.w;
-  L.n_xy = (uint16_t)(b.x & 0xffff); L.n_x = (uint16_t)(b.x >> 16);
-  L.n_y = (uint16_t)(b.y & 0xffff); L.kind = (uint8_t)((b.y >> 16) & 0xff); L.flags = (uint8_t)(b.y >> 24);
-  return L;
-}
-
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -144,8 +62,96 @@ __device__ __forceinline__ float lg2_approx(float x) {
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ void red_add(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ float ld_cg(const float* p) {
+  float v;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
 
-// Per-warp TMA ring over a contiguous global byte stream (the warp's entries of one phase).
+__device__ __forceinline__ Hyp load_hyp(const KernelParams& kp, const Lane& ln) {
+  const ThetaOffsets& o = kp.off;
+  Hyp hy;
+  hy.mu_d = ln.ld(o.mean_defence);
+  hy.sig_a = expf(ln.ld(o.log_std_attack));
+  hy.sig_d = expf(ln.ld(o.log_std_defence));
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    hy.mu[i] = o.mean[i] >= 0 ? ln.ld(o.mean[i]) : 0.0f;
+    hy.sig[i] = o.log_std[i] >= 0 ? expf(ln.ld(o.log_std[i])) : 0.0f;
+  }
+  return hy;
+}
+
+struct Hdr {
+  uint32_t own_off, vteam, kind, flags, n0, n1, n2, team;
+};
+__device__ __forceinline__ Hdr unpack_hdr(const uint4 h) {
+  Hdr H;
+  H.own_off = h.x;
+  H.vteam = h.y & 0xffffu;
+  H.kind = (h.y >> 16) & 0xffu;
+  H.flags = h.y >> 24;
+  H.n0 = h.z & 0xffffu;
+  H.n1 = h.z >> 16;
+  H.n2 = h.w & 0xffffu;
+  H.team = h.w >> 16;
+  return H;
+}
+
+__device__ __forceinline__ void add_own(float (&g)[6], uint32_t kind, float gx, float gy) {
+  if (kind == kH1) {
+    g[eAh1] += gx; g[eBh1] += gy;
+  } else if (kind == kA1) {
+    g[eBa1] += gx; g[eAa1] += gy;
+  } else {
+    g[eB0] += gx; g[eA0] += gy;
+  }
+}
+
+// exponent gradients of a team -> its raw slots (d/d att, d/d def, d/d venue effects).
+// ADD = false: first touch (phase 1), plain stores.  ADD = true: red.add.
+template <bool ADD>
+__device__ __forceinline__ void put_raw(const KernelParams& kp, const Lane& ln, int t, const float (&g)[6], float& hacc) {
+  const ThetaOffsets& o = kp.off;
+  const float ra = g[eAh1] + g[eAa1] + g[eA0];
+  const float rd = -(g[eBh1] + g[eBa1] + g[eB0]);
+  const float rx[4] = {g[eAh1], g[eAa1], -g[eBh1], -g[eBa1]};
+  if (kp.ndec == 0) hacc += rx[0];  // DIXON_COLES: scalar home advantage
+  if (!ln.active) return;
+  if (ADD) {
+    red_add(ln.g(o.za + t), ra);
+    red_add(ln.g(o.zd + t), rd);
+  } else {
+    *ln.g(o.za + t) = ra;
+    *ln.g(o.zd + t) = rd;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    if (i < kp.ndec) {
+      if (ADD) red_add(ln.g(o.dec[i] + t), rx[i]);
+      else *ln.g(o.dec[i] + t) = rx[i];
+    }
+  }
+}
+
+// one exponent of one virtual team gets `val` more gradient (arg-max fix-up; per-lane arguments)
+__device__ __forceinline__ void add_exponent(const KernelParams& kp, const Lane& ln, int v, int e, float val, float& hacc) {
+  if (val == 0.0f) return;
+  const ThetaOffsets& o = kp.off;
+  const int t = __ldg(kp.v_team + v);
+  const bool isA = e == eAh1 || e == eAa1 || e == eA0;
+  const float sv = isA ? val : -val;
+  red_add(ln.g((isA ? o.za : o.zd) + t), sv);
+  const int di = e == eAh1 ? 0 : e == eAa1 ? 1 : e == eBh1 ? 2 : e == eBa1 ? 3 : -1;
+  if (di >= 0 && di < kp.ndec) red_add(ln.g(o.dec[di] + t), sv);
+  if (kp.ndec == 0 && e == eAh1) hacc += val;
+  if (kp.Cf > 0) red_add(ln.sc + (long long)v * kp.Cpad, sv);
+}
+
+// Per-warp TMA ring over a contiguous global byte stream (the warp's lists of one phase).
 // One elected lane issues cp.async.bulk copies of kStageBytes into the warp's private ring and
 // every lane waits on the stage's mbarrier before reading it; the same warp produces and
 // consumes, so a __syncwarp() is all that is needed before a slot is refilled.
@@ -208,11 +214,16 @@ struct Stream {
       }
     }
   }
+  __device__ __forceinline__ Hdr header() {
+    uint4 h;
+    consume(16u, [&](uint32_t addr) { h = lds128u(addr); });
+    return unpack_hdr(h);
+  }
 };
 
 }  // namespace
 
-template <bool CLIP, int KMAX>
+template <bool CLIP>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __grid_constant__ KernelParams kp) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = kp.nwarps;
@@ -226,141 +237,87 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
   ln.sd = kp.sd;
   ln.active = chain_raw < kp.C;
   const uint32_t tab = smem_u32(smem) + lane * 8;  // + row byte offset
-  float* red = reinterpret_cast<float*>(smem + kp.smem_red);
+  unsigned long long* red_best = reinterpret_cast<unsigned long long*>(smem + kp.smem_red);  // [3][32]
+  uint32_t* red_found = reinterpret_cast<uint32_t*>(smem + kp.smem_red + 768);               // [2][32]
+  float* red_gc = reinterpret_cast<float*>(smem + kp.smem_red + 1024);                        // [W][32]
+  constexpr uint32_t ESZ = CLIP ? (uint32_t)sizeof(EntryClip) : (uint32_t)sizeof(Entry);
   Stream stream;
   stream.init(smem_u32(smem) + kp.smem_ring + warp * (kStages * kStageBytes),
               smem_u32(smem) + kp.smem_bar + warp * (kStages * 8), lane);
-  {  // phase-1 entries start streaming in while the prologue runs
-    const int e0 = __ldg(kp.warp_e1 + warp), e1 = __ldg(kp.warp_e1 + warp + 1);
-    const uint32_t esz = CLIP ? (uint32_t)sizeof(EntryClip) : (uint32_t)sizeof(Entry);
-    stream.begin(static_cast<const unsigned char*>(kp.ent1) + (size_t)e0 * esz, (uint32_t)(e1 - e0) * esz);
-  }
+  const uint32_t b1_0 = __ldg(kp.warp_b1 + warp), b1_1 = __ldg(kp.warp_b1 + warp + 1);
+  stream.begin(kp.stream1 + b1_0, b1_1 - b1_0);  // phase-1 lists start streaming in while the prologue runs
 
-  const bool dc = kp.model == BPLX_DIXON_COLES, ext = kp.model == BPLX_EXTENDED;
-  const bool has_rho = !dc;
-  const int ndec = dc ? 0 : (ext ? 1 : 4);
-
-  // ---- hyper-parameters ---------------------------------------------------------------------
-  Hyp hy;
-  hy.mu_d = ln.ld(o.mean_defence);
-  hy.sig_a = expf(ln.ld(o.log_std_attack));
-  hy.sig_d = expf(ln.ld(o.log_std_defence));
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    hy.mu[i] = o.mean[i] >= 0 ? ln.ld(o.mean[i]) : 0.0f;
-    hy.sig[i] = o.log_std[i] >= 0 ? expf(ln.ld(o.log_std[i])) : 0.0f;
-  }
-  float u = 0.5f;
-  if (has_rho) u = sigmoid_clipped(ln.ld(o.u));
-  hy.rho = has_rho ? 2.0f * u - 1.0f : 0.0f;
-  hy.inv_s2 = 1.0f / (1.0f - hy.rho * hy.rho);
-  float beta_a[KMAX > 0 ? KMAX : 1], beta_d[KMAX > 0 ? KMAX : 1];
-  if (KMAX > 0) {
-#pragma unroll
-    for (int k = 0; k < KMAX; k++) {
-      beta_a[k] = k < kp.K ? ln.ld(o.beta_a + k) : 0.0f;
-      beta_d[k] = k < kp.K ? ln.ld(o.beta_d + k) : 0.0f;
-    }
-  }
-  Acc<KMAX> acc;
-  acc.lp = acc.mu_d = acc.ls_a = acc.ls_d = acc.rho = 0.0f;
-#pragma unroll
-  for (int i = 0; i < 4; i++) acc.mu[i] = acc.ls[i] = 0.0f;
-#pragma unroll
-  for (int k = 0; k < (KMAX > 0 ? KMAX : 1); k++) acc.ba[k] = acc.bd[k] = 0.0f;
+  const int ndec = kp.ndec;
+  const bool dc = ndec == 0;
+  float lp_acc = 0.0f;  // this thread's share of the log-density
+  float hacc = 0.0f;    // DIXON_COLES: d/d home_advantage
 
   // ---- prologue -------------------------------------------------------------------------------
-  if (warp == 0) {  // zero rows used by padding entries
-    const uint32_t zr = (uint32_t)kp.V * kRowBytes;
+  if (warp == 0) {
+    const uint32_t zr = (uint32_t)kp.V * kRowBytes;  // zero rows used by padding entries
     if (kp.has1) {
       sts64(tab + kp.tabP1 + zr, 0.0f, 0.0f);
       sts64(tab + kp.tabQ1 + zr, 0.0f, 0.0f);
     }
     if (kp.has0) sts64(tab + kp.tabP0 + zr, 0.0f, 0.0f);
+    red_best[lane] = red_best[32 + lane] = red_best[64 + lane] = 0ull;
+    red_found[lane] = red_found[32 + lane] = 0xffffffffu;
   }
-  for (int t = warp; t < kp.T; t += W) {
-    const float za = ln.ld(o.za + t), zd = ln.ld(o.zd + t);
-    float am = 0.0f, dm = hy.mu_d;
-    if (KMAX > 0) {
-#pragma unroll
-      for (int k = 0; k < KMAX; k++) {
-        if (k < kp.K) {
-          const float x = __ldg(kp.Xs + (size_t)t * kp.K + k);
-          am = fmaf(x, beta_a[k], am);
-          dm = fmaf(x, beta_d[k], dm);
-        }
+  {
+    const Hyp hy = load_hyp(kp, ln);
+    for (int t = warp; t < kp.T; t += W) {
+      float am = 0.0f, dm = hy.mu_d;
+      for (int k = 0; k < kp.K; k++) {
+        const float x = __ldg(kp.Xs + (size_t)t * kp.K + k);
+        am = fmaf(x, ln.ld(o.beta_a + k), am);
+        dm = fmaf(x, ln.ld(o.beta_d + k), dm);
       }
-    }
-    const float att = fmaf(za, hy.sig_a, am), def = fmaf(zd, hy.sig_d, dm);
-    float p_za, p_zd, p_dec[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    if (has_rho) {  // za ~ N(0,1), zd ~ N(rho za, sqrt(1-rho^2))  (extended_dixon_coles.py:165-174)
-      const float e = zd - hy.rho * za;
-      const float es = e * hy.inv_s2;
-      acc.lp -= 0.5f * (za * za + e * es);
-      p_za = -za + hy.rho * es;
-      p_zd = -es;
-      acc.rho += es * za - hy.rho * es * es + hy.rho * hy.inv_s2;
-    } else {
-      acc.lp -= 0.5f * (za * za + zd * zd);
-      p_za = -za;
-      p_zd = -zd;
-    }
-    float x[4] = {dc ? hy.mu[0] : 0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      if (i < ndec) {
-        const float dec = ln.ld(o.dec[i] + t);
-        x[i] = fmaf(hy.sig[i], dec, hy.mu[i]);
-        acc.lp -= 0.5f * dec * dec;
-        p_dec[i] = -dec;
-      }
-    }
-    const int v0 = __ldg(kp.team_vptr + t), v1 = __ldg(kp.team_vptr + t + 1);
-    if (v0 == v1 && ln.active) {  // team without matches: prior gradient only
-      ln.gr[(long long)(o.za + t) * ln.sd] = p_za;
-      ln.gr[(long long)(o.zd + t) * ln.sd] = p_zd;
+      const float att = fmaf(ln.ld(o.za + t), hy.sig_a, am), def = fmaf(ln.ld(o.zd + t), hy.sig_d, dm);
+      float x[4] = {dc ? hy.mu[0] : 0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
       for (int i = 0; i < 4; i++)
-        if (i < ndec) ln.gr[(long long)(o.dec[i] + t) * ln.sd] = p_dec[i];
-    }
-    for (int v = v0; v < v1; v++) {
-      const float cf = kp.Cf > 0 ? ln.ld(o.conf + __ldg(kp.v_conf + v)) : 0.0f;
-      float ex[6];
-      ex[eAh1] = att + x[0] + cf;
-      ex[eBh1] = -def - x[2] - cf;
-      ex[eBa1] = -def - x[3] - cf;
-      ex[eAa1] = att + x[1] + cf;
-      ex[eA0] = att + cf;
-      ex[eB0] = -def - cf;
-      const uint32_t r = (uint32_t)v * kRowBytes;
-      if (kp.has1) {
-        sts64(tab + kp.tabP1 + r, expf(ex[eAh1]), expf(ex[eBh1]));
-        sts64(tab + kp.tabQ1 + r, expf(ex[eBa1]), expf(ex[eAa1]));
-      }
-      if (kp.has0) sts64(tab + kp.tabP0 + r, expf(ex[eA0]), expf(ex[eB0]));
-      float g[6];
+        if (i < ndec) x[i] = fmaf(hy.sig[i], ln.ld(o.dec[i] + t), hy.mu[i]);
+      if (!(__ldg(kp.team_flags + t) & 1) && ln.active) {  // team without matches: no list will write its slots
+        *ln.g(o.za + t) = 0.0f;
+        *ln.g(o.zd + t) = 0.0f;
 #pragma unroll
-      for (int e = 0; e < 6; e++) {
-        g[e] = CLIP ? 0.0f : __ldg(kp.yexp + (size_t)v * 6 + e);
-        acc.lp = fmaf(g[e], ex[e], acc.lp);
+        for (int i = 0; i < 4; i++)
+          if (i < ndec) *ln.g(o.dec[i] + t) = 0.0f;
       }
-      apply_vteam<KMAX>(kp, hy, acc, ln, true, v, g, v == v0, true, p_za, p_zd, p_dec);
+      const int v0 = __ldg(kp.team_vptr + t), v1 = __ldg(kp.team_vptr + t + 1);
+      for (int v = v0; v < v1; v++) {
+        const float cf = kp.Cf > 0 ? ln.ld(o.conf + __ldg(kp.v_conf + v)) : 0.0f;
+        float ex[6];
+        ex[eAh1] = att + x[0] + cf;
+        ex[eBh1] = -def - x[2] - cf;
+        ex[eBa1] = -def - x[3] - cf;
+        ex[eAa1] = att + x[1] + cf;
+        ex[eA0] = att + cf;
+        ex[eB0] = -def - cf;
+        const uint32_t r = (uint32_t)v * kRowBytes;
+        if (kp.has1) {
+          sts64(tab + kp.tabP1 + r, expf(ex[eAh1]), expf(ex[eBh1]));
+          sts64(tab + kp.tabQ1 + r, expf(ex[eBa1]), expf(ex[eAa1]));
+        }
+        if (kp.has0) sts64(tab + kp.tabP0 + r, expf(ex[eA0]), expf(ex[eB0]));
+        if (!CLIP) {  // static sum of w * y * log(lambda): linear in the exponents
+#pragma unroll
+          for (int e = 0; e < 6; e++) lp_acc = fmaf(__ldg(kp.yexp + (size_t)v * 6 + e), ex[e], lp_acc);
+        }
+      }
     }
   }
   __syncthreads();
 
   // ---- phase 1 ----------------------------------------------------------------------------------
   float best[3] = {0.0f, 0.0f, 0.0f};
-  int bestl[3] = {0, 0, 0};
+  uint32_t besth[3] = {0u, 0u, 0u};  // byte offset (in stream1) of the header of the list that holds the maximum
   {
-    float g[6];
-    const float zero4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    const int l0 = __ldg(kp.warp_l1 + warp), l1 = __ldg(kp.warp_l1 + warp + 1);
-    List Lnext = l0 < l1 ? load_list(kp.lists1 + l0) : List{};
-    for (int li = l0; li < l1; li++) {
-      const List L = Lnext;
-      if (li + 1 < l1) Lnext = load_list(kp.lists1 + li + 1);  // hide the header's latency behind this list
-      if (L.flags & kListFirst) {
+    float g[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f}, cacc = 0.0f;
+    while (stream.pos < stream.total) {
+      const uint32_t hoff = b1_0 + stream.pos;
+      const Hdr L = stream.header();
+      if (L.flags & kTeamFirst) {
 #pragma unroll
         for (int e = 0; e < 6; e++) g[e] = 0.0f;
       }
@@ -372,7 +329,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
         float ax0 = 0.0f, ay0 = 0.0f, ax1 = 0.0f, ay1 = 0.0f;
         if (home) {
           float m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
-          stream.consume(L.n * (uint32_t)sizeof(Entry), [&](uint32_t addr) {
+          stream.consume(L.n0 * ESZ, [&](uint32_t addr) {
             const uint4 q = lds128u(addr);  // two entries
             const float2 a = lds64(tab + q.x), b = lds64(tab + q.z);
             const float wa = __uint_as_float(q.y), wb = __uint_as_float(q.w);
@@ -383,11 +340,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
             m3 = fmaxf(m3, fmaxf(a.x * a.y, b.x * b.y));
           });
           const float v0 = own.x * m1, v1 = own.y * m2, v2 = (own.x * own.y) * m3;
-          if (v0 > best[0]) { best[0] = v0; bestl[0] = li; }
-          if (v1 > best[1]) { best[1] = v1; bestl[1] = li; }
-          if (v2 > best[2]) { best[2] = v2; bestl[2] = li; }
+          if (v0 > best[0]) { best[0] = v0; besth[0] = hoff; }
+          if (v1 > best[1]) { best[1] = v1; besth[1] = hoff; }
+          if (v2 > best[2]) { best[2] = v2; besth[2] = hoff; }
         } else {
-          stream.consume(L.n * (uint32_t)sizeof(Entry), [&](uint32_t addr) {
+          stream.consume(L.n0 * ESZ, [&](uint32_t addr) {
             const uint4 q = lds128u(addr);
             const float2 a = lds64(tab + q.x), b = lds64(tab + q.z);
             const float wa = __uint_as_float(q.y), wb = __uint_as_float(q.w);
@@ -396,70 +353,61 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
           });
         }
         const float SX = own.x * (ax0 + ax1), SY = own.y * (ay0 + ay1);
-        acc.lp -= 0.5f * (SX + SY);  // every match is in two lists
+        lp_acc -= 0.5f * (SX + SY);  // every match is in two lists
         gx = -SX;
         gy = -SY;
       } else {
         gx = gy = 0.0f;
-        if (home) {
-          float lp2 = 0.0f, lpw = 0.0f, m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
-          stream.consume(L.n * (uint32_t)sizeof(EntryClip), [&](uint32_t addr) {
-            const uint4 q = lds128u(addr);  // one entry: off, w, w*y_x, w*y_y
-            const float2 a = lds64(tab + q.x);
-            const float w = __uint_as_float(q.y), wyx = __uint_as_float(q.z), wyy = __uint_as_float(q.w);
-            const float X = own.x * a.x, Y = own.y * a.y;
-            const float Xc = fminf(X, 15.0f), Yc = fminf(Y, 15.0f);
+        float lp2 = 0.0f, lpw = 0.0f, m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
+        stream.consume(L.n0 * ESZ, [&](uint32_t addr) {
+          const uint4 q = lds128u(addr);  // one entry: off, w, w*y_x, w*y_y
+          const float2 a = lds64(tab + q.x);
+          const float w = __uint_as_float(q.y), wyx = __uint_as_float(q.z), wyy = __uint_as_float(q.w);
+          const float X = own.x * a.x, Y = own.y * a.y;
+          const float Xc = fminf(X, 15.0f), Yc = fminf(Y, 15.0f);
+          if (home) {  // warp-uniform
             lp2 = fmaf(wyx, lg2_approx(Xc), lp2);
             lp2 = fmaf(wyy, lg2_approx(Yc), lp2);
             lpw = fmaf(w, Xc + Yc, lpw);
             m1 = fmaxf(m1, Xc);
             m2 = fmaxf(m2, Yc);
             m3 = fmaxf(m3, Xc * Yc);
-            gx += X < 15.0f ? fmaf(-w, X, wyx) : 0.0f;
-            gy += Y < 15.0f ? fmaf(-w, Y, wyy) : 0.0f;
-          });
-          acc.lp += fmaf(lp2, kLn2, -lpw);
-          if (m1 > best[0]) { best[0] = m1; bestl[0] = li; }
-          if (m2 > best[1]) { best[1] = m2; bestl[1] = li; }
-          if (m3 > best[2]) { best[2] = m3; bestl[2] = li; }
-        } else {
-          stream.consume(L.n * (uint32_t)sizeof(EntryClip), [&](uint32_t addr) {
-            const uint4 q = lds128u(addr);
-            const float2 a = lds64(tab + q.x);
-            const float w = __uint_as_float(q.y), wyx = __uint_as_float(q.z), wyy = __uint_as_float(q.w);
-            const float X = own.x * a.x, Y = own.y * a.y;
-            gx += X < 15.0f ? fmaf(-w, X, wyx) : 0.0f;
-            gy += Y < 15.0f ? fmaf(-w, Y, wyy) : 0.0f;
-          });
+          }
+          gx += X < 15.0f ? fmaf(-w, X, wyx) : 0.0f;
+          gy += Y < 15.0f ? fmaf(-w, Y, wyy) : 0.0f;
+        });
+        if (home) {
+          lp_acc += fmaf(lp2, kLn2, -lpw);
+          if (m1 > best[0]) { best[0] = m1; besth[0] = hoff; }
+          if (m2 > best[1]) { best[1] = m2; besth[1] = hoff; }
+          if (m3 > best[2]) { best[2] = m3; besth[2] = hoff; }
         }
       }
       add_own(g, L.kind, gx, gy);
-      if (L.flags & kListLast) apply_vteam<KMAX>(kp, hy, acc, ln, true, (int)L.vteam, g, false, false, 0.0f, 0.0f, zero4);
+      if (kp.Cf > 0) {
+        cacc += L.kind == kH1 ? gx - gy : gy - gx;  // d/d (A - B) of the virtual team
+        if (L.flags & kVteamLast) {
+          if (ln.active) ln.sc[(long long)L.vteam * kp.Cpad] = cacc;
+          cacc = 0.0f;
+        }
+      }
+      if (L.flags & kTeamLast) put_raw<false>(kp, ln, (int)L.team, g, hacc);
     }
   }
-  {  // start fetching this warp's tau entries while the other warps finish phase 1
-    const int e0 = __ldg(kp.warp_e2 + warp), e1 = __ldg(kp.warp_e2 + warp + 1);
-    stream.begin(kp.ent2 + e0, (uint32_t)(e1 - e0) * (uint32_t)sizeof(Entry));
-  }
+  const uint32_t b2_0 = __ldg(kp.warp_b2 + warp), b2_1 = __ldg(kp.warp_b2 + warp + 1);
+  stream.begin(kp.stream2 + b2_0, b2_1 - b2_0);  // tau lists start streaming in during the bounds step
+
   // ---- bounds (bpl/_util.py:17-31) ------------------------------------------------------------------
 #pragma unroll
-  for (int q = 0; q < 3; q++) {
-    red[(warp * kRedRows + q) * 32 + lane] = best[q];
-    red[(warp * kRedRows + 3 + q) * 32 + lane] = __int_as_float(bestl[q]);
-  }
+  for (int q = 0; q < 3; q++)
+    if (best[q] > 0.0f)
+      atomicMax(red_best + q * 32 + lane, ((unsigned long long)__float_as_uint(best[q]) << 32) | besth[q]);
   __syncthreads();
 #pragma unroll
   for (int q = 0; q < 3; q++) {
-    best[q] = 0.0f;
-    bestl[q] = 0;
-  }
-  for (int w = 0; w < W; w++) {
-#pragma unroll
-    for (int q = 0; q < 3; q++) {
-      const float v = red[(w * kRedRows + q) * 32 + lane];
-      const int l = __float_as_int(red[(w * kRedRows + 3 + q) * 32 + lane]);
-      if (v > best[q]) { best[q] = v; bestl[q] = l; }
-    }
+    const unsigned long long b = red_best[q * 32 + lane];
+    best[q] = __uint_as_float((uint32_t)(b >> 32));
+    besth[q] = (uint32_t)b;
   }
   const float Lam = fmaxf(best[0], best[1]);
   const int qlam = best[0] >= best[1] ? 0 : 1;
@@ -468,39 +416,73 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
   const float r = sigmoid_clipped(ln.ld(o.raw));
   const float cc = fmaf(r, UB - LB, LB);
 
+  // ---- arg-max search: warp w looks at entries w, w+W, ... of each chain's two arg-max lists -----------
+#pragma unroll 1
+  for (int which = 0; which < 2; which++) {
+    const bool need = which == 0 || best[2] > 1.0f;  // UB = 1: no dependence on the rates
+    const uint32_t hoff = which == 0 ? (qlam == 0 ? besth[0] : besth[1]) : besth[2];
+    const float target = which == 0 ? Lam : best[2];
+    const int q = which == 0 ? qlam : 2;
+    const Hdr L = unpack_hdr(__ldg(reinterpret_cast<const uint4*>(kp.stream1 + hoff)));
+    const uint32_t n = need ? L.n0 : 0u;
+    float2 own = lds64(tab + L.own_off);
+    if (L.kind >= kH0) { const float s = own.x; own.x = own.y; own.y = s; }
+    const unsigned char* ent = kp.stream1 + hoff + 16;
+    const uint32_t nmax = __reduce_max_sync(kFull, n);
+    uint32_t found = 0xffffffffu;
+#pragma unroll 4
+    for (uint32_t i = warp; i < nmax; i += W) {
+      if (i < n) {
+        const uint32_t off = __ldg(reinterpret_cast<const uint32_t*>(ent + (size_t)i * ESZ));
+        const float2 a = lds64(tab + off);
+        float val;
+        if (CLIP) {
+          const float Xc = fminf(own.x * a.x, 15.0f), Yc = fminf(own.y * a.y, 15.0f);
+          val = q == 0 ? Xc : (q == 1 ? Yc : Xc * Yc);
+        } else {
+          val = q == 0 ? own.x * a.x : (q == 1 ? own.y * a.y : (own.x * own.y) * (a.x * a.y));
+        }
+        if (val == target) found = min(found, (i << 24) | off);
+      }
+    }
+    if (found != 0xffffffffu) atomicMin(red_found + which * 32 + lane, found);
+  }
+
   // ---- phase 2: tau terms (bpl/_util.py:54-91) -----------------------------------------------------
   float gc = 0.0f;
   {
-    float g[6];
-    const float zero4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    const int l0 = __ldg(kp.warp_l2 + warp), l1 = __ldg(kp.warp_l2 + warp + 1);
-    List Lnext = l0 < l1 ? load_list(kp.lists2 + l0) : List{};
-    for (int li = l0; li < l1; li++) {
-      const List L = Lnext;
-      if (li + 1 < l1) Lnext = load_list(kp.lists2 + li + 1);
-      if (L.flags & kListFirst) {
+    float g[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f}, cacc = 0.0f;
+    while (stream.pos < stream.total) {
+      const Hdr L = stream.header();
+      if (L.flags & kTeamFirst) {
 #pragma unroll
         for (int e = 0; e < 6; e++) g[e] = 0.0f;
       }
       float2 own = lds64(tab + L.own_off);
       if (L.kind >= kH0) { const float s = own.x; own.x = own.y; own.y = s; }
       const bool home = (L.kind & 1) == 0;
+      const float Pxy = own.x * own.y;
       float uxy = 0.0f, ux = 0.0f, uy = 0.0f, lt = 0.0f;     // unmasked (d/d corr_coef)
       float sxy_x = 0.0f, sxy_y = 0.0f, sx = 0.0f, sy = 0.0f;  // masked by "rate not clipped"
       // one entry = (opponent row offset, w); the ring is read two entries (16 bytes) at a time
       auto xy = [&](uint32_t off, float w) {  // tau = 1 - c X Y
         const float2 a = lds64(tab + off);
-        const float Xr = own.x * a.x, Yr = own.y * a.y;
-        const float X = CLIP ? fminf(Xr, 15.0f) : Xr, Y = CLIP ? fminf(Yr, 15.0f) : Yr;
-        const float t = X * Y;
-        const float tau = fmaxf(fmaf(-cc, t, 1.0f), 0.0f);
-        const float val = (w * t) * rcp_approx(tau);
-        uxy += val;
+        float t;
         if (CLIP) {
+          const float Xr = own.x * a.x, Yr = own.y * a.y;
+          t = fminf(Xr, 15.0f) * fminf(Yr, 15.0f);
+          const float tau = fmaxf(fmaf(-cc, t, 1.0f), 0.0f);
+          const float val = (w * t) * rcp_approx(tau);
+          uxy += val;
           sxy_x += Xr < 15.0f ? val : 0.0f;
           sxy_y += Yr < 15.0f ? val : 0.0f;
+          if (home) lt = fmaf(w, lg2_approx(tau), lt);
+        } else {
+          t = Pxy * (a.x * a.y);
+          const float tau = fmaxf(fmaf(-cc, t, 1.0f), 0.0f);
+          uxy = fmaf(w * t, rcp_approx(tau), uxy);
+          if (home) lt = fmaf(w, lg2_approx(tau), lt);
         }
-        if (home) lt = fmaf(w, lg2_approx(tau), lt);
       };
       auto one = [&](uint32_t off, float w, bool is_x, float& u, float& s) {  // tau = 1 + c X  (or Y)
         const float2 a = lds64(tab + off);
@@ -512,206 +494,217 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
         if (CLIP) s += Rr < 15.0f ? val : 0.0f;
         if (home) lt = fmaf(w, lg2_approx(tau), lt);
       };
-      stream.consume((uint32_t)L.n_xy * (uint32_t)sizeof(Entry), [&](uint32_t addr) {
+      stream.consume(L.n0 * (uint32_t)sizeof(Entry), [&](uint32_t addr) {
         const uint4 q = lds128u(addr);
         xy(q.x, __uint_as_float(q.y));
         xy(q.z, __uint_as_float(q.w));
       });
-      stream.consume((uint32_t)L.n_x * (uint32_t)sizeof(Entry), [&](uint32_t addr) {
+      stream.consume(L.n1 * (uint32_t)sizeof(Entry), [&](uint32_t addr) {
         const uint4 q = lds128u(addr);
         one(q.x, __uint_as_float(q.y), true, ux, sx);
         one(q.z, __uint_as_float(q.w), true, ux, sx);
       });
-      stream.consume((uint32_t)L.n_y * (uint32_t)sizeof(Entry), [&](uint32_t addr) {
+      stream.consume(L.n2 * (uint32_t)sizeof(Entry), [&](uint32_t addr) {
         const uint4 q = lds128u(addr);
         one(q.x, __uint_as_float(q.y), false, uy, sy);
         one(q.z, __uint_as_float(q.w), false, uy, sy);
       });
       if (!CLIP) { sxy_x = sxy_y = uxy; sx = ux; sy = uy; }
       if (home) {
-        acc.lp = fmaf(lt, kLn2, acc.lp);
+        lp_acc = fmaf(lt, kLn2, lp_acc);
         gc += ux + uy - uxy;
       }
-      add_own(g, L.kind, cc * (sx - sxy_x), cc * (sy - sxy_y));
-      if (L.flags & kListLast) apply_vteam<KMAX>(kp, hy, acc, ln, true, (int)L.vteam, g, false, false, 0.0f, 0.0f, zero4);
+      const float gx = cc * (sx - sxy_x), gy = cc * (sy - sxy_y);
+      add_own(g, L.kind, gx, gy);
+      if (kp.Cf > 0) {
+        cacc += L.kind == kH1 ? gx - gy : gy - gx;
+        if (L.flags & kVteamLast) {
+          if (ln.active) red_add(ln.sc + (long long)L.vteam * kp.Cpad, cacc);
+          cacc = 0.0f;
+        }
+      }
+      if (L.flags & kTeamLast) put_raw<true>(kp, ln, (int)L.team, g, hacc);
     }
   }
-  red[(warp * kRedRows + 6) * 32 + lane] = gc;
+  red_gc[warp * 32 + lane] = gc;
   __syncthreads();
   gc = 0.0f;
-  for (int w = 0; w < W; w++) gc += red[(w * kRedRows + 6) * 32 + lane];
+  for (int w = 0; w < W; w++) gc += red_gc[w * 32 + lane];
   {  // the 1-1 matches: tau = 1 - c for all of them
     const float t11 = fmaxf(1.0f - cc, 0.0f);
     gc -= kp.w11 / t11;
-    if (warp == 0 && kp.w11 != 0.0f) acc.lp = fmaf(kp.w11, logf(t11), acc.lp);
+    if (warp == 0 && kp.w11 != 0.0f) lp_acc = fmaf(kp.w11, logf(t11), lp_acc);
   }
 
-  // ---- arg-max fix-up: chains l = warp, warp+W, ... ----------------------------
-  {
-    const int my_l[2] = {qlam == 0 ? bestl[0] : bestl[1], bestl[2]};
-    const float my_t[2] = {Lam, best[2]};
-    const float zero4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    for (int l = warp; l < kChains; l += W) {
-      const uint32_t tab_l = smem_u32(smem) + l * 8;
+  // ---- arg-max fix-up: warp 0, every chain in its own lane -----------------------
+  if (warp == 0 && ln.active) {
 #pragma unroll 1
-      for (int which = 0; which < 2; which++) {
-        const int li = __shfl_sync(0xffffffffu, my_l[which], l);
-        const float target = __shfl_sync(0xffffffffu, my_t[which], l);
-        const int q = which == 0 ? __shfl_sync(0xffffffffu, qlam, l) : 2;
-        if (which == 1 && !(target > 1.0f)) continue;  // UB = 1: no dependence on the rates
-        const List L = load_list(kp.lists1 + li);
-        float2 own = lds64(tab_l + L.own_off);
-        if (L.kind >= kH0) { const float s = own.x; own.x = own.y; own.y = s; }
-        uint32_t f_off = 0;
-        float f_x = 0.0f, f_y = 0.0f;
-        bool found = false;
-        for (uint32_t i0 = 0; i0 < L.n && !found; i0 += 32) {
-          const uint32_t i = i0 + lane;
-          uint32_t off = 0;
-          float X = 0.0f, Y = 0.0f, val = -1.0f;
-          if (i < L.n) {
-            off = CLIP ? __ldg(&reinterpret_cast<const EntryClip*>(kp.ent1)[L.ent + i].off)
-                       : __ldg(&reinterpret_cast<const Entry*>(kp.ent1)[L.ent + i].off);
-            const float2 a = lds64(tab_l + off);
-            X = own.x * a.x;
-            Y = own.y * a.y;
-            if (CLIP) {
-              const float Xc = fminf(X, 15.0f), Yc = fminf(Y, 15.0f);
-              val = q == 0 ? Xc : (q == 1 ? Yc : Xc * Yc);
-            } else {
-              val = q == 0 ? X : (q == 1 ? Y : (own.x * own.y) * (a.x * a.y));
-            }
-          }
-          const unsigned hit = __ballot_sync(0xffffffffu, val == target);
-          if (hit) {
-            const int src = __ffs(hit) - 1;
-            f_off = __shfl_sync(0xffffffffu, off, src);
-            f_x = __shfl_sync(0xffffffffu, X, src);
-            f_y = __shfl_sync(0xffffffffu, Y, src);
-            found = true;
-          }
-        }
-        if (!found) continue;  // cannot happen (same arithmetic as phase 1); be safe
-        const bool h1 = L.kind == kH1;
-        const int opp_v = (int)((f_off - (h1 ? kp.tabQ1 : kp.tabP0)) / kRowBytes);
-        const int own_v = (int)L.vteam;
-        // weights of the two log-rates of the arg-max match (zero through a clipped rate)
-        float wx = 0.0f, wy = 0.0f;
-        if (which == 0) {
-          const float wgt = gc * (1.0f - r) / Lam;  // dc/dLB * dLB/d eta
-          if (q == 0) wx = (!CLIP || f_x < 15.0f) ? wgt : 0.0f;
-          else wy = (!CLIP || f_y < 15.0f) ? wgt : 0.0f;
-        } else {
-          const float wgt = -gc * r / best[2];  // dc/dUB * dUB/d eta (UB = 1 / max lambda_h lambda_a)
-          wx = (!CLIP || f_x < 15.0f) ? wgt : 0.0f;
-          wy = (!CLIP || f_y < 15.0f) ? wgt : 0.0f;
-        }
-        const int ox = h1 ? eAh1 : eB0, oy = h1 ? eBh1 : eA0;  // own exponents of X, Y
-        const int px = h1 ? eBa1 : eA0, py = h1 ? eAa1 : eB0;  // opponent's
-#pragma unroll 1
-        for (int side = 0; side < 2; side++) {
-          const int sx = side ? px : ox, sy = side ? py : oy;
-          float g[6];
-#pragma unroll
-          for (int e = 0; e < 6; e++) g[e] = (e == sx ? wx : 0.0f) + (e == sy ? wy : 0.0f);
-          apply_vteam<KMAX>(kp, hy, acc, ln, lane == l, side ? opp_v : own_v, g, false, false, 0.0f, 0.0f, zero4);
-        }
+    for (int which = 0; which < 2; which++) {
+      const uint32_t packed = red_found[which * 32 + lane];
+      if (packed == 0xffffffffu) continue;  // UB = 1 (or nothing matched: cannot happen, same arithmetic as phase 1)
+      const uint32_t f_off = packed & 0xffffffu;
+      const uint32_t hoff = which == 0 ? (qlam == 0 ? besth[0] : besth[1]) : besth[2];
+      const Hdr L = unpack_hdr(__ldg(reinterpret_cast<const uint4*>(kp.stream1 + hoff)));
+      float2 own = lds64(tab + L.own_off);
+      if (L.kind >= kH0) { const float s = own.x; own.x = own.y; own.y = s; }
+      const float2 a = lds64(tab + f_off);
+      const float f_x = own.x * a.x, f_y = own.y * a.y;
+      const bool h1 = L.kind == kH1;
+      const int opp_v = (int)((f_off - (h1 ? kp.tabQ1 : kp.tabP0)) / kRowBytes);
+      const int own_v = (int)L.vteam;
+      // weights of the two log-rates of the arg-max match (zero through a clipped rate)
+      float wx = 0.0f, wy = 0.0f;
+      if (which == 0) {
+        const float wgt = gc * (1.0f - r) / Lam;  // dc/dLB * dLB/d eta
+        if (qlam == 0) wx = (!CLIP || f_x < 15.0f) ? wgt : 0.0f;
+        else wy = (!CLIP || f_y < 15.0f) ? wgt : 0.0f;
+      } else {
+        const float wgt = -gc * r / best[2];  // dc/dUB * dUB/d eta (UB = 1 / max lambda_h lambda_a)
+        wx = (!CLIP || f_x < 15.0f) ? wgt : 0.0f;
+        wy = (!CLIP || f_y < 15.0f) ? wgt : 0.0f;
       }
+      add_exponent(kp, ln, own_v, h1 ? eAh1 : eB0, wx, hacc);  // own exponents of X, Y
+      add_exponent(kp, ln, own_v, h1 ? eBh1 : eA0, wy, hacc);
+      add_exponent(kp, ln, opp_v, h1 ? eBa1 : eA0, wx, hacc);  // the opponent's
+      add_exponent(kp, ln, opp_v, h1 ? eAa1 : eB0, wy, hacc);
     }
   }
-  __syncthreads();  // tables are dead from here on; fix-ups of all chains are in memory
+  __syncthreads();  // tables are dead from here on; every raw slot is final
 
-  // ---- confederation gradients -------------------------------------------------------------------------
+  // ---- team pass: raw slots -> parameter gradients, priors, hyper-parameter sums ---------------------------
+  const bool has_rho = !dc;
+  float u = 0.5f, rho = 0.0f, inv_s2 = 1.0f;
+  if (has_rho) {
+    u = sigmoid_clipped(ln.ld(o.u));
+    rho = 2.0f * u - 1.0f;
+    inv_s2 = 1.0f / (1.0f - rho * rho);
+  }
+  float a_mu_d = 0.0f, a_ls_a = 0.0f, a_ls_d = 0.0f, a_rho = 0.0f, a_mu[4], a_ls[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) a_mu[i] = a_ls[i] = 0.0f;
+  {
+    const Hyp hy = load_hyp(kp, ln);
+    float* team_rows = reinterpret_cast<float*>(smem + kp.epi_team);
+    for (int t = warp; t < kp.T; t += W) {
+      const float za = ln.ld(o.za + t), zd = ln.ld(o.zd + t);
+      const float4 ys = __ldg(reinterpret_cast<const float4*>(kp.yteam + (size_t)t * 8));
+      const float2 ys2 = __ldg(reinterpret_cast<const float2*>(kp.yteam + (size_t)t * 8 + 4));
+      const float ystat[6] = {ys.x, ys.y, ys.z, ys.w, ys2.x, ys2.y};
+      const float ra = ld_cg(ln.g(o.za + t)) + ystat[0];
+      const float rd = ld_cg(ln.g(o.zd + t)) + ystat[1];
+      float p_za, p_zd;
+      if (has_rho) {  // za ~ N(0,1), zd ~ N(rho za, sqrt(1-rho^2))  (extended_dixon_coles.py:165-174)
+        const float e = zd - rho * za;
+        const float es = e * inv_s2;
+        lp_acc -= 0.5f * (za * za + e * es);
+        p_za = -za + rho * es;
+        p_zd = -es;
+        a_rho += es * za - rho * es * es + rho * inv_s2;
+      } else {
+        lp_acc -= 0.5f * (za * za + zd * zd);
+        p_za = -za;
+        p_zd = -zd;
+      }
+      if (ln.active) {
+        *ln.g(o.za + t) = fmaf(hy.sig_a, ra, p_za);
+        *ln.g(o.zd + t) = fmaf(hy.sig_d, rd, p_zd);
+      }
+      a_ls_a = fmaf(hy.sig_a * za, ra, a_ls_a);
+      a_ls_d = fmaf(hy.sig_d * zd, rd, a_ls_d);
+      a_mu_d += rd;
+      if (dc) a_mu[0] += ystat[2];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        if (i < ndec) {
+          const float dec = ln.ld(o.dec[i] + t);
+          const float rx = ld_cg(ln.g(o.dec[i] + t)) + ystat[2 + i];
+          lp_acc -= 0.5f * dec * dec;
+          if (ln.active) *ln.g(o.dec[i] + t) = fmaf(hy.sig[i], rx, -dec);
+          a_mu[i] += rx;
+          a_ls[i] = fmaf(hy.sig[i] * dec, rx, a_ls[i]);
+        }
+      }
+      if (kp.K > 0) {  // rows for the covariate-coefficient pass
+        team_rows[(size_t)t * 64 + lane] = ra;
+        team_rows[(size_t)t * 64 + 32 + lane] = rd;
+      }
+    }
+    if (dc) a_mu[0] += hacc;
+  }
+  // confederation strengths: N(0,1) prior + sum over the virtual teams of the confederation
   for (int k = warp; k < kp.Cf; k += W) {
     const float cf = ln.ld(o.conf + k);
-    float s = -cf;  // N(0,1) prior
-    acc.lp -= 0.5f * cf * cf;
+    float s = __ldg(kp.yconf + k) - cf;
+    lp_acc -= 0.5f * cf * cf;
     const int j0 = __ldg(kp.conf_vptr + k), j1 = __ldg(kp.conf_vptr + k + 1);
-    for (int j = j0; j < j1; j++) s += ln.sc[(long long)__ldg(kp.conf_vlist + j) * kp.Cpad];
-    if (ln.active) ln.gr[(long long)(o.conf + k) * ln.sd] = s;
+    for (int j = j0; j < j1; j++) s += ld_cg(ln.sc + (long long)__ldg(kp.conf_vlist + j) * kp.Cpad);
+    if (ln.active) *ln.g(o.conf + k) = s;
   }
 
   // ---- cross-warp reduction of the hyper accumulators (table area is reused) ----------------------------
-  const int NH = hyper_rows(kp.K);
-  float* part = reinterpret_cast<float*>(smem);
+  float* part = reinterpret_cast<float*>(smem + kp.epi_part);
   {
-    float* p = part + (size_t)warp * NH * 32 + lane;
-    p[0 * 32] = acc.lp; p[1 * 32] = acc.mu_d; p[2 * 32] = acc.ls_a; p[3 * 32] = acc.ls_d;
+    float* p = part + (size_t)warp * kPartRows * 32 + lane;
+    p[0 * 32] = lp_acc; p[1 * 32] = a_mu_d; p[2 * 32] = a_ls_a; p[3 * 32] = a_ls_d;
 #pragma unroll
-    for (int i = 0; i < 4; i++) { p[(4 + i) * 32] = acc.mu[i]; p[(8 + i) * 32] = acc.ls[i]; }
-    p[12 * 32] = acc.rho;
-    if (KMAX > 0) {
-#pragma unroll
-      for (int k = 0; k < KMAX; k++)
-        if (k < kp.K) { p[(13 + k) * 32] = acc.ba[k]; p[(13 + kp.K + k) * 32] = acc.bd[k]; }
-    }
+    for (int i = 0; i < 4; i++) { p[(4 + i) * 32] = a_mu[i]; p[(8 + i) * 32] = a_ls[i]; }
+    p[12 * 32] = a_rho;
   }
   __syncthreads();
+  // covariate coefficients: d/d beta[k] = sum_t Xs[t,k] * d/d (att | def)[t]; N(0,1) prior
+  for (int task = warp; task < 2 * kp.K; task += W) {
+    const int k = task >> 1, isd = task & 1;
+    const float* rows = reinterpret_cast<const float*>(smem + kp.epi_team) + isd * 32 + lane;
+    const int d = (isd ? o.beta_d : o.beta_a) + k;
+    float s = -ln.ld(d);
+    for (int t = 0; t < kp.T; t++) s = fmaf(__ldg(kp.Xs + (size_t)t * kp.K + k), rows[(size_t)t * 64], s);
+    if (ln.active) *ln.g(d) = s;
+  }
   if (warp != 0) return;
   auto total = [&](int row) {
     float s = 0.0f;
-    for (int w = 0; w < W; w++) s += part[((size_t)w * NH + row) * 32 + lane];
+    for (int w = 0; w < W; w++) s += part[((size_t)w * kPartRows + row) * 32 + lane];
     return s;
   };
   float lp = total(0) + kp.const_term;
-  auto gstore = [&](int d, float v) { if (ln.active) ln.gr[(long long)d * ln.sd] = v; };
-  auto normal = [&](float x, float loc, float scale, int d, float extra) {
-    const float z = (x - loc) / scale;
-    lp += -0.5f * z * z - logf(scale) - kLogSqrt2Pi;
-    gstore(d, -z / scale + extra);
-  };
-  auto halfnormal_exp = [&](float sig, float scale, int d, float extra) {  // HalfNormal on exp(x) + Jacobian x
-    const float z = sig / scale;
-    lp += -0.5f * z * z - logf(scale) - kLogSqrt2Pi + kLn2 + ln.ld(d);
-    gstore(d, -z * z + 1.0f + extra);
-  };
-  const bool neu = kp.model == BPLX_NEUTRAL || kp.model == BPLX_NEUTRAL_WC;
-  const float std_scale = neu ? 0.5f : 1.0f;  // neutral_dixon_coles.py:138-139
-  normal(hy.mu_d, 0.0f, 1.0f, o.mean_defence, total(1));
-  halfnormal_exp(hy.sig_a, std_scale, o.log_std_attack, total(2));
-  halfnormal_exp(hy.sig_d, std_scale, o.log_std_defence, total(3));
-  if (!neu) {
-    normal(hy.mu[0], 0.1f, 0.2f, o.mean[0], total(4));
-    if (ext) halfnormal_exp(hy.sig[0], 1.0f, o.log_std[0], total(8));
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      normal(hy.mu[i], (i & 1) ? -0.1f : 0.1f, 0.2f, o.mean[i], total(4 + i));
-      halfnormal_exp(hy.sig[i], 1.0f, o.log_std[i], total(8 + i));
+  for (int h = 0; h < kp.nhyper; h++) {
+    const HyperDesc hd = kp.hyper[h];
+    const float x = ln.ld(hd.off);
+    const float acc = total(hd.row);
+    float gval;
+    if (hd.kind == 0) {  // Normal(loc, scale)
+      const float z = (x - hd.loc) * hd.inv_scale;
+      lp -= 0.5f * z * z;
+      gval = fmaf(-z, hd.inv_scale, acc);
+    } else {  // HalfNormal(scale) on exp(x) + Jacobian x
+      const float z = expf(x) * hd.inv_scale;
+      lp += fmaf(-0.5f * z, z, x);
+      gval = fmaf(-z, z, 1.0f) + acc;
     }
+    if (ln.active) *ln.g(hd.off) = gval;
   }
-  if (KMAX > 0) {
-#pragma unroll
-    for (int k = 0; k < KMAX; k++) {
-      if (k < kp.K) {
-        normal(beta_a[k], 0.0f, 1.0f, o.beta_a + k, total(13 + k));
-        normal(beta_d[k], 0.0f, 1.0f, o.beta_d + k, total(13 + kp.K + k));
-      }
-    }
+  for (int k = 0; k < kp.K; k++) {
+    const float ba = ln.ld(o.beta_a + k), bd = ln.ld(o.beta_d + k);
+    lp -= 0.5f * (ba * ba + bd * bd);
   }
-  // per-team constants of the standardised pair and the decentred sites
-  lp -= (float)kp.T * (2.0f + (float)ndec) * kLogSqrt2Pi;
-  lp -= (float)kp.Cf * kLogSqrt2Pi;
-  if (has_rho) {  // u ~ Beta(2,4) + sigmoid Jacobian; rho = 2u - 1
-    lp += 0.5f * (float)kp.T * logf(hy.inv_s2);
-    const float lu = logf(u), l1u = logf(1.0f - u);
-    lp += 2.0f * lu + 4.0f * l1u + 2.99573227355399099f;  // log 20
-    gstore(o.u, 2.0f - 6.0f * u + total(12) * 2.0f * u * (1.0f - u));
+  if (has_rho) {  // u ~ Beta(2,4) + sigmoid Jacobian; rho = 2u - 1; sum_t -log sqrt(1 - rho^2)
+    lp += 0.5f * (float)kp.T * logf(inv_s2);
+    lp += 2.0f * logf(u) + 4.0f * logf(1.0f - u);
+    if (ln.active) *ln.g(o.u) = 2.0f - 6.0f * u + total(12) * 2.0f * u * (1.0f - u);
   }
-  {  // corr_coef_raw ~ Beta(2,2) + Jacobian; corr_coef = LB + r (UB - LB)
-    lp += 2.0f * (logf(r) + logf(1.0f - r)) + 1.79175946922805500f;  // log 6
-    gstore(o.raw, 2.0f * (1.0f - 2.0f * r) + gc * r * (1.0f - r) * (UB - LB));
-  }
+  // corr_coef_raw ~ Beta(2,2) + Jacobian; corr_coef = LB + r (UB - LB)
+  lp += 2.0f * (logf(r) + logf(1.0f - r));
   if (ln.active) {
+    *ln.g(o.raw) = 2.0f * (1.0f - 2.0f * r) + gc * r * (1.0f - r) * (UB - LB);
     kp.lp[chain] = lp;
     if (kp.corr_coef) kp.corr_coef[chain] = cc;
   }
 }
 
 // ---- host launcher --------------------------------------------------------------------------------------
-template <bool CLIP, int KMAX>
+template <bool CLIP>
 static int launch_t(const KernelParams& kp, cudaStream_t stream, bool set_attr) {
-  auto* fn = &logdensity_kernel<CLIP, KMAX>;
+  auto* fn = &logdensity_kernel<CLIP>;
   if (set_attr) {
     BPLX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return BPLX_OK;
@@ -723,12 +716,11 @@ static int launch_t(const KernelParams& kp, cudaStream_t stream, bool set_attr) 
   return BPLX_OK;
 }
 
-static int dispatch(const KernelParams& kp, cudaStream_t stream, bool set_attr) {
-  if (kp.clip) return kp.K > 0 ? launch_t<true, kMaxCov>(kp, stream, set_attr) : launch_t<true, 0>(kp, stream, set_attr);
-  return kp.K > 0 ? launch_t<false, kMaxCov>(kp, stream, set_attr) : launch_t<false, 0>(kp, stream, set_attr);
+int logdensity_set_attributes(const KernelParams& kp) {
+  return kp.clip ? launch_t<true>(kp, nullptr, true) : launch_t<false>(kp, nullptr, true);
 }
-
-int logdensity_set_attributes(const KernelParams& kp) { return dispatch(kp, nullptr, true); }
-int launch_logdensity(const KernelParams& kp, cudaStream_t stream) { return dispatch(kp, stream, false); }
+int launch_logdensity(const KernelParams& kp, cudaStream_t stream) {
+  return kp.clip ? launch_t<true>(kp, stream, false) : launch_t<false>(kp, stream, false);
+}
 
 }  // namespace bplx

@@ -96,7 +96,7 @@ int make_layout(int model, int T, int K, int Cf, ThetaOffsets* o, std::string* s
 
 }  // namespace
 
-int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err) {
+int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err, int force_warps) {
   const int model = d.model, M = d.num_matches, T = d.num_teams, K = d.num_covariates;
   const bool wc = model == BPLX_NEUTRAL_WC;
   const bool neutral = wc || model == BPLX_NEUTRAL;
@@ -122,7 +122,7 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err) {
       FAIL(BPLX_E_INVALID, "team index out of range at match %d", m);
     if (wc && (d.home_conf[m] >= Cf || d.away_conf[m] >= Cf))
       FAIL(BPLX_E_INVALID, "confederation index out of range at match %d", m);
-    if (d.weights && !(d.weights[m] >= 0.0f) )
+    if (d.weights && !(d.weights[m] >= 0.0f && d.weights[m] <= 3.0e38f))
       FAIL(BPLX_E_INVALID, "weights must be finite and non-negative (match %d)", m);
   }
 
@@ -133,7 +133,41 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err) {
   kp.K = K;
   kp.Cf = Cf;
   kp.clip = model == BPLX_EXTENDED;
+  kp.ndec = model == BPLX_DIXON_COLES ? 0 : (model == BPLX_EXTENDED ? 1 : 4);
   kp.D = make_layout(model, T, K, Cf, &kp.off, &P.layout);
+
+  // ---- scalar hyper-parameter sites and every theta-independent constant --------
+  const double kLogSqrt2Pi = 0.91893853320467274178, kLog2 = 0.69314718055994530942;
+  double const_term = 0.0;
+  {
+    int n = 0;
+    auto normal = [&](int off, int row, double loc, double scale) {
+      kp.hyper[n++] = HyperDesc{off, row, 0, (float)loc, (float)(1.0 / scale)};
+      const_term += -std::log(scale) - kLogSqrt2Pi;
+    };
+    auto halfnormal = [&](int off, int row, double scale) {
+      kp.hyper[n++] = HyperDesc{off, row, 1, 0.0f, (float)(1.0 / scale)};
+      const_term += -std::log(scale) - kLogSqrt2Pi + kLog2;
+    };
+    const double std_scale = neutral ? 0.5 : 1.0;  // neutral_dixon_coles.py:138-139
+    normal(kp.off.mean_defence, 1, 0.0, 1.0);
+    halfnormal(kp.off.log_std_attack, 2, std_scale);
+    halfnormal(kp.off.log_std_defence, 3, std_scale);
+    if (!neutral) {
+      normal(kp.off.mean[0], 4, 0.1, 0.2);
+      if (model == BPLX_EXTENDED) halfnormal(kp.off.log_std[0], 8, 1.0);
+    } else {
+      for (int i = 0; i < 4; i++) {
+        normal(kp.off.mean[i], 4 + i, (i & 1) ? -0.1 : 0.1, 0.2);
+        halfnormal(kp.off.log_std[i], 8 + i, 1.0);
+      }
+    }
+    kp.nhyper = n;
+    const_term -= (double)T * (2.0 + kp.ndec) * kLogSqrt2Pi;   // standardised pair + decentred sites, N(.,1)
+    const_term -= (double)(Cf + 2 * K) * kLogSqrt2Pi;          // confederation strengths, covariate coefficients
+    if (model != BPLX_DIXON_COLES) const_term += std::log(20.0);  // u ~ Beta(2, 4)
+    const_term += std::log(6.0);                                   // corr_coef_raw ~ Beta(2, 2)
+  }
 
   // ---- virtual teams -------------------------------------------------------------------------
   std::map<std::pair<int, int>, int> vmap;  // (team, conf) -> v, ordered by team then conf
@@ -153,6 +187,7 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err) {
     P.v_team.push_back((uint16_t)kv.first.first);
     P.v_conf.push_back((uint8_t)kv.first.second);
   }
+  if (V > 65535) FAIL(BPLX_E_UNSUPPORTED, "too many (team, confederation) pairs (%d)", V);
   kp.V = V;
   P.team_vptr.assign(T + 1, 0);
   for (int v = 0; v < V; v++) P.team_vptr[P.v_team[v] + 1]++;
@@ -189,18 +224,11 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err) {
   }
   const uint32_t table_bytes = off;
 
-  // ---- number of warps -------------------------------------------------------------------------
-  int W = 16;
-  if (const char* e = getenv("BPLX_NWARPS")) W = atoi(e);
-  if (W > kMaxWarps) W = kMaxWarps;
-  if (W < 1) W = 1;
-  kp.nwarps = W;
-
   // ---- per-match entries -----------------------------------------------------------------------
   // raw1[v][kind], raw2[v][kind]
   std::vector<std::vector<RawEntry>> raw1((size_t)V * 4), raw2((size_t)V * 4);
   std::vector<double> yexp((size_t)V * 6, 0.0);
-  double w11 = 0.0, const_term = 0.0;
+  double w11 = 0.0;
   for (int m = 0; m < M; m++) {
     const int h = d.home_team[m], a = d.away_team[m];
     const int hc = wc ? d.home_conf[m] : 0, ac = wc ? d.away_conf[m] : 0;
@@ -246,6 +274,25 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err) {
   kp.const_term = (float)const_term;
   P.yexp.resize(yexp.size());
   for (size_t i = 0; i < yexp.size(); i++) P.yexp[i] = (float)yexp[i];
+  {  // the same static sums folded per team / per confederation
+    std::vector<double> yt((size_t)T * 8, 0.0), yc((size_t)Cf, 0.0);
+    for (int v = 0; v < V; v++) {
+      const double* g = &yexp[(size_t)v * 6];
+      double* o = &yt[(size_t)P.v_team[v] * 8];
+      const double gA = g[eAh1] + g[eAa1] + g[eA0], gB = g[eBh1] + g[eBa1] + g[eB0];
+      o[0] += gA;
+      o[1] -= gB;
+      o[2] += g[eAh1];
+      o[3] += g[eAa1];
+      o[4] -= g[eBh1];
+      o[5] -= g[eBa1];
+      if (wc) yc[P.v_conf[v]] += gA - gB;
+    }
+    P.yteam.resize(yt.size());
+    for (size_t i = 0; i < yt.size(); i++) P.yteam[i] = (float)yt[i];
+    P.yconf.resize(yc.size());
+    for (size_t i = 0; i < yc.size(); i++) P.yconf[i] = (float)yc[i];
+  }
   P.Xs.assign(d.covariates ? d.covariates : nullptr, d.covariates ? d.covariates + (size_t)T * K : nullptr);
 
   auto own_off = [&](int v, int kind) -> uint32_t {
@@ -273,140 +320,164 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err) {
   };
   for (auto& v : raw1) merge(v);
   for (auto& v : raw2) merge(v);
+  P.team_flags.assign(T, 0);
+  for (int v = 0; v < V; v++)
+    for (int k = 0; k < 4; k++)
+      if (!raw1[(size_t)v * 4 + k].empty()) P.team_flags[P.v_team[v]] |= 1;
 
-  // ---- assign virtual teams to warps (longest processing time first) ---------------------------
-  // All virtual teams of a team go to the same warp: the owner thread of (team, chain) is the only
-  // one that read-modify-writes that team's gradient entries inside a phase.
-  auto assign = [&](const std::vector<std::vector<RawEntry>>& raw, double per_entry, double per_vteam,
-                    std::vector<std::vector<int>>* by_warp) {
+  // ---- assign teams to warps (longest processing time first) ------------------------------------
+  // All lists of a team go to the same warp: the owner thread of (team, chain) is the only one that
+  // touches that team's raw slots inside a phase.
+  auto team_costs = [&](const std::vector<std::vector<RawEntry>>& raw, double per_entry, double per_list,
+                        double per_team) {
     std::vector<double> cost(T, 0.0);
-    for (int v = 0; v < V; v++) {
-      size_t n = 0;
-      for (int k = 0; k < 4; k++) n += raw[(size_t)v * 4 + k].size();
-      if (n) cost[P.v_team[v]] += per_vteam + per_entry * (double)n;
-    }
+    for (int v = 0; v < V; v++)
+      for (int k = 0; k < 4; k++) {
+        const size_t n = raw[(size_t)v * 4 + k].size();
+        if (n) cost[P.v_team[v]] += per_list * (double)((n + kListMax - 1) / kListMax) + per_entry * (double)n;
+      }
+    for (int t = 0; t < T; t++)
+      if (cost[t] > 0.0) cost[t] += per_team;
+    return cost;
+  };
+  auto assign = [&](const std::vector<double>& cost, int W, std::vector<std::vector<int>>* teams) {
     std::vector<int> order(T);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
     std::vector<double> load(W, 0.0);
-    std::vector<std::vector<int>> teams(W);
+    teams->assign(W, {});
     for (int t : order) {
       if (cost[t] == 0.0) continue;
       int best = 0;
       for (int w = 1; w < W; w++)
         if (load[w] < load[best]) best = w;
       load[best] += cost[t];
-      teams[best].push_back(t);
+      (*teams)[best].push_back(t);
     }
-    by_warp->assign(W, {});
-    for (int w = 0; w < W; w++) {
-      std::sort(teams[w].begin(), teams[w].end());
-      for (int t : teams[w])
-        for (int v = P.team_vptr[t]; v < P.team_vptr[t + 1]; v++) {
-          size_t n = 0;
-          for (int k = 0; k < 4; k++) n += raw[(size_t)v * 4 + k].size();
-          if (n) (*by_warp)[w].push_back(v);
-        }
-    }
+    for (auto& v : *teams) std::sort(v.begin(), v.end());
+    return *std::max_element(load.begin(), load.end());
   };
+  // rough instruction counts per entry / list / team of the two phases
+  const std::vector<double> cost1 = team_costs(raw1, kp.clip ? 16.0 : 6.0, 40.0, 30.0);
+  const std::vector<double> cost2 = team_costs(raw2, 12.0, 60.0, 30.0);
+  int W = 16;
   std::vector<std::vector<int>> w1, w2;
-  assign(raw1, 1.0, 16.0, &w1);
-  assign(raw2, 3.0, 24.0, &w2);
-
-  // ---- emit lists -------------------------------------------------------------------------------
-  const uint32_t zero_row = (uint32_t)V * kRowBytes;
-  P.n1 = P.n2 = 0;
-  P.warp_l1.assign(W + 1, 0);
-  P.warp_l2.assign(W + 1, 0);
-  P.warp_e1.assign(W + 1, 0);
-  P.warp_e2.assign(W + 1, 0);
-  for (int w = 0; w < W; w++) {
-    // phase 1
-    for (int v : w1[w]) {
-      size_t first = P.lists1.size();
-      for (int k = 0; k < 4; k++) {
-        const auto& r = raw1[(size_t)v * 4 + k];
-        P.n1 += (long long)r.size();
-        for (size_t lo = 0; lo < r.size(); lo += kListMax) {
-          size_t hi = std::min(r.size(), lo + (size_t)kListMax);
-          List L{};
-          L.ent = (uint32_t)(kp.clip ? P.ent1c.size() : P.ent1.size());
-          L.own_off = own_off(v, k);
-          L.vteam = (uint32_t)v;
-          L.kind = (uint8_t)k;
-          uint32_t n = 0;
-          for (size_t i = lo; i < hi; i++, n++) {
-            uint32_t o = opp_base(k) + r[i].opp * kRowBytes;
-            if (kp.clip)
-              P.ent1c.push_back({o, (float)r[i].w, (float)r[i].wyx, (float)r[i].wyy});
-            else
-              P.ent1.push_back({o, (float)r[i].w});
-          }
-          if (!kp.clip && (n & 1)) {  // pad to an even count with a zero-row entry
-            P.ent1.push_back({opp_base(k) + zero_row, 0.0f});
-            n++;
-          }
-          L.n = n;
-          P.lists1.push_back(L);
-        }
-      }
-      if (P.lists1.size() > first) {
-        P.lists1[first].flags |= kListFirst;
-        P.lists1.back().flags |= kListLast;
-      }
-    }
-    P.warp_l1[w + 1] = (int32_t)P.lists1.size();
-    P.warp_e1[w + 1] = (int32_t)(kp.clip ? P.ent1c.size() : P.ent1.size());
-    // phase 2
-    for (int v : w2[w]) {
-      size_t first = P.lists2.size();
-      for (int k = 0; k < 4; k++) {
-        const auto& r = raw2[(size_t)v * 4 + k];
-        P.n2 += (long long)r.size();
-        for (size_t lo = 0; lo < r.size(); lo += kListMax) {
-          size_t hi = std::min(r.size(), lo + (size_t)kListMax);
-          List L{};
-          L.ent = (uint32_t)P.ent2.size();
-          L.own_off = own_off(v, k);
-          L.vteam = (uint32_t)v;
-          L.kind = (uint8_t)k;
-          uint16_t cnt[3] = {0, 0, 0};
-          size_t i = lo;
-          for (int c = 0; c < 3; c++) {
-            for (; i < hi && r[i].cls == c; i++) {
-              P.ent2.push_back({opp_base(k) + r[i].opp * kRowBytes, (float)r[i].w});
-              cnt[c]++;
-            }
-            if (cnt[c] & 1) {
-              P.ent2.push_back({opp_base(k) + zero_row, 0.0f});
-              cnt[c]++;
-            }
-          }
-          L.n_xy = cnt[0];
-          L.n_x = cnt[1];
-          L.n_y = cnt[2];
-          L.n = (uint32_t)cnt[0] + cnt[1] + cnt[2];
-          P.lists2.push_back(L);
-        }
-      }
-      if (P.lists2.size() > first) {
-        P.lists2[first].flags |= kListFirst;
-        P.lists2.back().flags |= kListLast;
-      }
-    }
-    P.warp_l2[w + 1] = (int32_t)P.lists2.size();
-    P.warp_e2[w + 1] = (int32_t)P.ent2.size();
+  if (force_warps <= 0) {
+    if (const char* e = getenv("BPLX_NWARPS")) force_warps = atoi(e);
   }
-  P.n1_padded = (long long)(kp.clip ? P.ent1c.size() : P.ent1.size());
-  P.n2_padded = (long long)P.ent2.size();
+  if (force_warps > 0) {
+    W = std::min(force_warps, kMaxWarps);
+  } else {
+    // the makespan of the slower warp decides; more warps than needed only cost shared memory
+    double best = 0.0;
+    for (int cand : {8, 12, 16, 20, 24}) {
+      if (cand > kMaxWarps) continue;
+      std::vector<std::vector<int>> t1, t2;
+      const double span = assign(cost1, cand, &t1) + assign(cost2, cand, &t2) + 4.0 * cand;
+      if (best == 0.0 || span < 0.97 * best) best = span, W = cand;
+    }
+  }
+  kp.nwarps = W;
+  assign(cost1, W, &w1);
+  assign(cost2, W, &w2);
+
+  // ---- emit the streams ---------------------------------------------------------------------------
+  const uint32_t zero_row = (uint32_t)V * kRowBytes;
+  auto put = [](std::vector<unsigned char>* s, const void* p, size_t n) {
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    s->insert(s->end(), b, b + n);
+  };
+  P.n1 = P.n2 = P.n1_padded = P.n2_padded = P.nlists1 = P.nlists2 = 0;
+  P.warp_b1.assign(W + 1, 0);
+  P.warp_b2.assign(W + 1, 0);
+  for (int phase = 1; phase <= 2; phase++) {
+    const auto& raw = phase == 1 ? raw1 : raw2;
+    const auto& by_warp = phase == 1 ? w1 : w2;
+    std::vector<unsigned char>& S = phase == 1 ? P.stream1 : P.stream2;
+    std::vector<uint32_t>& wb = phase == 1 ? P.warp_b1 : P.warp_b2;
+    S.clear();
+    for (int w = 0; w < W; w++) {
+      for (int t : by_warp[w]) {
+        size_t team_first_hdr = (size_t)-1, last_hdr = 0;
+        for (int v = P.team_vptr[t]; v < P.team_vptr[t + 1]; v++) {
+          size_t vteam_last_hdr = (size_t)-1;
+          for (int k = 0; k < 4; k++) {
+            const auto& r = raw[(size_t)v * 4 + k];
+            (phase == 1 ? P.n1 : P.n2) += (long long)r.size();
+            for (size_t lo = 0; lo < r.size(); lo += kListMax) {
+              const size_t hi = std::min(r.size(), lo + (size_t)kListMax);
+              ListHdr H{};
+              H.own_off = own_off(v, k);
+              H.vteam = (uint16_t)v;
+              H.kind = (uint8_t)k;
+              H.team = (uint16_t)t;
+              const size_t hdr_at = S.size();
+              put(&S, &H, sizeof H);
+              uint16_t cnt[3] = {0, 0, 0};
+              if (phase == 1) {
+                for (size_t i = lo; i < hi; i++, cnt[0]++) {
+                  const uint32_t o = opp_base(k) + r[i].opp * kRowBytes;
+                  if (kp.clip) {
+                    EntryClip e{o, (float)r[i].w, (float)r[i].wyx, (float)r[i].wyy};
+                    put(&S, &e, sizeof e);
+                  } else {
+                    Entry e{o, (float)r[i].w};
+                    put(&S, &e, sizeof e);
+                  }
+                }
+                if (!kp.clip && (cnt[0] & 1)) {  // pad to an even count with a zero-row entry
+                  Entry e{opp_base(k) + zero_row, 0.0f};
+                  put(&S, &e, sizeof e);
+                  cnt[0]++;
+                }
+                P.n1_padded += cnt[0];
+                P.nlists1++;
+              } else {
+                size_t i = lo;
+                for (int c = 0; c < 3; c++) {
+                  for (; i < hi && r[i].cls == c; i++, cnt[c]++) {
+                    Entry e{opp_base(k) + r[i].opp * kRowBytes, (float)r[i].w};
+                    put(&S, &e, sizeof e);
+                  }
+                  if (cnt[c] & 1) {
+                    Entry e{opp_base(k) + zero_row, 0.0f};
+                    put(&S, &e, sizeof e);
+                    cnt[c]++;
+                  }
+                }
+                P.n2_padded += cnt[0] + cnt[1] + cnt[2];
+                P.nlists2++;
+              }
+              ListHdr* hp = reinterpret_cast<ListHdr*>(&S[hdr_at]);
+              hp->n0 = cnt[0];
+              hp->n1 = cnt[1];
+              hp->n2 = cnt[2];
+              if (team_first_hdr == (size_t)-1) team_first_hdr = hdr_at;
+              vteam_last_hdr = last_hdr = hdr_at;
+            }
+          }
+          if (vteam_last_hdr != (size_t)-1) reinterpret_cast<ListHdr*>(&S[vteam_last_hdr])->flags |= kVteamLast;
+        }
+        if (team_first_hdr != (size_t)-1) {
+          reinterpret_cast<ListHdr*>(&S[team_first_hdr])->flags |= kTeamFirst;
+          reinterpret_cast<ListHdr*>(&S[last_hdr])->flags |= kTeamLast;
+        }
+      }
+      wb[w + 1] = (uint32_t)S.size();
+    }
+    if (S.empty()) S.resize(16, 0);  // never upload an empty buffer
+  }
 
   // ---- shared-memory carve-up --------------------------------------------------------------------
-  uint32_t epi = (uint32_t)W * hyper_rows(K) * 128u;
-  kp.tab_bytes = std::max(table_bytes, epi);
+  kp.epi_team = 0;
+  kp.epi_part = K > 0 ? (uint32_t)T * kRowBytes : 0u;
+  const uint32_t epi = kp.epi_part + (uint32_t)W * kPartRows * 128u;
+  kp.tab_bytes = (std::max(table_bytes, epi) + 127u) / 128u * 128u;
   kp.smem_ring = kp.tab_bytes;
   kp.smem_bar = kp.smem_ring + (uint32_t)W * kStages * kStageBytes;
   kp.smem_red = (kp.smem_bar + (uint32_t)W * kStages * 8u + 127u) / 128u * 128u;
-  kp.smem_total = kp.smem_red + (uint32_t)W * kRedRows * 128u;
+  // red area: best[3][32] u64 | found[2][32] u32 | gc[W][32] f32
+  kp.smem_total = kp.smem_red + 3u * 256u + 2u * 128u + (uint32_t)W * 128u;
   if (kp.smem_total > 227u * 1024u)
     FAIL(BPLX_E_UNSUPPORTED, "problem needs %u bytes of shared memory per CTA (max %u): too many (team, confederation) pairs (%d)",
          kp.smem_total, 227u * 1024u, V);

@@ -18,11 +18,18 @@
 //   list           : the matches of one virtual team in one role at one venue class (kind H1, A1,
 //                    H0, A0), cut into pieces of at most kListMax entries.  Every match is in exactly
 //                    two lists, so every per-team sum is accumulated in registers by the one warp
-//                    that owns the virtual team: no atomics, deterministic.
+//                    that owns the team: no atomics between warps, deterministic.
 //                    Inside a list the two rates of an entry are X = own'.x * opp.x and
 //                    Y = own'.y * opp.y, where own' is the own row (swapped for the neutral kinds).
 //   entry          : (byte offset of the opponent row, weight); identical (list, opponent) pairs
 //                    are merged with summed weights.
+//   stream         : what a warp reads in one phase: its lists back to back, each a 16-byte ListHdr
+//                    followed by its entries (a multiple of 16 bytes), fetched through the warp's
+//                    TMA ring.  Phase 1 = rates (Poisson part + maxima), phase 2 = tau matches.
+//   raw slot       : while the phases run, the caller's grad entries of a team's own parameters
+//                    (attack/defence pair and the venue effects) hold the gradient with respect to
+//                    the team's log-rate halves; the final team pass turns them into parameter
+//                    gradients (priors, chain rule) in place.
 #pragma once
 #include <stdint.h>
 
@@ -31,28 +38,24 @@
 
 #include "../../include/bplx.h"
 
-#if defined(__CUDACC__)
-#define BPLX_HD __host__ __device__
-#else
-#define BPLX_HD
-#endif
-
 namespace bplx {
 
 constexpr int kChains = 32;       // chains per CTA: one lane per chain
 constexpr int kRowBytes = 256;    // one table row: float2 x 32 lanes
 constexpr int kListMax = 128;     // entries per list piece (bounds the arg-max rescan)
-constexpr int kMaxCov = 8;        // covariates supported by the kernel
-constexpr int kMaxWarps = 16;
-constexpr int kRedRows = 8;       // per-warp rows in the reduction area
-constexpr int kStageBytes = 512;  // one TMA bulk copy of a warp's entry stream
+constexpr int kMaxCov = 16;       // covariates supported by the kernel
+constexpr int kMaxWarps = 24;     // warps per CTA (register budget: 65536 / (24*32) = 85 per thread)
+constexpr int kStageBytes = 512;  // one TMA bulk copy of a warp's stream
 constexpr int kStages = 2;        // ring depth per warp
+constexpr int kAccRows = 13;      // hyper accumulators: lp, mu_d, ls_a, ls_d, mu[4], ls[4], rho
+constexpr int kPartRows = 16;     // rows per warp in the final cross-warp reduction
 
 enum Kind : uint8_t { kH1 = 0, kA1 = 1, kH0 = 2, kA0 = 3 };
 enum Exponent : int { eAh1 = 0, eBh1 = 1, eBa1 = 2, eAa1 = 3, eA0 = 4, eB0 = 5 };
 
-constexpr uint8_t kListFirst = 1;  // first list of its virtual team in this warp's sequence
-constexpr uint8_t kListLast = 2;   // last one: apply the accumulated exponent gradients
+constexpr uint8_t kTeamFirst = 1;  // first list of its team in this warp's stream: clear the accumulators
+constexpr uint8_t kTeamLast = 2;   // last one: write the team's raw slots
+constexpr uint8_t kVteamLast = 4;  // last list of its virtual team: write the confederation scratch
 
 // phase-1 entry (plain) and phase-2 entry: 8 bytes
 struct Entry {
@@ -67,17 +70,17 @@ struct EntryClip {
   float wyy;  // sum of w * goals of the Y rate
 };
 
-struct List {  // 32 bytes, read warp-uniformly
-  uint32_t ent;      // first entry
-  uint32_t n;        // phase 1: number of entries (even; padded with zero-row entries)
+struct ListHdr {  // 16 bytes, in front of the entries of every list
   uint32_t own_off;  // byte offset of the own row
-  uint32_t vteam;
-  uint16_t n_xy, n_x, n_y;  // phase 2: entries per tau class (each even), stored in this order
+  uint16_t vteam;
   uint8_t kind;
   uint8_t flags;
-  uint32_t pad[2];
+  uint16_t n0;  // phase 1: entries (even for 8-byte entries) | phase 2: tau = 1 - c X Y entries (even)
+  uint16_t n1;  // phase 2: tau = 1 + c X entries (even)
+  uint16_t n2;  // phase 2: tau = 1 + c Y entries (even)
+  uint16_t team;
 };
-static_assert(sizeof(List) == 32, "List must be 32 bytes");
+static_assert(sizeof(ListHdr) == 16, "ListHdr must be 16 bytes");
 
 // offsets of the sites inside the flat unconstrained vector (-1 = absent)
 struct ThetaOffsets {
@@ -92,33 +95,45 @@ struct ThetaOffsets {
   int raw;             // logit corr_coef_raw
 };
 
+// a scalar hyper-parameter site: Normal(loc, scale) on theta, or HalfNormal(scale) on exp(theta);
+// the normalising constants are folded into KernelParams::const_term
+struct HyperDesc {
+  int off;   // offset in theta
+  int row;   // accumulator row holding the likelihood part of its gradient
+  int kind;  // 0 = normal, 1 = half-normal on exp(theta) (+ Jacobian)
+  float loc, inv_scale;
+};
+
 // everything the kernel needs; device pointers are filled by api.cu after upload
 struct KernelParams {
   int model, T, K, Cf, V;
   int D, nwarps;
+  int ndec;        // decentred per-team venue sites: 0 (DC), 1 (EXT), 4 (NEU, WC)
   int clip;        // Extended: rates clipped at 15
   int has1, has0;  // venue classes present
   uint32_t tabP1, tabQ1, tabP0;  // byte offsets of the tables (row V of each = zero row)
-  uint32_t tab_bytes;
+  uint32_t tab_bytes;            // table area (reused by the epilogue)
   uint32_t smem_ring, smem_bar, smem_red, smem_total;  // carve-up (bytes)
+  uint32_t epi_team, epi_part;   // epilogue reuse of the table area: team rows, per-warp partials
   ThetaOffsets off;
-  const List* lists1;
-  const List* lists2;
-  const void* ent1;    // Entry or EntryClip
-  const Entry* ent2;
-  const int32_t* warp_l1;  // [nwarps+1] list range of each warp, phase 1
-  const int32_t* warp_l2;  // [nwarps+1]
-  const int32_t* warp_e1;  // [nwarps+1] entry range of each warp (contiguous stream), phase 1
-  const int32_t* warp_e2;  // [nwarps+1]
-  const int32_t* team_vptr;   // [T+1] virtual teams of each team (CSR over v, v sorted by team)
-  const uint16_t* v_team;     // [V]
-  const uint8_t* v_conf;      // [V]
-  const int32_t* conf_vptr;   // [Cf+1]
-  const int32_t* conf_vlist;  // [V]
-  const float* yexp;          // [V*6] static sums of w*goals per exponent (zero for clip models)
-  const float* Xs;            // [T*K]
+  const unsigned char* stream1;  // phase-1 streams of all warps
+  const unsigned char* stream2;  // phase-2 streams
+  const uint32_t* warp_b1;       // [nwarps+1] byte range of each warp's phase-1 stream
+  const uint32_t* warp_b2;       // [nwarps+1]
+  const int32_t* team_vptr;      // [T+1] virtual teams of each team (CSR over v, v sorted by team)
+  const uint8_t* team_flags;     // [T] bit 0: the team has lists (phase 1 writes its raw slots)
+  const uint16_t* v_team;        // [V]
+  const uint8_t* v_conf;         // [V]
+  const int32_t* conf_vptr;      // [Cf+1]
+  const int32_t* conf_vlist;     // [V]
+  const float* yexp;             // [V*6] static sums of w*goals per exponent (zero for clip models)
+  const float* yteam;            // [T*8] the same folded per team: d/d att, d/d def, d/d venue effect[4], 0, 0
+  const float* yconf;            // [Cf]  ... and per confederation
+  const float* Xs;               // [T*K]
+  HyperDesc hyper[12];           // scalar hyper-parameter sites (priors + chain rule in the epilogue)
+  int nhyper;
   float w11;         // sum of weights of 1-1 matches
-  float const_term;  // -sum w (lgamma(yh+1) + lgamma(ya+1))
+  float const_term;  // -sum w (lgamma(yh+1) + lgamma(ya+1)) + every normalising constant of the priors
   // call arguments
   int C;
   long long sd, sc;  // element strides of theta/grad: index = d*sd + c*sc
@@ -130,23 +145,22 @@ struct KernelParams {
   int Cpad;
 };
 
-BPLX_HD inline int hyper_rows(int K) { return 16 + 2 * K; }
-
 struct HostPlan {
   KernelParams kp{};  // scalar fields filled; pointers null
-  std::vector<List> lists1, lists2;
-  std::vector<Entry> ent1, ent2;
-  std::vector<EntryClip> ent1c;
-  std::vector<int32_t> warp_l1, warp_l2, warp_e1, warp_e2, team_vptr, conf_vptr, conf_vlist;
+  std::vector<unsigned char> stream1, stream2;
+  std::vector<uint32_t> warp_b1, warp_b2;
+  std::vector<int32_t> team_vptr, conf_vptr, conf_vlist;
+  std::vector<uint8_t> team_flags;
   std::vector<uint16_t> v_team;
   std::vector<uint8_t> v_conf;
-  std::vector<float> yexp, Xs;
+  std::vector<float> yexp, yteam, yconf, Xs;
   std::string layout;  // "name:offset:count:transform;" records
   // statistics
-  long long n1 = 0, n2 = 0, n1_padded = 0, n2_padded = 0;
+  long long n1 = 0, n2 = 0, n1_padded = 0, n2_padded = 0, nlists1 = 0, nlists2 = 0;
 };
 
 // Builds the plan; returns BPLX_OK or a negative status with the message in `err`.
-int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err);
+// `force_warps` > 0 overrides the warp-count choice (tests, tuning).
+int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err, int force_warps = 0);
 
 }  // namespace bplx

@@ -19,68 +19,35 @@ using namespace bplx;
 namespace {
 
 constexpr double kLogSqrt2Pi = 0.91893853320467274178;
-constexpr double kLog2 = 0.69314718055994530942;
 
 struct Row { double x, y; };
-
-struct Ctx {
-  const HostPlan* P;
-  const KernelParams* kp;
-  const double* th;
-  double* grad;
-  // constrained hypers
-  double mu_d, sig_a, sig_d, mu[4], sig[4], rho, s2;
-  double beta_a[kMaxCov], beta_d[kMaxCov];
-  // hyper gradient accumulators
-  double a_mu_d = 0, a_ls_a = 0, a_ls_d = 0, a_mu[4] = {0, 0, 0, 0}, a_ls[4] = {0, 0, 0, 0}, a_rho = 0;
-  double a_ba[kMaxCov] = {0}, a_bd[kMaxCov] = {0};
-  std::vector<double> a_conf;
-  double lp = 0;
-};
 
 const int kOwnX[4] = {eAh1, eBa1, eB0, eB0};
 const int kOwnY[4] = {eBh1, eAa1, eA0, eA0};
 const int kOppX[4] = {eBa1, eAh1, eA0, eA0};
 const int kOppY[4] = {eAa1, eBh1, eB0, eB0};
 
-// exponent gradients of virtual team v -> raw parameter gradients
-void apply_vteam(Ctx& c, int v, const double g[6]) {
-  const KernelParams& kp = *c.kp;
-  const ThetaOffsets& o = kp.off;
-  const int t = c.P->v_team[v];
-  const double gA = g[eAh1] + g[eAa1] + g[eA0];
-  const double gB = g[eBh1] + g[eBa1] + g[eB0];
-  const double g_att = gA, g_def = -gB;
-  if (kp.model == BPLX_NEUTRAL_WC) c.a_conf[c.P->v_conf[v]] += gA - gB;
-  const double za = c.th[o.za + t], zd = c.th[o.zd + t];
-  c.grad[o.za + t] += c.sig_a * g_att;
-  c.a_ls_a += c.sig_a * za * g_att;
-  c.grad[o.zd + t] += c.sig_d * g_def;
-  c.a_ls_d += c.sig_d * zd * g_def;
-  c.a_mu_d += g_def;
-  for (int k = 0; k < kp.K; k++) {
-    c.a_ba[k] += c.P->Xs[(size_t)t * kp.K + k] * g_att;
-    c.a_bd[k] += c.P->Xs[(size_t)t * kp.K + k] * g_def;
-  }
-  const double gx[4] = {g[eAh1], g[eAa1], -g[eBh1], -g[eBa1]};  // ha, aa, hd, ad
-  if (kp.model == BPLX_DIXON_COLES) {
-    c.a_mu[0] += gx[0];
-  } else {
-    const int nx = kp.model == BPLX_EXTENDED ? 1 : 4;
-    for (int i = 0; i < nx; i++) {
-      const double dec = c.th[o.dec[i] + t];
-      c.grad[o.dec[i] + t] += c.sig[i] * gx[i];
-      c.a_mu[i] += gx[i];
-      c.a_ls[i] += c.sig[i] * dec * gx[i];
-    }
-  }
+struct Raw {  // raw slots of the walk: d/d (att, def, venue effects) per team, d/d (A - B) per virtual team
+  std::vector<double> att, def, x[4], conf_v;
+  double hacc = 0;  // DIXON_COLES: d/d home_advantage
+};
+
+// exponent gradients of one virtual team -> raw slots
+void put_raw(const HostPlan& P, Raw& R, int v, const double g[6]) {
+  const int t = P.v_team[v];
+  const double gA = g[eAh1] + g[eAa1] + g[eA0], gB = g[eBh1] + g[eBa1] + g[eB0];
+  R.att[t] += gA;
+  R.def[t] -= gB;
+  R.x[0][t] += g[eAh1];
+  R.x[1][t] += g[eAa1];
+  R.x[2][t] -= g[eBh1];
+  R.x[3][t] -= g[eBa1];
+  R.conf_v[v] += gA - gB;
+  if (P.kp.ndec == 0) R.hacc += g[eAh1];
 }
 
-double sigmoid_clipped(double x, bool* clipped) {
-  // numpyro SigmoidTransform: clip(expit(x), finfo.tiny, 1 - finfo.eps) -- in double here
-  double s = 1.0 / (1.0 + std::exp(-x));
-  *clipped = false;
-  return s;
+const ListHdr* hdr_at(const std::vector<unsigned char>& S, size_t off) {
+  return reinterpret_cast<const ListHdr*>(&S[off]);
 }
 
 }  // namespace
@@ -96,73 +63,36 @@ extern "C" int bplx_plancheck_eval(const bplx_problem_desc* desc, const double* 
   }
   const KernelParams& kp = P.kp;
   const ThetaOffsets& o = kp.off;
-  const int T = kp.T, K = kp.K, V = kp.V, Cf = kp.Cf, D = kp.D;
+  const int T = kp.T, K = kp.K, V = kp.V, Cf = kp.Cf, D = kp.D, ndec = kp.ndec;
   for (int i = 0; i < D; i++) grad[i] = 0.0;
-  Ctx c;
-  c.P = &P;
-  c.kp = &kp;
-  c.th = theta;
-  c.grad = grad;
-  c.a_conf.assign(Cf, 0.0);
-  const bool dc = kp.model == BPLX_DIXON_COLES, ext = kp.model == BPLX_EXTENDED;
-  const bool neu = kp.model == BPLX_NEUTRAL || kp.model == BPLX_NEUTRAL_WC;
+  const bool dc = kp.model == BPLX_DIXON_COLES;
   const bool has_rho = !dc;
+  const size_t esz1 = kp.clip ? sizeof(EntryClip) : sizeof(Entry);
+  double lp = 0;
   // ---- hypers -----------------------------------------------------------------------------------
-  c.mu_d = theta[o.mean_defence];
-  c.sig_a = std::exp(theta[o.log_std_attack]);
-  c.sig_d = std::exp(theta[o.log_std_defence]);
+  const double mu_d = theta[o.mean_defence];
+  const double sig_a = std::exp(theta[o.log_std_attack]), sig_d = std::exp(theta[o.log_std_defence]);
+  double mu[4], sig[4];
   for (int i = 0; i < 4; i++) {
-    c.mu[i] = o.mean[i] >= 0 ? theta[o.mean[i]] : 0.0;
-    c.sig[i] = o.log_std[i] >= 0 ? std::exp(theta[o.log_std[i]]) : 0.0;
+    mu[i] = o.mean[i] >= 0 ? theta[o.mean[i]] : 0.0;
+    sig[i] = o.log_std[i] >= 0 ? std::exp(theta[o.log_std[i]]) : 0.0;
   }
-  double u = 0.5;
-  bool clipped;
-  if (has_rho) u = sigmoid_clipped(theta[o.u], &clipped);
-  c.rho = has_rho ? 2.0 * u - 1.0 : 0.0;
-  c.s2 = 1.0 - c.rho * c.rho;
-  for (int k = 0; k < K; k++) {
-    c.beta_a[k] = theta[o.beta_a + k];
-    c.beta_d[k] = theta[o.beta_d + k];
-  }
-  // ---- prologue: tables, team priors, static y part ---------------------------------------------
-  const size_t rows = (size_t)V + 1;
+  const double u = has_rho ? 1.0 / (1.0 + std::exp(-theta[o.u])) : 0.5;
+  const double rho = has_rho ? 2.0 * u - 1.0 : 0.0, s2 = 1.0 - rho * rho;
+  // ---- prologue: tables, static y part ------------------------------------------------------------
   std::vector<Row> tab(kp.tab_bytes / kRowBytes + 4, Row{0, 0});  // one Row per table row
   auto row = [&](uint32_t off) -> Row& { return tab[off / kRowBytes]; };
-  (void)rows;
   for (int t = 0; t < T; t++) {
-    const double za = theta[o.za + t], zd = theta[o.zd + t];
-    double am = 0, dm = c.mu_d;
+    double am = 0, dm = mu_d;
     for (int k = 0; k < K; k++) {
-      am += P.Xs[(size_t)t * K + k] * c.beta_a[k];
-      dm += P.Xs[(size_t)t * K + k] * c.beta_d[k];
+      am += P.Xs[(size_t)t * K + k] * theta[o.beta_a + k];
+      dm += P.Xs[(size_t)t * K + k] * theta[o.beta_d + k];
     }
-    const double att = am + za * c.sig_a, def = dm + zd * c.sig_d;
-    // priors on the standardised pair (extended_dixon_coles.py:165-174) or independent normals
-    if (has_rho) {
-      const double e = zd - c.rho * za;
-      c.lp += -0.5 * za * za - kLogSqrt2Pi - 0.5 * e * e / c.s2 - 0.5 * std::log(c.s2) - kLogSqrt2Pi;
-      grad[o.za + t] += -za + c.rho * e / c.s2;
-      grad[o.zd + t] += -e / c.s2;
-      c.a_rho += e * za / c.s2 - c.rho * e * e / (c.s2 * c.s2) + c.rho / c.s2;
-    } else {
-      c.lp += -0.5 * za * za - 0.5 * zd * zd - 2 * kLogSqrt2Pi;
-      grad[o.za + t] += -za;
-      grad[o.zd + t] += -zd;
-    }
-    double x[4] = {0, 0, 0, 0};
-    if (dc) {
-      x[0] = c.mu[0];
-    } else {
-      const int nx = ext ? 1 : 4;
-      for (int i = 0; i < nx; i++) {
-        const double dec = theta[o.dec[i] + t];
-        x[i] = c.mu[i] + c.sig[i] * dec;
-        c.lp += -0.5 * dec * dec - kLogSqrt2Pi;
-        grad[o.dec[i] + t] += -dec;
-      }
-    }
+    const double att = am + theta[o.za + t] * sig_a, def = dm + theta[o.zd + t] * sig_d;
+    double x[4] = {dc ? mu[0] : 0.0, 0, 0, 0};
+    for (int i = 0; i < ndec; i++) x[i] = mu[i] + sig[i] * theta[o.dec[i] + t];
     for (int v = P.team_vptr[t]; v < P.team_vptr[t + 1]; v++) {
-      const double cf = kp.model == BPLX_NEUTRAL_WC ? theta[o.conf + P.v_conf[v]] : 0.0;
+      const double cf = Cf > 0 ? theta[o.conf + P.v_conf[v]] : 0.0;
       double ex[6];
       ex[eAh1] = att + x[0] + cf;
       ex[eBh1] = -def - x[2] - cf;
@@ -175,31 +105,40 @@ extern "C" int bplx_plancheck_eval(const bplx_problem_desc* desc, const double* 
         row(kp.tabQ1 + v * kRowBytes) = Row{std::exp(ex[eBa1]), std::exp(ex[eAa1])};
       }
       if (kp.has0) row(kp.tabP0 + v * kRowBytes) = Row{std::exp(ex[eA0]), std::exp(ex[eB0])};
-      double g[6];
-      for (int e = 0; e < 6; e++) {
-        g[e] = P.yexp[(size_t)v * 6 + e];
-        c.lp += g[e] * ex[e];
-      }
-      apply_vteam(c, v, g);
+      for (int e = 0; e < 6; e++) lp += P.yexp[(size_t)v * 6 + e] * ex[e];
     }
   }
-  (void)neu;
-  // ---- phase 1 ------------------------------------------------------------------------------------
+  Raw R;
+  R.att.assign(T, 0.0);
+  R.def.assign(T, 0.0);
+  for (auto& v : R.x) v.assign(T, 0.0);
+  R.conf_v.assign(V, 0.0);
+  // ---- phase 1: walk every warp's stream ------------------------------------------------------------
   double best[3] = {0, 0, 0};  // max X, max Y, max XY over home-role lists
-  int best_list[3] = {-1, -1, -1};
-  double g[6];
+  size_t best_hdr[3] = {0, 0, 0};
+  std::vector<int> seen_first(T, 0), seen_last(T, 0);
   for (int w = 0; w < kp.nwarps; w++) {
-    for (int li = P.warp_l1[w]; li < P.warp_l1[w + 1]; li++) {
-      const List& L = P.lists1[li];
-      if (L.flags & kListFirst) memset(g, 0, sizeof g);
+    size_t pos = P.warp_b1[w];
+    const size_t end = P.warp_b1[w + 1];
+    double g[6] = {0, 0, 0, 0, 0, 0};
+    while (pos < end) {
+      const size_t hoff = pos;
+      const ListHdr& L = *hdr_at(P.stream1, pos);
+      pos += sizeof(ListHdr);
+      if (L.flags & kTeamFirst) {
+        memset(g, 0, sizeof g);
+        if (seen_first[L.team]++) return -110;  // a team must be owned by exactly one warp
+      }
+      if (P.v_team[L.vteam] != L.team) return -111;
       Row own = row(L.own_off);
       if (L.kind >= kH0) std::swap(own.x, own.y);
       const bool home = L.kind == kH1 || L.kind == kH0;
       double gx = 0, gy = 0;
       if (!kp.clip) {
+        if (L.n0 & 1) return -112;
         double ax = 0, ay = 0, m1 = 0, m2 = 0, m3 = 0;
-        for (uint32_t i = 0; i < L.n; i++) {
-          const Entry& e = P.ent1[L.ent + i];
+        for (uint32_t i = 0; i < L.n0; i++, pos += esz1) {
+          const Entry& e = *reinterpret_cast<const Entry*>(&P.stream1[pos]);
           const Row& op = row(e.off);
           ax += e.w * op.x;
           ay += e.w * op.y;
@@ -208,133 +147,112 @@ extern "C" int bplx_plancheck_eval(const bplx_problem_desc* desc, const double* 
           m3 = std::max(m3, op.x * op.y);
         }
         const double SX = own.x * ax, SY = own.y * ay;
-        c.lp -= 0.5 * (SX + SY);
+        lp -= 0.5 * (SX + SY);
         gx = -SX;
         gy = -SY;
         if (home) {
           const double v[3] = {own.x * m1, own.y * m2, own.x * own.y * m3};
           for (int q = 0; q < 3; q++)
-            if (v[q] > best[q]) best[q] = v[q], best_list[q] = li;
+            if (v[q] > best[q]) best[q] = v[q], best_hdr[q] = hoff;
         }
       } else {
-        for (uint32_t i = 0; i < L.n; i++) {
-          const EntryClip& e = P.ent1c[L.ent + i];
+        for (uint32_t i = 0; i < L.n0; i++, pos += esz1) {
+          const EntryClip& e = *reinterpret_cast<const EntryClip*>(&P.stream1[pos]);
           const Row& op = row(e.off);
           const double X = own.x * op.x, Y = own.y * op.y;
           const double Xc = std::min(X, 15.0), Yc = std::min(Y, 15.0);
           if (home) {
-            c.lp += e.wyx * std::log(Xc) - e.w * Xc + e.wyy * std::log(Yc) - e.w * Yc;
+            lp += e.wyx * std::log(Xc) - e.w * Xc + e.wyy * std::log(Yc) - e.w * Yc;
             const double v[3] = {Xc, Yc, Xc * Yc};
             for (int q = 0; q < 3; q++)
-              if (v[q] > best[q]) best[q] = v[q], best_list[q] = li;
+              if (v[q] > best[q]) best[q] = v[q], best_hdr[q] = hoff;
           }
           if (X < 15.0) gx += e.wyx - e.w * X;
           if (Y < 15.0) gy += e.wyy - e.w * Y;
         }
       }
-      g[kOwnX[L.kind]] += gx;
-      g[kOwnY[L.kind]] += gy;
-      if (L.flags & kListLast) apply_vteam(c, (int)L.vteam, g);
+      double gl[6] = {0, 0, 0, 0, 0, 0};
+      gl[kOwnX[L.kind]] += gx;
+      gl[kOwnY[L.kind]] += gy;
+      put_raw(P, R, L.vteam, gl);
+      if (L.flags & kTeamLast) seen_last[L.team]++;
     }
+    if (pos != end) return -113;
   }
+  for (int t = 0; t < T; t++)
+    if (seen_first[t] != seen_last[t] || seen_first[t] != (P.team_flags[t] & 1)) return -114;
   // ---- bounds and corr_coef (bpl/_util.py:17-31) ---------------------------------------------------
   const double Lam = std::max(best[0], best[1]);
   const double LB = -1.0 / Lam;
   const double UB = std::min(1.0 / best[2], 1.0);
-  const double r = sigmoid_clipped(theta[o.raw], &clipped);
+  const double r = 1.0 / (1.0 + std::exp(-theta[o.raw]));
   const double cc = LB + r * (UB - LB);
   *corr_out = cc;
   // ---- phase 2: tau terms ----------------------------------------------------------------------------
   double Gc = 0;
   for (int w = 0; w < kp.nwarps; w++) {
-    for (int li = P.warp_l2[w]; li < P.warp_l2[w + 1]; li++) {
-      const List& L = P.lists2[li];
-      if (L.flags & kListFirst) memset(g, 0, sizeof g);
+    size_t pos = P.warp_b2[w];
+    const size_t end = P.warp_b2[w + 1];
+    while (pos < end) {
+      const ListHdr& L = *hdr_at(P.stream2, pos);
+      pos += sizeof(ListHdr);
+      if ((L.n0 | L.n1 | L.n2) & 1) return -120;
       Row own = row(L.own_off);
       if (L.kind >= kH0) std::swap(own.x, own.y);
       const bool home = L.kind == kH1 || L.kind == kH0;
-      double uxy = 0, ux = 0, uy = 0, lt = 0;
-      uint32_t i = L.ent;
-      auto rates = [&](const Entry& e, double* X, double* Y) {
-        const Row& op = row(e.off);
-        *X = own.x * op.x;
-        *Y = own.y * op.y;
-        if (kp.clip) *X = std::min(*X, 15.0), *Y = std::min(*Y, 15.0);
-      };
-      double X, Y;
-      for (uint32_t k = 0; k < L.n_xy; k++, i++) {
-        const Entry& e = P.ent2[i];
-        rates(e, &X, &Y);
-        const double tau = 1.0 - cc * X * Y;
-        uxy += e.w * X * Y / tau;
-        if (e.w != 0) lt += e.w * std::log(tau);
-      }
-      for (uint32_t k = 0; k < L.n_x; k++, i++) {
-        const Entry& e = P.ent2[i];
-        rates(e, &X, &Y);
-        const double tau = 1.0 + cc * X;
-        ux += e.w * X / tau;
-        if (e.w != 0) lt += e.w * std::log(tau);
-      }
-      for (uint32_t k = 0; k < L.n_y; k++, i++) {
-        const Entry& e = P.ent2[i];
-        rates(e, &X, &Y);
-        const double tau = 1.0 + cc * Y;
-        uy += e.w * Y / tau;
-        if (e.w != 0) lt += e.w * std::log(tau);
-      }
-      // residuals wrt the two log-rates; a clipped rate has zero derivative
-      double gx = cc * (ux - uxy), gy = cc * (uy - uxy);
-      if (kp.clip) {
-        // per-entry clip masks are needed: redo with masks (clip models are tiny; clarity over speed)
-        gx = gy = 0;
-        uint32_t j = L.ent;
-        for (uint32_t k = 0; k < L.n_xy; k++, j++) {
-          const Entry& e = P.ent2[j];
+      double gx = 0, gy = 0, lt = 0, dG = 0;
+      const uint32_t n[3] = {L.n0, L.n1, L.n2};
+      for (int cls = 0; cls < 3; cls++) {
+        for (uint32_t k = 0; k < n[cls]; k++, pos += sizeof(Entry)) {
+          const Entry& e = *reinterpret_cast<const Entry*>(&P.stream2[pos]);
+          if (e.w == 0.0f) continue;  // padding
           const Row& op = row(e.off);
           const double Xr = own.x * op.x, Yr = own.y * op.y;
-          rates(e, &X, &Y);
-          const double q = e.w * cc * X * Y / (1.0 - cc * X * Y);
-          if (Xr < 15.0) gx -= q;
-          if (Yr < 15.0) gy -= q;
-        }
-        for (uint32_t k = 0; k < L.n_x; k++, j++) {
-          const Entry& e = P.ent2[j];
-          const Row& op = row(e.off);
-          const double Xr = own.x * op.x;
-          rates(e, &X, &Y);
-          if (Xr < 15.0) gx += e.w * cc * X / (1.0 + cc * X);
-        }
-        for (uint32_t k = 0; k < L.n_y; k++, j++) {
-          const Entry& e = P.ent2[j];
-          const Row& op = row(e.off);
-          const double Yr = own.y * op.y;
-          rates(e, &X, &Y);
-          if (Yr < 15.0) gy += e.w * cc * Y / (1.0 + cc * Y);
+          const double X = kp.clip ? std::min(Xr, 15.0) : Xr, Y = kp.clip ? std::min(Yr, 15.0) : Yr;
+          const bool xfree = !kp.clip || Xr < 15.0, yfree = !kp.clip || Yr < 15.0;  // a clipped rate has zero derivative
+          if (cls == 0) {
+            const double tau = 1.0 - cc * X * Y, q = e.w * X * Y / tau;
+            lt += e.w * std::log(tau);
+            dG -= q;
+            if (xfree) gx -= cc * q;
+            if (yfree) gy -= cc * q;
+          } else if (cls == 1) {
+            const double tau = 1.0 + cc * X, q = e.w * X / tau;
+            lt += e.w * std::log(tau);
+            dG += q;
+            if (xfree) gx += cc * q;
+          } else {
+            const double tau = 1.0 + cc * Y, q = e.w * Y / tau;
+            lt += e.w * std::log(tau);
+            dG += q;
+            if (yfree) gy += cc * q;
+          }
         }
       }
       if (home) {
-        c.lp += lt;
-        Gc += ux + uy - uxy;
+        lp += lt;
+        Gc += dG;
       }
-      g[kOwnX[L.kind]] += gx;
-      g[kOwnY[L.kind]] += gy;
-      if (L.flags & kListLast) apply_vteam(c, (int)L.vteam, g);
+      double gl[6] = {0, 0, 0, 0, 0, 0};
+      gl[kOwnX[L.kind]] += gx;
+      gl[kOwnY[L.kind]] += gy;
+      put_raw(P, R, L.vteam, gl);
     }
+    if (pos != end) return -121;
   }
-  c.lp += kp.w11 * std::log(1.0 - cc);
+  lp += kp.w11 * std::log(1.0 - cc);
   Gc -= kp.w11 / (1.0 - cc);
   // ---- arg-max fix-up -----------------------------------------------------------
   // dc/dLB = 1 - r, dLB/dLam = 1/Lam^2, dLam/d eta = Lam  (zero when the max is a clipped rate)
   auto find = [&](int q, int* own_v, int* opp_v, int* kind, double* Xr, double* Yr) {
-    const List& L = P.lists1[best_list[q]];
+    const ListHdr& L = *hdr_at(P.stream1, best_hdr[q]);
     Row own = row(L.own_off);
     if (L.kind >= kH0) std::swap(own.x, own.y);
     *own_v = (int)L.vteam;
     *kind = L.kind;
     *opp_v = -1;
-    for (uint32_t i = 0; i < L.n; i++) {
-      const uint32_t off = kp.clip ? P.ent1c[L.ent + i].off : P.ent1[L.ent + i].off;
+    for (uint32_t i = 0; i < L.n0; i++) {
+      const uint32_t off = *reinterpret_cast<const uint32_t*>(&P.stream1[best_hdr[q] + 16 + i * esz1]);
       const Row& op = row(off);
       double X = own.x * op.x, Y = own.y * op.y;
       double Xc = kp.clip ? std::min(X, 15.0) : X, Yc = kp.clip ? std::min(Y, 15.0) : Y;
@@ -360,8 +278,8 @@ extern "C" int bplx_plancheck_eval(const bplx_problem_desc* desc, const double* 
       double g1[6] = {0}, g2[6] = {0};
       g1[q == 0 ? kOwnX[kind] : kOwnY[kind]] = wgt;
       g2[q == 0 ? kOppX[kind] : kOppY[kind]] = wgt;
-      apply_vteam(c, ov, g1);
-      apply_vteam(c, pv, g2);
+      put_raw(P, R, ov, g1);
+      put_raw(P, R, pv, g2);
     }
   }
   if (best[2] > 1.0) {
@@ -373,56 +291,80 @@ extern "C" int bplx_plancheck_eval(const bplx_problem_desc* desc, const double* 
     double g1[6] = {0}, g2[6] = {0};
     if (!kp.clip || Xr < 15.0) g1[kOwnX[kind]] += wgt, g2[kOppX[kind]] += wgt;
     if (!kp.clip || Yr < 15.0) g1[kOwnY[kind]] += wgt, g2[kOppY[kind]] += wgt;
-    apply_vteam(c, ov, g1);
-    apply_vteam(c, pv, g2);
+    put_raw(P, R, ov, g1);
+    put_raw(P, R, pv, g2);
   }
-  // ---- hyper priors, Jacobians, chain rule -------------------------------------------------------------
-  auto normal = [&](double x, double loc, double scale, int off) {
-    const double z = (x - loc) / scale;
-    c.lp += -0.5 * z * z - std::log(scale) - kLogSqrt2Pi;
-    grad[off] += -z / scale;
-  };
-  auto halfnormal_exp = [&](double sig, double scale, int off, double acc) {
-    // HalfNormal(scale) on sig = exp(x) plus the Jacobian x
-    const double z = sig / scale;
-    c.lp += -0.5 * z * z - std::log(scale) - kLogSqrt2Pi + kLog2 + theta[off];
-    grad[off] += -z * z + 1.0 + acc;
-  };
-  const double std_scale = neu ? 0.5 : 1.0;  // neutral_dixon_coles.py:138-139
-  normal(c.mu_d, 0.0, 1.0, o.mean_defence);
-  grad[o.mean_defence] += c.a_mu_d;
-  halfnormal_exp(c.sig_a, std_scale, o.log_std_attack, c.a_ls_a);
-  halfnormal_exp(c.sig_d, std_scale, o.log_std_defence, c.a_ls_d);
-  if (dc || ext) {
-    normal(c.mu[0], 0.1, 0.2, o.mean[0]);
-    grad[o.mean[0]] += c.a_mu[0];
-    if (ext) halfnormal_exp(c.sig[0], 1.0, o.log_std[0], c.a_ls[0]);
-  } else {
-    const double loc[4] = {0.1, -0.1, 0.1, -0.1};
-    for (int i = 0; i < 4; i++) {
-      normal(c.mu[i], loc[i], 0.2, o.mean[i]);
-      grad[o.mean[i]] += c.a_mu[i];
-      halfnormal_exp(c.sig[i], 1.0, o.log_std[i], c.a_ls[i]);
+  // ---- team pass: raw slots + static parts -> parameter gradients, priors, hyper sums ------------------
+  double acc[kAccRows] = {0};
+  std::vector<double> a_ba(K, 0.0), a_bd(K, 0.0);
+  for (int t = 0; t < T; t++) {
+    const double za = theta[o.za + t], zd = theta[o.zd + t];
+    const float* ys = &P.yteam[(size_t)t * 8];
+    const double ra = R.att[t] + ys[0], rd = R.def[t] + ys[1];
+    if (has_rho) {
+      const double e = zd - rho * za;
+      lp += -0.5 * za * za - 0.5 * e * e / s2;
+      grad[o.za + t] = -za + rho * e / s2 + sig_a * ra;
+      grad[o.zd + t] = -e / s2 + sig_d * rd;
+      acc[12] += e * za / s2 - rho * e * e / (s2 * s2) + rho / s2;
+    } else {
+      lp += -0.5 * za * za - 0.5 * zd * zd;
+      grad[o.za + t] = -za + sig_a * ra;
+      grad[o.zd + t] = -zd + sig_d * rd;
+    }
+    acc[2] += sig_a * za * ra;
+    acc[3] += sig_d * zd * rd;
+    acc[1] += rd;
+    if (dc) acc[4] += ys[2];
+    for (int i = 0; i < ndec; i++) {
+      const double dec = theta[o.dec[i] + t], rx = R.x[i][t] + ys[2 + i];
+      lp -= 0.5 * dec * dec;
+      grad[o.dec[i] + t] = -dec + sig[i] * rx;
+      acc[4 + i] += rx;
+      acc[8 + i] += sig[i] * dec * rx;
+    }
+    for (int k = 0; k < K; k++) {
+      a_ba[k] += P.Xs[(size_t)t * K + k] * ra;
+      a_bd[k] += P.Xs[(size_t)t * K + k] * rd;
     }
   }
+  if (dc) acc[4] += R.hacc;
+  for (int k = 0; k < Cf; k++) {
+    const double cf = theta[o.conf + k];
+    double s = P.yconf[k] - cf;
+    lp -= 0.5 * cf * cf;
+    for (int j = P.conf_vptr[k]; j < P.conf_vptr[k + 1]; j++) s += R.conf_v[P.conf_vlist[j]];
+    grad[o.conf + k] = s;
+  }
   for (int k = 0; k < K; k++) {
-    normal(c.beta_a[k], 0.0, 1.0, o.beta_a + k);
-    grad[o.beta_a + k] += c.a_ba[k];
-    normal(c.beta_d[k], 0.0, 1.0, o.beta_d + k);
-    grad[o.beta_d + k] += c.a_bd[k];
+    const double ba = theta[o.beta_a + k], bd = theta[o.beta_d + k];
+    lp -= 0.5 * (ba * ba + bd * bd);
+    grad[o.beta_a + k] = -ba + a_ba[k];
+    grad[o.beta_d + k] = -bd + a_bd[k];
+  }
+  // ---- hyper priors, Jacobians (normalising constants are in const_term) ---------------------------------
+  for (int h = 0; h < kp.nhyper; h++) {
+    const HyperDesc& hd = kp.hyper[h];
+    const double x = theta[hd.off];
+    if (hd.kind == 0) {
+      const double z = (x - hd.loc) * hd.inv_scale;
+      lp -= 0.5 * z * z;
+      grad[hd.off] = -z * hd.inv_scale + acc[hd.row];
+    } else {
+      const double z = std::exp(x) * hd.inv_scale;
+      lp += -0.5 * z * z + x;
+      grad[hd.off] = -z * z + 1.0 + acc[hd.row];
+    }
   }
   if (has_rho) {  // u ~ Beta(2, 4) + sigmoid Jacobian; rho = 2u - 1
-    c.lp += std::log(u) + 3.0 * std::log(1.0 - u) + std::log(20.0) + std::log(u) + std::log(1.0 - u);
-    grad[o.u] += (1.0 - u) - 3.0 * u + (1.0 - 2.0 * u) + c.a_rho * 2.0 * u * (1.0 - u);
-  }
-  for (int k = 0; k < Cf; k++) {
-    normal(theta[o.conf + k], 0.0, 1.0, o.conf + k);
-    grad[o.conf + k] += c.a_conf[k];
+    lp += -0.5 * T * std::log(s2) + 2.0 * std::log(u) + 4.0 * std::log(1.0 - u);
+    grad[o.u] = 2.0 - 6.0 * u + acc[12] * 2.0 * u * (1.0 - u);
   }
   // corr_coef_raw ~ Beta(2, 2) + Jacobian; c = LB + r (UB - LB)
-  c.lp += 2.0 * (std::log(r) + std::log(1.0 - r)) + std::log(6.0);
-  grad[o.raw] += 2.0 * (1.0 - 2.0 * r) + Gc * r * (1.0 - r) * (UB - LB);
-  c.lp += kp.const_term;
-  *lp_out = c.lp;
+  lp += 2.0 * (std::log(r) + std::log(1.0 - r));
+  grad[o.raw] = 2.0 * (1.0 - 2.0 * r) + Gc * r * (1.0 - r) * (UB - LB);
+  lp += kp.const_term;
+  (void)kLogSqrt2Pi;
+  *lp_out = lp;
   return 0;
 }
