@@ -58,6 +58,8 @@ static int enqueue(const bplx_problem* p, int C, int layout, int ld, const float
   } else {
     BPLX_REQUIRE(false, BPLX_E_INVALID, "unknown layout %d", layout);
   }
+  BPLX_REQUIRE((long long)kp.D * (long long)kp.sd + (long long)C * (long long)kp.sc < (1ll << 31), BPLX_E_UNSUPPORTED,
+               "theta / grad of %d x %d elements exceed the 31-bit element index of the kernel", C, kp.D);
   const size_t need = workspace_bytes(kp, C);
   BPLX_REQUIRE(ws_bytes >= need && (need == 0 || ws != nullptr), BPLX_E_WORKSPACE,
                "workspace too small: %zu bytes given, %zu needed", ws_bytes, need);

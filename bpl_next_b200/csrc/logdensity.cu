@@ -41,10 +41,10 @@ struct Lane {
   const float* th;  // theta + chain * sc
   float* gr;        // grad  + chain * sc
   float* sc;        // scratch + chain
-  long long sd;
+  int sd;
   bool active;
-  __device__ __forceinline__ float ld(int d) const { return __ldg(th + (long long)d * sd); }
-  __device__ __forceinline__ float* g(int d) const { return gr + (long long)d * sd; }
+  __device__ __forceinline__ float ld(int d) const { return __ldg(th + (uint32_t)(d * sd)); }
+  __device__ __forceinline__ float* g(int d) const { return gr + (uint32_t)(d * sd); }
 };
 
 __device__ __forceinline__ float sigmoid_clipped(float x) {
@@ -137,34 +137,21 @@ __device__ __forceinline__ void put_raw(const KernelParams& kp, const Lane& ln, 
   }
 }
 
-// one exponent of one virtual team gets `val` more gradient (arg-max fix-up; per-lane arguments)
-__device__ __forceinline__ void add_exponent(const KernelParams& kp, const Lane& ln, int v, int e, float val, float& hacc) {
-  if (val == 0.0f) return;
-  const ThetaOffsets& o = kp.off;
-  const int t = __ldg(kp.v_team + v);
-  const bool isA = e == eAh1 || e == eAa1 || e == eA0;
-  const float sv = isA ? val : -val;
-  red_add(ln.g((isA ? o.za : o.zd) + t), sv);
-  const int di = e == eAh1 ? 0 : e == eAa1 ? 1 : e == eBh1 ? 2 : e == eBa1 ? 3 : -1;
-  if (di >= 0 && di < kp.ndec) red_add(ln.g(o.dec[di] + t), sv);
-  if (kp.ndec == 0 && e == eAh1) hacc += val;
-  if (kp.Cf > 0) red_add(ln.sc + (long long)v * kp.Cpad, sv);
-}
-
-// Per-warp TMA ring over a contiguous global byte stream (the warp's lists of one phase).
-// One elected lane issues cp.async.bulk copies of kStageBytes into the warp's private ring and
-// every lane waits on the stage's mbarrier before reading it; the same warp produces and
-// consumes, so a __syncwarp() is all that is needed before a slot is refilled.
-struct Stream {
-  uint32_t ring, bar;        // shared addresses: kStages * kStageBytes ring, kStages mbarriers
+// Per-warp TMA ring over a contiguous global byte stream (the warp's list pieces of one phase).
+// One elected lane issues cp.async.bulk copies of one stage into the warp's private ring and every
+// lane waits on the stage's mbarrier before reading it; the same warp produces and consumes, so a
+// __syncwarp() is all that is needed before a slot is refilled.  Pieces never straddle a stage.
+struct Ring {
+  uint32_t ring, bar;        // shared addresses: kStages stages, kStages mbarriers
+  uint32_t S;                // stage bytes
   const unsigned char* src;  // current stream
-  uint32_t total, pos;       // bytes in / consumed from the current stream
+  uint32_t total;            // bytes in the current stream
   uint32_t gs0, gs_next;     // ring-stage counter at the start of / after the current stream
   int lane;
 
-  __device__ __forceinline__ void init(uint32_t ring_, uint32_t bar_, int lane_) {
-    ring = ring_; bar = bar_; lane = lane_;
-    total = pos = gs0 = gs_next = 0;
+  __device__ __forceinline__ void init(uint32_t ring_, uint32_t bar_, uint32_t S_, int lane_) {
+    ring = ring_; bar = bar_; S = S_; lane = lane_;
+    total = gs0 = gs_next = 0;
     src = nullptr;
     if (lane == 0) {
 #pragma unroll
@@ -175,51 +162,63 @@ struct Stream {
     __syncwarp();
   }
   __device__ __forceinline__ void issue(uint32_t k) {  // stage k of the current stream
-    const uint32_t b0 = k * kStageBytes;
+    const uint32_t b0 = k * S;
     if (lane == 0 && b0 < total) {
-      const uint32_t bytes = min((uint32_t)kStageBytes, total - b0);
+      const uint32_t bytes = min(S, total - b0);
       const uint32_t slot = (gs0 + k) % kStages;
       mbar_arrive_expect_tx(bar + 8 * slot, bytes);
-      tma_load_1d(ring + slot * kStageBytes, src + b0, bytes, bar + 8 * slot);
+      tma_load_1d(ring + slot * S, src + b0, bytes, bar + 8 * slot);
     }
   }
   __device__ __forceinline__ void begin(const void* src_, uint32_t total_bytes) {
     __syncwarp();  // every lane is done with the previous stream's stages
     src = static_cast<const unsigned char*>(src_);
     total = total_bytes;
-    pos = 0;
     gs0 = gs_next;
-    gs_next = gs0 + (total_bytes + kStageBytes - 1) / kStageBytes;
+    gs_next = gs0 + (total_bytes + S - 1) / S;
 #pragma unroll
     for (int s = 0; s < kStages; s++) issue(s);
   }
-  // body(shared address of a 16-byte unit), for nbytes (multiple of 16) of the stream
-  template <typename F>
-  __device__ __forceinline__ void consume(uint32_t nbytes, F&& body) {
-    while (nbytes) {
-      const uint32_t in_stage = pos & (kStageBytes - 1);
-      const uint32_t k = pos / kStageBytes;
-      const uint32_t idx = gs0 + k;
-      const uint32_t slot = idx % kStages;
-      if (in_stage == 0) mbar_wait(bar + 8 * slot, (idx / kStages) & 1);
-      const uint32_t chunk = min(nbytes, (uint32_t)kStageBytes - in_stage);
-      const uint32_t a0 = ring + slot * kStageBytes + in_stage;
-#pragma unroll 4
-      for (uint32_t o = 0; o < chunk; o += 16) body(a0 + o);
-      pos += chunk;
-      nbytes -= chunk;
-      if ((pos & (kStageBytes - 1)) == 0) {
-        __syncwarp();
-        issue(k + kStages);
-      }
-    }
+  __device__ __forceinline__ uint32_t num_stages() const { return (total + S - 1) / S; }
+  // waits for stage k; returns its shared address, *bytes = its size
+  __device__ __forceinline__ uint32_t acquire(uint32_t k, uint32_t* bytes) {
+    const uint32_t idx = gs0 + k, slot = idx % kStages;
+    mbar_wait(bar + 8 * slot, (idx / kStages) & 1);
+    *bytes = min(S, total - k * S);
+    return ring + slot * S;
   }
-  __device__ __forceinline__ Hdr header() {
-    uint4 h;
-    consume(16u, [&](uint32_t addr) { h = lds128u(addr); });
-    return unpack_hdr(h);
+  __device__ __forceinline__ void release(uint32_t k) {
+    __syncwarp();
+    issue(k + kStages);
   }
 };
+
+// the two arg-max matches of a chain, as every warp needs them in the team pass
+struct Fixup {
+  uint32_t teams[2];  // per which: own team | opp team << 16 (0xffff = none)
+  uint32_t confs;     // 4 x 8 bits: (which, side) -> confederation (WC)
+  uint32_t vts[2];    // per which: own vteam | opp vteam << 16
+  float vx[2], vy[2]; // gradient reaching the X / Y log-rate of the arg-max match
+  uint32_t h1;        // bit which: the list kind is H1 (else H0)
+};
+
+// d/d (att, def, venue effects) of team t gets the fix-up of (which, side) when it is that match's team
+__device__ __forceinline__ void fold_fixup(const Fixup& fx, int which, int side, float& ra, float& rd, float (&rx)[4]) {
+  const bool h1 = (fx.h1 >> which) & 1u;
+  const float vx = fx.vx[which], vy = fx.vy[which];
+  if (side == 0) {
+    if (h1) { ra += vx; rx[0] += vx; rd -= vy; rx[2] -= vy; }  // X -> A_h1, Y -> B_h1
+    else { rd -= vx; ra += vy; }                                 // X -> B_0,  Y -> A_0
+  } else {
+    if (h1) { rd -= vx; rx[3] -= vx; ra += vy; rx[1] += vy; }  // X -> B_a1, Y -> A_a1
+    else { ra += vx; rd -= vy; }                                 // X -> A_0,  Y -> B_0
+  }
+}
+__device__ __forceinline__ float fixup_conf(const Fixup& fx, int which, int side) {  // d/d (A - B)
+  const bool h1 = (fx.h1 >> which) & 1u;
+  const float d = fx.vx[which] - fx.vy[which];
+  return ((side == 0) == h1) ? d : -d;
+}
 
 }  // namespace
 
@@ -231,21 +230,35 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
   const int chain_raw = blockIdx.x * kChains + lane;
   const int chain = min(chain_raw, kp.C - 1);
   Lane ln;
-  ln.th = kp.theta + (long long)chain * kp.sc;
-  ln.gr = kp.grad + (long long)chain * kp.sc;
+  ln.th = kp.theta + (size_t)chain * (size_t)kp.sc;
+  ln.gr = kp.grad + (size_t)chain * (size_t)kp.sc;
   ln.sc = kp.scratch + chain;
   ln.sd = kp.sd;
   ln.active = chain_raw < kp.C;
   const uint32_t tab = smem_u32(smem) + lane * 8;  // + row byte offset
   unsigned long long* red_best = reinterpret_cast<unsigned long long*>(smem + kp.smem_red);  // [3][32]
   uint32_t* red_found = reinterpret_cast<uint32_t*>(smem + kp.smem_red + 768);               // [2][32]
-  float* red_gc = reinterpret_cast<float*>(smem + kp.smem_red + 1024);                        // [W][32]
+  uint32_t* red_info = reinterpret_cast<uint32_t*>(smem + kp.smem_red + 1024);               // [2][32]
+  float* red_gc = reinterpret_cast<float*>(smem + kp.smem_red + 1280);                        // [W][32]
   constexpr uint32_t ESZ = CLIP ? (uint32_t)sizeof(EntryClip) : (uint32_t)sizeof(Entry);
-  Stream stream;
-  stream.init(smem_u32(smem) + kp.smem_ring + warp * (kStages * kStageBytes),
-              smem_u32(smem) + kp.smem_bar + warp * (kStages * 8), lane);
+  Ring ring;
+  ring.init(smem_u32(smem) + kp.smem_ring + warp * (kStages * kp.stage_bytes),
+            smem_u32(smem) + kp.smem_bar + warp * (kStages * 8), kp.stage_bytes, lane);
   const uint32_t b1_0 = __ldg(kp.warp_b1 + warp), b1_1 = __ldg(kp.warp_b1 + warp + 1);
-  stream.begin(kp.stream1 + b1_0, b1_1 - b1_0);  // phase-1 lists start streaming in while the prologue runs
+  ring.begin(kp.stream1 + b1_0, b1_1 - b1_0);  // phase-1 pieces start streaming in while the prologue runs
+  {  // pull this CTA's slice of theta into L2 in one go: every later read of it is a hit
+    const int nthr = W * 32;
+    if (kp.sd == 1) {  // chain-major: 32 rows of D floats
+      const int per = (kp.D + 31) / 32;
+      for (int i = threadIdx.x; i < 32 * per; i += nthr) {
+        const int c = min(blockIdx.x * kChains + i / per, kp.C - 1);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(kp.theta + (size_t)c * (size_t)kp.sc + (size_t)(i % per) * 32));
+      }
+    } else {
+      for (int d = threadIdx.x; d < kp.D; d += nthr)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(kp.theta + (size_t)d * (size_t)kp.sd + (size_t)blockIdx.x * kChains));
+    }
+  }
 
   const int ndec = kp.ndec;
   const bool dc = ndec == 0;
@@ -311,91 +324,104 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
 
   // ---- phase 1 ----------------------------------------------------------------------------------
   float best[3] = {0.0f, 0.0f, 0.0f};
-  uint32_t besth[3] = {0u, 0u, 0u};  // byte offset (in stream1) of the header of the list that holds the maximum
+  uint32_t besth[3] = {0u, 0u, 0u};  // byte offset (in stream1) of the header of the piece that holds the maximum
   {
     float g[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f}, cacc = 0.0f;
-    while (stream.pos < stream.total) {
-      const uint32_t hoff = b1_0 + stream.pos;
-      const Hdr L = stream.header();
-      if (L.flags & kTeamFirst) {
+    const uint32_t nst = ring.num_stages();
+    for (uint32_t k = 0; k < nst; k++) {
+      uint32_t bytes;
+      const uint32_t a0 = ring.acquire(k, &bytes);
+      uint32_t a = a0;
+      const uint32_t aend = a0 + bytes;
+      while (a < aend) {
+        const uint32_t hoff = b1_0 + k * ring.S + (a - a0);
+        const Hdr L = unpack_hdr(lds128u(a));
+        a += 16;
+        const uint32_t e_end = a + L.n0 * ESZ;
+        if (L.flags & kTeamFirst) {
 #pragma unroll
-        for (int e = 0; e < 6; e++) g[e] = 0.0f;
-      }
-      float2 own = lds64(tab + L.own_off);
-      if (L.kind >= kH0) { const float s = own.x; own.x = own.y; own.y = s; }
-      const bool home = (L.kind & 1) == 0;
-      float gx, gy;
-      if (!CLIP) {
-        float ax0 = 0.0f, ay0 = 0.0f, ax1 = 0.0f, ay1 = 0.0f;
-        if (home) {
-          float m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
-          stream.consume(L.n0 * ESZ, [&](uint32_t addr) {
-            const uint4 q = lds128u(addr);  // two entries
-            const float2 a = lds64(tab + q.x), b = lds64(tab + q.z);
-            const float wa = __uint_as_float(q.y), wb = __uint_as_float(q.w);
-            ax0 = fmaf(wa, a.x, ax0); ay0 = fmaf(wa, a.y, ay0);
-            ax1 = fmaf(wb, b.x, ax1); ay1 = fmaf(wb, b.y, ay1);
-            m1 = fmaxf(m1, fmaxf(a.x, b.x));
-            m2 = fmaxf(m2, fmaxf(a.y, b.y));
-            m3 = fmaxf(m3, fmaxf(a.x * a.y, b.x * b.y));
-          });
-          const float v0 = own.x * m1, v1 = own.y * m2, v2 = (own.x * own.y) * m3;
-          if (v0 > best[0]) { best[0] = v0; besth[0] = hoff; }
-          if (v1 > best[1]) { best[1] = v1; besth[1] = hoff; }
-          if (v2 > best[2]) { best[2] = v2; besth[2] = hoff; }
-        } else {
-          stream.consume(L.n0 * ESZ, [&](uint32_t addr) {
-            const uint4 q = lds128u(addr);
-            const float2 a = lds64(tab + q.x), b = lds64(tab + q.z);
-            const float wa = __uint_as_float(q.y), wb = __uint_as_float(q.w);
-            ax0 = fmaf(wa, a.x, ax0); ay0 = fmaf(wa, a.y, ay0);
-            ax1 = fmaf(wb, b.x, ax1); ay1 = fmaf(wb, b.y, ay1);
-          });
+          for (int e = 0; e < 6; e++) g[e] = 0.0f;
         }
-        const float SX = own.x * (ax0 + ax1), SY = own.y * (ay0 + ay1);
-        lp_acc -= 0.5f * (SX + SY);  // every match is in two lists
-        gx = -SX;
-        gy = -SY;
-      } else {
-        gx = gy = 0.0f;
-        float lp2 = 0.0f, lpw = 0.0f, m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
-        stream.consume(L.n0 * ESZ, [&](uint32_t addr) {
-          const uint4 q = lds128u(addr);  // one entry: off, w, w*y_x, w*y_y
-          const float2 a = lds64(tab + q.x);
-          const float w = __uint_as_float(q.y), wyx = __uint_as_float(q.z), wyy = __uint_as_float(q.w);
-          const float X = own.x * a.x, Y = own.y * a.y;
-          const float Xc = fminf(X, 15.0f), Yc = fminf(Y, 15.0f);
-          if (home) {  // warp-uniform
-            lp2 = fmaf(wyx, lg2_approx(Xc), lp2);
-            lp2 = fmaf(wyy, lg2_approx(Yc), lp2);
-            lpw = fmaf(w, Xc + Yc, lpw);
-            m1 = fmaxf(m1, Xc);
-            m2 = fmaxf(m2, Yc);
-            m3 = fmaxf(m3, Xc * Yc);
+        float2 own = lds64(tab + L.own_off);
+        if (L.kind >= kH0) { const float s = own.x; own.x = own.y; own.y = s; }
+        const bool home = (L.kind & 1) == 0;
+        float gx, gy;
+        if (!CLIP) {
+          float ax0 = 0.0f, ay0 = 0.0f, ax1 = 0.0f, ay1 = 0.0f;
+          if (home) {
+            float m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
+#pragma unroll 4
+            for (; a < e_end; a += 16) {
+              const uint4 q = lds128u(a);  // two entries
+              const float2 ea = lds64(tab + q.x), eb = lds64(tab + q.z);
+              const float wa = __uint_as_float(q.y), wb = __uint_as_float(q.w);
+              ax0 = fmaf(wa, ea.x, ax0); ay0 = fmaf(wa, ea.y, ay0);
+              ax1 = fmaf(wb, eb.x, ax1); ay1 = fmaf(wb, eb.y, ay1);
+              m1 = fmaxf(m1, fmaxf(ea.x, eb.x));
+              m2 = fmaxf(m2, fmaxf(ea.y, eb.y));
+              m3 = fmaxf(m3, fmaxf(ea.x * ea.y, eb.x * eb.y));
+            }
+            const float v0 = own.x * m1, v1 = own.y * m2, v2 = (own.x * own.y) * m3;
+            if (v0 > best[0]) { best[0] = v0; besth[0] = hoff; }
+            if (v1 > best[1]) { best[1] = v1; besth[1] = hoff; }
+            if (v2 > best[2]) { best[2] = v2; besth[2] = hoff; }
+          } else {
+#pragma unroll 4
+            for (; a < e_end; a += 16) {
+              const uint4 q = lds128u(a);
+              const float2 ea = lds64(tab + q.x), eb = lds64(tab + q.z);
+              const float wa = __uint_as_float(q.y), wb = __uint_as_float(q.w);
+              ax0 = fmaf(wa, ea.x, ax0); ay0 = fmaf(wa, ea.y, ay0);
+              ax1 = fmaf(wb, eb.x, ax1); ay1 = fmaf(wb, eb.y, ay1);
+            }
           }
-          gx += X < 15.0f ? fmaf(-w, X, wyx) : 0.0f;
-          gy += Y < 15.0f ? fmaf(-w, Y, wyy) : 0.0f;
-        });
-        if (home) {
-          lp_acc += fmaf(lp2, kLn2, -lpw);
-          if (m1 > best[0]) { best[0] = m1; besth[0] = hoff; }
-          if (m2 > best[1]) { best[1] = m2; besth[1] = hoff; }
-          if (m3 > best[2]) { best[2] = m3; besth[2] = hoff; }
+          const float SX = own.x * (ax0 + ax1), SY = own.y * (ay0 + ay1);
+          lp_acc -= 0.5f * (SX + SY);  // every match is in two lists
+          gx = -SX;
+          gy = -SY;
+        } else {
+          gx = gy = 0.0f;
+          float lp2 = 0.0f, lpw = 0.0f, m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
+#pragma unroll 2
+          for (; a < e_end; a += 16) {
+            const uint4 q = lds128u(a);  // one entry: off, w, w*y_x, w*y_y
+            const float2 ea = lds64(tab + q.x);
+            const float w = __uint_as_float(q.y), wyx = __uint_as_float(q.z), wyy = __uint_as_float(q.w);
+            const float X = own.x * ea.x, Y = own.y * ea.y;
+            const float Xc = fminf(X, 15.0f), Yc = fminf(Y, 15.0f);
+            if (home) {  // warp-uniform
+              lp2 = fmaf(wyx, lg2_approx(Xc), lp2);
+              lp2 = fmaf(wyy, lg2_approx(Yc), lp2);
+              lpw = fmaf(w, Xc + Yc, lpw);
+              m1 = fmaxf(m1, Xc);
+              m2 = fmaxf(m2, Yc);
+              m3 = fmaxf(m3, Xc * Yc);
+            }
+            gx += X < 15.0f ? fmaf(-w, X, wyx) : 0.0f;
+            gy += Y < 15.0f ? fmaf(-w, Y, wyy) : 0.0f;
+          }
+          if (home) {
+            lp_acc += fmaf(lp2, kLn2, -lpw);
+            if (m1 > best[0]) { best[0] = m1; besth[0] = hoff; }
+            if (m2 > best[1]) { best[1] = m2; besth[1] = hoff; }
+            if (m3 > best[2]) { best[2] = m3; besth[2] = hoff; }
+          }
         }
-      }
-      add_own(g, L.kind, gx, gy);
-      if (kp.Cf > 0) {
-        cacc += L.kind == kH1 ? gx - gy : gy - gx;  // d/d (A - B) of the virtual team
-        if (L.flags & kVteamLast) {
-          if (ln.active) ln.sc[(long long)L.vteam * kp.Cpad] = cacc;
-          cacc = 0.0f;
+        add_own(g, L.kind, gx, gy);
+        if (kp.Cf > 0) {
+          cacc += L.kind == kH1 ? gx - gy : gy - gx;  // d/d (A - B) of the virtual team
+          if (L.flags & kVteamLast) {
+            if (ln.active) ln.sc[(size_t)L.vteam * kp.Cpad] = cacc;
+            cacc = 0.0f;
+          }
         }
+        if (L.flags & kTeamLast) put_raw<false>(kp, ln, (int)L.team, g, hacc);
       }
-      if (L.flags & kTeamLast) put_raw<false>(kp, ln, (int)L.team, g, hacc);
+      ring.release(k);
     }
   }
   const uint32_t b2_0 = __ldg(kp.warp_b2 + warp), b2_1 = __ldg(kp.warp_b2 + warp + 1);
-  stream.begin(kp.stream2 + b2_0, b2_1 - b2_0);  // tau lists start streaming in during the bounds step
+  ring.begin(kp.stream2 + b2_0, b2_1 - b2_0);  // tau pieces start streaming in during the bounds step
 
   // ---- bounds (bpl/_util.py:17-31) ------------------------------------------------------------------
 #pragma unroll
@@ -416,7 +442,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
   const float r = sigmoid_clipped(ln.ld(o.raw));
   const float cc = fmaf(r, UB - LB, LB);
 
-  // ---- arg-max search: warp w looks at entries w, w+W, ... of each chain's two arg-max lists -----------
+  // ---- arg-max search: warp w looks at entries w, w+W, ... of each chain's two arg-max pieces -----------
 #pragma unroll 1
   for (int which = 0; which < 2; which++) {
     const bool need = which == 0 || best[2] > 1.0f;  // UB = 1: no dependence on the rates
@@ -429,105 +455,127 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
     if (L.kind >= kH0) { const float s = own.x; own.x = own.y; own.y = s; }
     const unsigned char* ent = kp.stream1 + hoff + 16;
     const uint32_t nmax = __reduce_max_sync(kFull, n);
-    uint32_t found = 0xffffffffu;
+    uint32_t found = 0xffffffffu, info = 0u;
 #pragma unroll 4
     for (uint32_t i = warp; i < nmax; i += W) {
       if (i < n) {
         const uint32_t off = __ldg(reinterpret_cast<const uint32_t*>(ent + (size_t)i * ESZ));
-        const float2 a = lds64(tab + off);
+        const float2 ea = lds64(tab + off);
+        const float X = own.x * ea.x, Y = own.y * ea.y;
         float val;
         if (CLIP) {
-          const float Xc = fminf(own.x * a.x, 15.0f), Yc = fminf(own.y * a.y, 15.0f);
+          const float Xc = fminf(X, 15.0f), Yc = fminf(Y, 15.0f);
           val = q == 0 ? Xc : (q == 1 ? Yc : Xc * Yc);
         } else {
-          val = q == 0 ? own.x * a.x : (q == 1 ? own.y * a.y : (own.x * own.y) * (a.x * a.y));
+          val = q == 0 ? X : (q == 1 ? Y : (own.x * own.y) * (ea.x * ea.y));
         }
-        if (val == target) found = min(found, (i << 24) | off);
+        if (val == target && ((i << 24) | off) < found) {
+          found = (i << 24) | off;
+          // own vteam | kind | "X not clipped" | "Y not clipped"
+          info = L.vteam | (L.kind << 16) | ((!CLIP || X < 15.0f) ? 1u << 18 : 0u) | ((!CLIP || Y < 15.0f) ? 1u << 19 : 0u);
+        }
       }
     }
-    if (found != 0xffffffffu) atomicMin(red_found + which * 32 + lane, found);
+    if (found != 0xffffffffu) {
+      atomicMin(red_found + which * 32 + lane, found);
+      red_info[which * 32 + lane] = info;  // several finders only under exact ties: any of them will do
+    }
   }
 
   // ---- phase 2: tau terms (bpl/_util.py:54-91) -----------------------------------------------------
   float gc = 0.0f;
   {
     float g[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f}, cacc = 0.0f;
-    while (stream.pos < stream.total) {
-      const Hdr L = stream.header();
-      if (L.flags & kTeamFirst) {
+    const uint32_t nst = ring.num_stages();
+    for (uint32_t k = 0; k < nst; k++) {
+      uint32_t bytes;
+      const uint32_t a0 = ring.acquire(k, &bytes);
+      uint32_t a = a0;
+      const uint32_t aend = a0 + bytes;
+      while (a < aend) {
+        const Hdr L = unpack_hdr(lds128u(a));
+        a += 16;
+        if (L.flags & kTeamFirst) {
 #pragma unroll
-        for (int e = 0; e < 6; e++) g[e] = 0.0f;
-      }
-      float2 own = lds64(tab + L.own_off);
-      if (L.kind >= kH0) { const float s = own.x; own.x = own.y; own.y = s; }
-      const bool home = (L.kind & 1) == 0;
-      const float Pxy = own.x * own.y;
-      float uxy = 0.0f, ux = 0.0f, uy = 0.0f, lt = 0.0f;     // unmasked (d/d corr_coef)
-      float sxy_x = 0.0f, sxy_y = 0.0f, sx = 0.0f, sy = 0.0f;  // masked by "rate not clipped"
-      // one entry = (opponent row offset, w); the ring is read two entries (16 bytes) at a time
-      auto xy = [&](uint32_t off, float w) {  // tau = 1 - c X Y
-        const float2 a = lds64(tab + off);
-        float t;
-        if (CLIP) {
-          const float Xr = own.x * a.x, Yr = own.y * a.y;
-          t = fminf(Xr, 15.0f) * fminf(Yr, 15.0f);
-          const float tau = fmaxf(fmaf(-cc, t, 1.0f), 0.0f);
-          const float val = (w * t) * rcp_approx(tau);
-          uxy += val;
-          sxy_x += Xr < 15.0f ? val : 0.0f;
-          sxy_y += Yr < 15.0f ? val : 0.0f;
-          if (home) lt = fmaf(w, lg2_approx(tau), lt);
-        } else {
-          t = Pxy * (a.x * a.y);
-          const float tau = fmaxf(fmaf(-cc, t, 1.0f), 0.0f);
-          uxy = fmaf(w * t, rcp_approx(tau), uxy);
-          if (home) lt = fmaf(w, lg2_approx(tau), lt);
+          for (int e = 0; e < 6; e++) g[e] = 0.0f;
         }
-      };
-      auto one = [&](uint32_t off, float w, bool is_x, float& u, float& s) {  // tau = 1 + c X  (or Y)
-        const float2 a = lds64(tab + off);
-        const float Rr = is_x ? own.x * a.x : own.y * a.y;
-        const float R = CLIP ? fminf(Rr, 15.0f) : Rr;
-        const float tau = fmaxf(fmaf(cc, R, 1.0f), 0.0f);
-        const float val = (w * R) * rcp_approx(tau);
-        u += val;
-        if (CLIP) s += Rr < 15.0f ? val : 0.0f;
-        if (home) lt = fmaf(w, lg2_approx(tau), lt);
-      };
-      stream.consume(L.n0 * (uint32_t)sizeof(Entry), [&](uint32_t addr) {
-        const uint4 q = lds128u(addr);
-        xy(q.x, __uint_as_float(q.y));
-        xy(q.z, __uint_as_float(q.w));
-      });
-      stream.consume(L.n1 * (uint32_t)sizeof(Entry), [&](uint32_t addr) {
-        const uint4 q = lds128u(addr);
-        one(q.x, __uint_as_float(q.y), true, ux, sx);
-        one(q.z, __uint_as_float(q.w), true, ux, sx);
-      });
-      stream.consume(L.n2 * (uint32_t)sizeof(Entry), [&](uint32_t addr) {
-        const uint4 q = lds128u(addr);
-        one(q.x, __uint_as_float(q.y), false, uy, sy);
-        one(q.z, __uint_as_float(q.w), false, uy, sy);
-      });
-      if (!CLIP) { sxy_x = sxy_y = uxy; sx = ux; sy = uy; }
-      if (home) {
-        lp_acc = fmaf(lt, kLn2, lp_acc);
-        gc += ux + uy - uxy;
-      }
-      const float gx = cc * (sx - sxy_x), gy = cc * (sy - sxy_y);
-      add_own(g, L.kind, gx, gy);
-      if (kp.Cf > 0) {
-        cacc += L.kind == kH1 ? gx - gy : gy - gx;
-        if (L.flags & kVteamLast) {
-          if (ln.active) red_add(ln.sc + (long long)L.vteam * kp.Cpad, cacc);
-          cacc = 0.0f;
+        float2 own = lds64(tab + L.own_off);
+        if (L.kind >= kH0) { const float s = own.x; own.x = own.y; own.y = s; }
+        const bool home = (L.kind & 1) == 0;
+        float lt = 0.0f, uxy = 0.0f, sxy_x = 0.0f, sxy_y = 0.0f;
+        {  // tau = 1 - c X Y
+          const float Pxy = own.x * own.y;
+          const uint32_t e_end = a + L.n0 * (uint32_t)sizeof(Entry);
+#pragma unroll 2
+          for (; a < e_end; a += 16) {
+            const uint4 q = lds128u(a);  // two entries (opponent row offset, w)
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+              const float2 ea = lds64(tab + (j ? q.z : q.x));
+              const float w = __uint_as_float(j ? q.w : q.y);
+              if (CLIP) {
+                const float Xr = own.x * ea.x, Yr = own.y * ea.y;
+                const float t = fminf(Xr, 15.0f) * fminf(Yr, 15.0f);
+                const float tau = fmaxf(fmaf(-cc, t, 1.0f), 0.0f);
+                const float val = (w * t) * rcp_approx(tau);
+                uxy += val;
+                sxy_x += Xr < 15.0f ? val : 0.0f;
+                sxy_y += Yr < 15.0f ? val : 0.0f;
+                if (home) lt = fmaf(w, lg2_approx(tau), lt);
+              } else {
+                const float t = Pxy * (ea.x * ea.y);
+                const float tau = fmaxf(fmaf(-cc, t, 1.0f), 0.0f);
+                uxy = fmaf(w * t, rcp_approx(tau), uxy);
+                if (home) lt = fmaf(w, lg2_approx(tau), lt);
+              }
+            }
+          }
         }
+        float u1[2] = {0.0f, 0.0f}, s1[2] = {0.0f, 0.0f};  // tau = 1 + c X, then tau = 1 + c Y
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          const float oc = c == 0 ? own.x : own.y;
+          const uint32_t e_end = a + (c == 0 ? L.n1 : L.n2) * (uint32_t)sizeof(Entry);
+          float u = 0.0f, sm = 0.0f;
+#pragma unroll 2
+          for (; a < e_end; a += 16) {
+            const uint4 q = lds128u(a);
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+              const float Rr = oc * lds32(tab + (j ? q.z : q.x));  // `off` already selects .x or .y
+              const float w = __uint_as_float(j ? q.w : q.y);
+              const float R = CLIP ? fminf(Rr, 15.0f) : Rr;
+              const float tau = fmaxf(fmaf(cc, R, 1.0f), 0.0f);
+              const float val = (w * R) * rcp_approx(tau);
+              u += val;
+              if (CLIP) sm += Rr < 15.0f ? val : 0.0f;
+              if (home) lt = fmaf(w, lg2_approx(tau), lt);
+            }
+          }
+          u1[c] = u;
+          s1[c] = CLIP ? sm : u;
+        }
+        if (!CLIP) sxy_x = sxy_y = uxy;
+        if (home) {
+          lp_acc = fmaf(lt, kLn2, lp_acc);
+          gc += u1[0] + u1[1] - uxy;
+        }
+        const float gx = cc * (s1[0] - sxy_x), gy = cc * (s1[1] - sxy_y);
+        add_own(g, L.kind, gx, gy);
+        if (kp.Cf > 0) {
+          cacc += L.kind == kH1 ? gx - gy : gy - gx;
+          if (L.flags & kVteamLast) {
+            if (ln.active) red_add(ln.sc + (size_t)L.vteam * kp.Cpad, cacc);
+            cacc = 0.0f;
+          }
+        }
+        if (L.flags & kTeamLast) put_raw<true>(kp, ln, (int)L.team, g, hacc);
       }
-      if (L.flags & kTeamLast) put_raw<true>(kp, ln, (int)L.team, g, hacc);
+      ring.release(k);
     }
   }
   red_gc[warp * 32 + lane] = gc;
-  __syncthreads();
+  __syncthreads();  // tables are dead from here on; raw slots hold both phases
   gc = 0.0f;
   for (int w = 0; w < W; w++) gc += red_gc[w * 32 + lane];
   {  // the 1-1 matches: tau = 1 - c for all of them
@@ -536,40 +584,40 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
     if (warp == 0 && kp.w11 != 0.0f) lp_acc = fmaf(kp.w11, logf(t11), lp_acc);
   }
 
-  // ---- arg-max fix-up: warp 0, every chain in its own lane -----------------------
-  if (warp == 0 && ln.active) {
-#pragma unroll 1
-    for (int which = 0; which < 2; which++) {
-      const uint32_t packed = red_found[which * 32 + lane];
-      if (packed == 0xffffffffu) continue;  // UB = 1 (or nothing matched: cannot happen, same arithmetic as phase 1)
+  // ---- arg-max fix-up: every warp works out the two matches of its chain and folds
+  //      them into the team pass below ---------------------------------------------------------------------
+  Fixup fx;
+  fx.h1 = 0u;
+  fx.confs = 0u;
+#pragma unroll
+  for (int which = 0; which < 2; which++) {
+    const uint32_t packed = red_found[which * 32 + lane];
+    fx.teams[which] = 0xffffffffu;
+    fx.vts[which] = 0u;
+    fx.vx[which] = fx.vy[which] = 0.0f;
+    if (packed != 0xffffffffu) {  // else: UB = 1 (or nothing matched: cannot happen, same arithmetic as phase 1)
+      const uint32_t info = red_info[which * 32 + lane];
       const uint32_t f_off = packed & 0xffffffu;
-      const uint32_t hoff = which == 0 ? (qlam == 0 ? besth[0] : besth[1]) : besth[2];
-      const Hdr L = unpack_hdr(__ldg(reinterpret_cast<const uint4*>(kp.stream1 + hoff)));
-      float2 own = lds64(tab + L.own_off);
-      if (L.kind >= kH0) { const float s = own.x; own.x = own.y; own.y = s; }
-      const float2 a = lds64(tab + f_off);
-      const float f_x = own.x * a.x, f_y = own.y * a.y;
-      const bool h1 = L.kind == kH1;
-      const int opp_v = (int)((f_off - (h1 ? kp.tabQ1 : kp.tabP0)) / kRowBytes);
-      const int own_v = (int)L.vteam;
-      // weights of the two log-rates of the arg-max match (zero through a clipped rate)
-      float wx = 0.0f, wy = 0.0f;
+      const bool h1 = ((info >> 16) & 3u) == kH1;
+      const uint32_t own_v = info & 0xffffu;
+      const uint32_t opp_v = (f_off - (h1 ? kp.tabQ1 : kp.tabP0)) / kRowBytes;
+      const bool xfree = (info >> 18) & 1u, yfree = (info >> 19) & 1u;
       if (which == 0) {
         const float wgt = gc * (1.0f - r) / Lam;  // dc/dLB * dLB/d eta
-        if (qlam == 0) wx = (!CLIP || f_x < 15.0f) ? wgt : 0.0f;
-        else wy = (!CLIP || f_y < 15.0f) ? wgt : 0.0f;
+        fx.vx[0] = (qlam == 0 && xfree) ? wgt : 0.0f;
+        fx.vy[0] = (qlam == 1 && yfree) ? wgt : 0.0f;
       } else {
         const float wgt = -gc * r / best[2];  // dc/dUB * dUB/d eta (UB = 1 / max lambda_h lambda_a)
-        wx = (!CLIP || f_x < 15.0f) ? wgt : 0.0f;
-        wy = (!CLIP || f_y < 15.0f) ? wgt : 0.0f;
+        fx.vx[1] = xfree ? wgt : 0.0f;
+        fx.vy[1] = yfree ? wgt : 0.0f;
       }
-      add_exponent(kp, ln, own_v, h1 ? eAh1 : eB0, wx, hacc);  // own exponents of X, Y
-      add_exponent(kp, ln, own_v, h1 ? eBh1 : eA0, wy, hacc);
-      add_exponent(kp, ln, opp_v, h1 ? eBa1 : eA0, wx, hacc);  // the opponent's
-      add_exponent(kp, ln, opp_v, h1 ? eAa1 : eB0, wy, hacc);
+      fx.h1 |= (h1 ? 1u : 0u) << which;
+      fx.vts[which] = own_v | (opp_v << 16);
+      fx.teams[which] = (uint32_t)__ldg(kp.v_team + own_v) | ((uint32_t)__ldg(kp.v_team + opp_v) << 16);
+      if (kp.Cf > 0)
+        fx.confs |= ((uint32_t)__ldg(kp.v_conf + own_v) | ((uint32_t)__ldg(kp.v_conf + opp_v) << 8)) << (16 * which);
     }
   }
-  __syncthreads();  // tables are dead from here on; every raw slot is final
 
   // ---- team pass: raw slots -> parameter gradients, priors, hyper-parameter sums ---------------------------
   const bool has_rho = !dc;
@@ -589,9 +637,22 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
       const float za = ln.ld(o.za + t), zd = ln.ld(o.zd + t);
       const float4 ys = __ldg(reinterpret_cast<const float4*>(kp.yteam + (size_t)t * 8));
       const float2 ys2 = __ldg(reinterpret_cast<const float2*>(kp.yteam + (size_t)t * 8 + 4));
-      const float ystat[6] = {ys.x, ys.y, ys.z, ys.w, ys2.x, ys2.y};
-      const float ra = ld_cg(ln.g(o.za + t)) + ystat[0];
-      const float rd = ld_cg(ln.g(o.zd + t)) + ystat[1];
+      float ra = ld_cg(ln.g(o.za + t)) + ys.x;
+      float rd = ld_cg(ln.g(o.zd + t)) + ys.y;
+      float rx[4] = {ys.z, ys.w, ys2.x, ys2.y};
+      float dec[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        if (i < ndec) {
+          dec[i] = ln.ld(o.dec[i] + t);
+          rx[i] += ld_cg(ln.g(o.dec[i] + t));
+        }
+      }
+#pragma unroll
+      for (int which = 0; which < 2; which++) {
+        if ((fx.teams[which] & 0xffffu) == (uint32_t)t) fold_fixup(fx, which, 0, ra, rd, rx);
+        if ((fx.teams[which] >> 16) == (uint32_t)t) fold_fixup(fx, which, 1, ra, rd, rx);
+      }
       float p_za, p_zd;
       if (has_rho) {  // za ~ N(0,1), zd ~ N(rho za, sqrt(1-rho^2))  (extended_dixon_coles.py:165-174)
         const float e = zd - rho * za;
@@ -612,16 +673,14 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
       a_ls_a = fmaf(hy.sig_a * za, ra, a_ls_a);
       a_ls_d = fmaf(hy.sig_d * zd, rd, a_ls_d);
       a_mu_d += rd;
-      if (dc) a_mu[0] += ystat[2];
+      if (dc) a_mu[0] += rx[0];
 #pragma unroll
       for (int i = 0; i < 4; i++) {
         if (i < ndec) {
-          const float dec = ln.ld(o.dec[i] + t);
-          const float rx = ld_cg(ln.g(o.dec[i] + t)) + ystat[2 + i];
-          lp_acc -= 0.5f * dec * dec;
-          if (ln.active) *ln.g(o.dec[i] + t) = fmaf(hy.sig[i], rx, -dec);
-          a_mu[i] += rx;
-          a_ls[i] = fmaf(hy.sig[i] * dec, rx, a_ls[i]);
+          lp_acc -= 0.5f * dec[i] * dec[i];
+          if (ln.active) *ln.g(o.dec[i] + t) = fmaf(hy.sig[i], rx[i], -dec[i]);
+          a_mu[i] += rx[i];
+          a_ls[i] = fmaf(hy.sig[i] * dec[i], rx[i], a_ls[i]);
         }
       }
       if (kp.K > 0) {  // rows for the covariate-coefficient pass
@@ -637,7 +696,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
     float s = __ldg(kp.yconf + k) - cf;
     lp_acc -= 0.5f * cf * cf;
     const int j0 = __ldg(kp.conf_vptr + k), j1 = __ldg(kp.conf_vptr + k + 1);
-    for (int j = j0; j < j1; j++) s += ld_cg(ln.sc + (long long)__ldg(kp.conf_vlist + j) * kp.Cpad);
+    for (int j = j0; j < j1; j++) s += ld_cg(ln.sc + (size_t)__ldg(kp.conf_vlist + j) * kp.Cpad);
+#pragma unroll
+    for (int ws = 0; ws < 4; ws++)
+      if (fx.teams[ws >> 1] != 0xffffffffu && ((fx.confs >> (8 * ((ws >> 1) * 2 + (ws & 1)))) & 0xffu) == (uint32_t)k)
+        s += fixup_conf(fx, ws >> 1, ws & 1);
     if (ln.active) *ln.g(o.conf + k) = s;
   }
 
@@ -651,53 +714,59 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
     p[12 * 32] = a_rho;
   }
   __syncthreads();
-  // covariate coefficients: d/d beta[k] = sum_t Xs[t,k] * d/d (att | def)[t]; N(0,1) prior
-  for (int task = warp; task < 2 * kp.K; task += W) {
-    const int k = task >> 1, isd = task & 1;
-    const float* rows = reinterpret_cast<const float*>(smem + kp.epi_team) + isd * 32 + lane;
-    const int d = (isd ? o.beta_d : o.beta_a) + k;
-    float s = -ln.ld(d);
-    for (int t = 0; t < kp.T; t++) s = fmaf(__ldg(kp.Xs + (size_t)t * kp.K + k), rows[(size_t)t * 64], s);
-    if (ln.active) *ln.g(d) = s;
-  }
-  if (warp != 0) return;
+  // the epilogue items are dealt round-robin to the warps: scalar hyper sites, u, corr_coef_raw, coefficients
   auto total = [&](int row) {
     float s = 0.0f;
     for (int w = 0; w < W; w++) s += part[((size_t)w * kPartRows + row) * 32 + lane];
     return s;
   };
-  float lp = total(0) + kp.const_term;
-  for (int h = 0; h < kp.nhyper; h++) {
-    const HyperDesc hd = kp.hyper[h];
-    const float x = ln.ld(hd.off);
-    const float acc = total(hd.row);
-    float gval;
-    if (hd.kind == 0) {  // Normal(loc, scale)
-      const float z = (x - hd.loc) * hd.inv_scale;
-      lp -= 0.5f * z * z;
-      gval = fmaf(-z, hd.inv_scale, acc);
-    } else {  // HalfNormal(scale) on exp(x) + Jacobian x
-      const float z = expf(x) * hd.inv_scale;
-      lp += fmaf(-0.5f * z, z, x);
-      gval = fmaf(-z, z, 1.0f) + acc;
+  float lp = 0.0f;
+  const int n_items = kp.nhyper + 2 + 2 * kp.K;
+  for (int item = warp; item < n_items; item += W) {
+    if (item < kp.nhyper) {
+      const HyperDesc hd = kp.hyper[item];
+      const float x = ln.ld(hd.off);
+      const float acc = total(hd.row);
+      float gval;
+      if (hd.kind == 0) {  // Normal(loc, scale)
+        const float z = (x - hd.loc) * hd.inv_scale;
+        lp -= 0.5f * z * z;
+        gval = fmaf(-z, hd.inv_scale, acc);
+      } else {  // HalfNormal(scale) on exp(x) + Jacobian x
+        const float z = expf(x) * hd.inv_scale;
+        lp += fmaf(-0.5f * z, z, x);
+        gval = fmaf(-z, z, 1.0f) + acc;
+      }
+      if (ln.active) *ln.g(hd.off) = gval;
+    } else if (item == kp.nhyper) {
+      if (has_rho) {  // u ~ Beta(2,4) + sigmoid Jacobian; rho = 2u - 1; sum_t -log sqrt(1 - rho^2)
+        lp += 0.5f * (float)kp.T * logf(inv_s2) + 2.0f * logf(u) + 4.0f * logf(1.0f - u);
+        if (ln.active) *ln.g(o.u) = 2.0f - 6.0f * u + total(12) * 2.0f * u * (1.0f - u);
+      }
+    } else if (item == kp.nhyper + 1) {
+      // corr_coef_raw ~ Beta(2,2) + Jacobian; corr_coef = LB + r (UB - LB); also the likelihood + team-prior sum
+      lp += total(0) + 2.0f * (logf(r) + logf(1.0f - r));
+      if (ln.active) {
+        *ln.g(o.raw) = 2.0f * (1.0f - 2.0f * r) + gc * r * (1.0f - r) * (UB - LB);
+        if (kp.corr_coef) kp.corr_coef[chain] = cc;
+      }
+    } else {  // covariate coefficients: d/d beta[k] = sum_t Xs[t,k] * d/d (att | def)[t]; N(0,1) prior
+      const int task = item - kp.nhyper - 2, k = task >> 1, isd = task & 1;
+      const float* rows = reinterpret_cast<const float*>(smem + kp.epi_team) + isd * 32 + lane;
+      const int d = (isd ? o.beta_d : o.beta_a) + k;
+      const float b = ln.ld(d);
+      float s = -b;
+      lp -= 0.5f * b * b;
+      for (int t = 0; t < kp.T; t++) s = fmaf(__ldg(kp.Xs + (size_t)t * kp.K + k), rows[(size_t)t * 64], s);
+      if (ln.active) *ln.g(d) = s;
     }
-    if (ln.active) *ln.g(hd.off) = gval;
   }
-  for (int k = 0; k < kp.K; k++) {
-    const float ba = ln.ld(o.beta_a + k), bd = ln.ld(o.beta_d + k);
-    lp -= 0.5f * (ba * ba + bd * bd);
-  }
-  if (has_rho) {  // u ~ Beta(2,4) + sigmoid Jacobian; rho = 2u - 1; sum_t -log sqrt(1 - rho^2)
-    lp += 0.5f * (float)kp.T * logf(inv_s2);
-    lp += 2.0f * logf(u) + 4.0f * logf(1.0f - u);
-    if (ln.active) *ln.g(o.u) = 2.0f - 6.0f * u + total(12) * 2.0f * u * (1.0f - u);
-  }
-  // corr_coef_raw ~ Beta(2,2) + Jacobian; corr_coef = LB + r (UB - LB)
-  lp += 2.0f * (logf(r) + logf(1.0f - r));
-  if (ln.active) {
-    *ln.g(o.raw) = 2.0f * (1.0f - 2.0f * r) + gc * r * (1.0f - r) * (UB - LB);
+  red_gc[warp * 32 + lane] = lp;  // every warp read its gc sum before the previous barrier: the rows are free
+  __syncthreads();
+  if (warp == 0 && ln.active) {
+    lp = kp.const_term;
+    for (int w = 0; w < W; w++) lp += red_gc[w * 32 + lane];
     kp.lp[chain] = lp;
-    if (kp.corr_coef) kp.corr_coef[chain] = cc;
   }
 }
 

@@ -334,7 +334,7 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err, int 
     for (int v = 0; v < V; v++)
       for (int k = 0; k < 4; k++) {
         const size_t n = raw[(size_t)v * 4 + k].size();
-        if (n) cost[P.v_team[v]] += per_list * (double)((n + kListMax - 1) / kListMax) + per_entry * (double)n;
+        if (n) cost[P.v_team[v]] += per_list * (1.0 + (double)n / 100.0) + per_entry * (double)n;
       }
     for (int t = 0; t < T; t++)
       if (cost[t] > 0.0) cost[t] += per_team;
@@ -357,27 +357,43 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err, int 
     for (auto& v : *teams) std::sort(v.begin(), v.end());
     return *std::max_element(load.begin(), load.end());
   };
-  // rough instruction counts per entry / list / team of the two phases
+  // rough instruction counts per entry / list piece / team of the two phases
   const std::vector<double> cost1 = team_costs(raw1, kp.clip ? 16.0 : 6.0, 40.0, 30.0);
   const std::vector<double> cost2 = team_costs(raw2, 12.0, 60.0, 30.0);
-  int W = 16;
+  // shared memory left for the rings decides how many warps / which stage size fit
+  auto smem_need = [&](int W, uint32_t stage) {
+    const uint32_t epi = (K > 0 ? (uint32_t)T * kRowBytes : 0u) + (uint32_t)W * kPartRows * 128u;
+    const uint32_t tabb = (std::max(table_bytes, epi) + 127u) / 128u * 128u;
+    return tabb + (uint32_t)W * kStages * stage + 128u + (uint32_t)W * kStages * 8u + 3u * 256u + 2u * 128u + 2u * 128u +
+           (uint32_t)W * 128u;
+  };
+  const uint32_t kSmemMax = 227u * 1024u;
+  int W = 0;
+  uint32_t stage = 1024;
   std::vector<std::vector<int>> w1, w2;
   if (force_warps <= 0) {
     if (const char* e = getenv("BPLX_NWARPS")) force_warps = atoi(e);
   }
+  if (const char* e = getenv("BPLX_STAGE")) stage = (uint32_t)atoi(e) == 512u ? 512u : 1024u;
   if (force_warps > 0) {
-    W = std::min(force_warps, kMaxWarps);
+    W = std::max(1, std::min(force_warps, kMaxWarps));
+    if (smem_need(W, stage) > kSmemMax) stage = 512;
   } else {
     // the makespan of the slower warp decides; more warps than needed only cost shared memory
     double best = 0.0;
-    for (int cand : {8, 12, 16, 20, 24}) {
+    for (int cand : {4, 8, 12, 16, 20, 24}) {
       if (cand > kMaxWarps) continue;
+      uint32_t st = stage;
+      if (smem_need(cand, st) > kSmemMax) st = 512;
+      if (smem_need(cand, st) > kSmemMax) continue;
       std::vector<std::vector<int>> t1, t2;
-      const double span = assign(cost1, cand, &t1) + assign(cost2, cand, &t2) + 4.0 * cand;
-      if (best == 0.0 || span < 0.97 * best) best = span, W = cand;
+      const double span = assign(cost1, cand, &t1) + assign(cost2, cand, &t2) + 4.0 * cand + (st == 512 ? 0.05 * best : 0.0);
+      if (W == 0 || span < 0.97 * best) best = span, W = cand, stage = st;
     }
+    if (W == 0) W = 4, stage = 512;
   }
   kp.nwarps = W;
+  kp.stage_bytes = stage;
   assign(cost1, W, &w1);
   assign(cost2, W, &w2);
 
@@ -395,63 +411,77 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err, int 
     const auto& by_warp = phase == 1 ? w1 : w2;
     std::vector<unsigned char>& S = phase == 1 ? P.stream1 : P.stream2;
     std::vector<uint32_t>& wb = phase == 1 ? P.warp_b1 : P.warp_b2;
+    const size_t esz = (phase == 1 && kp.clip) ? sizeof(EntryClip) : sizeof(Entry);
     S.clear();
     for (int w = 0; w < W; w++) {
+      const size_t wstart = S.size();
       for (int t : by_warp[w]) {
         size_t team_first_hdr = (size_t)-1, last_hdr = 0;
         for (int v = P.team_vptr[t]; v < P.team_vptr[t + 1]; v++) {
           size_t vteam_last_hdr = (size_t)-1;
           for (int k = 0; k < 4; k++) {
             const auto& r = raw[(size_t)v * 4 + k];
+            if (r.empty()) continue;
             (phase == 1 ? P.n1 : P.n2) += (long long)r.size();
-            for (size_t lo = 0; lo < r.size(); lo += kListMax) {
-              const size_t hi = std::min(r.size(), lo + (size_t)kListMax);
+            // the padded entry sequence of the list, with the tau class of every entry
+            std::vector<unsigned char> body;
+            std::vector<uint8_t> cls;
+            if (phase == 1) {
+              for (const RawEntry& e : r) {
+                const uint32_t o = opp_base(k) + e.opp * kRowBytes;
+                if (kp.clip) {
+                  EntryClip x{o, (float)e.w, (float)e.wyx, (float)e.wyy};
+                  put(&body, &x, sizeof x);
+                } else {
+                  Entry x{o, (float)e.w};
+                  put(&body, &x, sizeof x);
+                }
+                cls.push_back(0);
+              }
+              if (!kp.clip && (r.size() & 1)) {  // pad to an even count with a zero-row entry
+                Entry x{opp_base(k) + zero_row, 0.0f};
+                put(&body, &x, sizeof x);
+                cls.push_back(0);
+              }
+            } else {
+              size_t i = 0;
+              for (int c = 0; c < 3; c++) {
+                const uint32_t comp = c == 2 ? 4u : 0u;  // the Y class reads the .y float of the opponent row
+                size_t cnt = 0;
+                for (; i < r.size() && r[i].cls == c; i++, cnt++) {
+                  Entry x{opp_base(k) + r[i].opp * kRowBytes + comp, (float)r[i].w};
+                  put(&body, &x, sizeof x);
+                  cls.push_back((uint8_t)c);
+                }
+                if (cnt & 1) {
+                  Entry x{opp_base(k) + zero_row + comp, 0.0f};
+                  put(&body, &x, sizeof x);
+                  cls.push_back((uint8_t)c);
+                }
+              }
+            }
+            (phase == 1 ? P.n1_padded : P.n2_padded) += (long long)cls.size();
+            // cut into pieces that stay inside a stage
+            size_t done = 0;  // entries emitted
+            while (done < cls.size()) {
+              const size_t in_stage = (S.size() - wstart) % stage;
+              const size_t space = stage - in_stage - sizeof(ListHdr);  // a multiple of 16, possibly 0
+              const size_t take = std::min(cls.size() - done, space / esz);
               ListHdr H{};
               H.own_off = own_off(v, k);
               H.vteam = (uint16_t)v;
               H.kind = (uint8_t)k;
               H.team = (uint16_t)t;
+              uint16_t cnt[3] = {0, 0, 0};
+              for (size_t i = done; i < done + take; i++) cnt[cls[i]]++;
+              H.n0 = cnt[0];
+              H.n1 = cnt[1];
+              H.n2 = cnt[2];
               const size_t hdr_at = S.size();
               put(&S, &H, sizeof H);
-              uint16_t cnt[3] = {0, 0, 0};
-              if (phase == 1) {
-                for (size_t i = lo; i < hi; i++, cnt[0]++) {
-                  const uint32_t o = opp_base(k) + r[i].opp * kRowBytes;
-                  if (kp.clip) {
-                    EntryClip e{o, (float)r[i].w, (float)r[i].wyx, (float)r[i].wyy};
-                    put(&S, &e, sizeof e);
-                  } else {
-                    Entry e{o, (float)r[i].w};
-                    put(&S, &e, sizeof e);
-                  }
-                }
-                if (!kp.clip && (cnt[0] & 1)) {  // pad to an even count with a zero-row entry
-                  Entry e{opp_base(k) + zero_row, 0.0f};
-                  put(&S, &e, sizeof e);
-                  cnt[0]++;
-                }
-                P.n1_padded += cnt[0];
-                P.nlists1++;
-              } else {
-                size_t i = lo;
-                for (int c = 0; c < 3; c++) {
-                  for (; i < hi && r[i].cls == c; i++, cnt[c]++) {
-                    Entry e{opp_base(k) + r[i].opp * kRowBytes, (float)r[i].w};
-                    put(&S, &e, sizeof e);
-                  }
-                  if (cnt[c] & 1) {
-                    Entry e{opp_base(k) + zero_row, 0.0f};
-                    put(&S, &e, sizeof e);
-                    cnt[c]++;
-                  }
-                }
-                P.n2_padded += cnt[0] + cnt[1] + cnt[2];
-                P.nlists2++;
-              }
-              ListHdr* hp = reinterpret_cast<ListHdr*>(&S[hdr_at]);
-              hp->n0 = cnt[0];
-              hp->n1 = cnt[1];
-              hp->n2 = cnt[2];
+              put(&S, body.data() + done * esz, take * esz);
+              done += take;
+              (phase == 1 ? P.nlists1 : P.nlists2)++;
               if (team_first_hdr == (size_t)-1) team_first_hdr = hdr_at;
               vteam_last_hdr = last_hdr = hdr_at;
             }
@@ -474,13 +504,13 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err, int 
   const uint32_t epi = kp.epi_part + (uint32_t)W * kPartRows * 128u;
   kp.tab_bytes = (std::max(table_bytes, epi) + 127u) / 128u * 128u;
   kp.smem_ring = kp.tab_bytes;
-  kp.smem_bar = kp.smem_ring + (uint32_t)W * kStages * kStageBytes;
+  kp.smem_bar = kp.smem_ring + (uint32_t)W * kStages * stage;
   kp.smem_red = (kp.smem_bar + (uint32_t)W * kStages * 8u + 127u) / 128u * 128u;
-  // red area: best[3][32] u64 | found[2][32] u32 | gc[W][32] f32
-  kp.smem_total = kp.smem_red + 3u * 256u + 2u * 128u + (uint32_t)W * 128u;
-  if (kp.smem_total > 227u * 1024u)
+  // red area: best[3][32] u64 | found[2][32] u32 | info[2][32] u32 | gc / lp parts [W][32] f32
+  kp.smem_total = kp.smem_red + 3u * 256u + 2u * 128u + 2u * 128u + (uint32_t)W * 128u;
+  if (kp.smem_total > kSmemMax)
     FAIL(BPLX_E_UNSUPPORTED, "problem needs %u bytes of shared memory per CTA (max %u): too many (team, confederation) pairs (%d)",
-         kp.smem_total, 227u * 1024u, V);
+         kp.smem_total, kSmemMax, V);
 #undef FAIL
   return BPLX_OK;
 }

@@ -23,9 +23,11 @@
 //                    Y = own'.y * opp.y, where own' is the own row (swapped for the neutral kinds).
 //   entry          : (byte offset of the opponent row, weight); identical (list, opponent) pairs
 //                    are merged with summed weights.
-//   stream         : what a warp reads in one phase: its lists back to back, each a 16-byte ListHdr
-//                    followed by its entries (a multiple of 16 bytes), fetched through the warp's
-//                    TMA ring.  Phase 1 = rates (Poisson part + maxima), phase 2 = tau matches.
+//   stream         : what a warp reads in one phase: its lists back to back, fetched stage by stage
+//                    (stage_bytes each) through the warp's TMA ring.  A list is stored as pieces, each
+//                    a 16-byte ListHdr followed by its entries (a multiple of 16 bytes); a piece never
+//                    straddles a stage boundary, so the kernel walks a stage with plain pointer
+//                    arithmetic.  Phase 1 = rates (Poisson part + maxima), phase 2 = tau matches.
 //   raw slot       : while the phases run, the caller's grad entries of a team's own parameters
 //                    (attack/defence pair and the venue effects) hold the gradient with respect to
 //                    the team's log-rate halves; the final team pass turns them into parameter
@@ -42,20 +44,18 @@ namespace bplx {
 
 constexpr int kChains = 32;       // chains per CTA: one lane per chain
 constexpr int kRowBytes = 256;    // one table row: float2 x 32 lanes
-constexpr int kListMax = 128;     // entries per list piece (bounds the arg-max rescan)
 constexpr int kMaxCov = 16;       // covariates supported by the kernel
 constexpr int kMaxWarps = 24;     // warps per CTA (register budget: 65536 / (24*32) = 85 per thread)
-constexpr int kStageBytes = 512;  // one TMA bulk copy of a warp's stream
-constexpr int kStages = 2;        // ring depth per warp
+constexpr int kStages = 2;        // ring depth per warp (stage size: KernelParams::stage_bytes, 512 or 1024)
 constexpr int kAccRows = 13;      // hyper accumulators: lp, mu_d, ls_a, ls_d, mu[4], ls[4], rho
 constexpr int kPartRows = 16;     // rows per warp in the final cross-warp reduction
 
 enum Kind : uint8_t { kH1 = 0, kA1 = 1, kH0 = 2, kA0 = 3 };
 enum Exponent : int { eAh1 = 0, eBh1 = 1, eBa1 = 2, eAa1 = 3, eA0 = 4, eB0 = 5 };
 
-constexpr uint8_t kTeamFirst = 1;  // first list of its team in this warp's stream: clear the accumulators
+constexpr uint8_t kTeamFirst = 1;  // first piece of its team in this warp's stream: clear the accumulators
 constexpr uint8_t kTeamLast = 2;   // last one: write the team's raw slots
-constexpr uint8_t kVteamLast = 4;  // last list of its virtual team: write the confederation scratch
+constexpr uint8_t kVteamLast = 4;  // last piece of its virtual team: write the confederation scratch
 
 // phase-1 entry (plain) and phase-2 entry: 8 bytes
 struct Entry {
@@ -70,14 +70,14 @@ struct EntryClip {
   float wyy;  // sum of w * goals of the Y rate
 };
 
-struct ListHdr {  // 16 bytes, in front of the entries of every list
+struct ListHdr {  // 16 bytes, in front of the entries of every list piece
   uint32_t own_off;  // byte offset of the own row
   uint16_t vteam;
   uint8_t kind;
   uint8_t flags;
   uint16_t n0;  // phase 1: entries (even for 8-byte entries) | phase 2: tau = 1 - c X Y entries (even)
-  uint16_t n1;  // phase 2: tau = 1 + c X entries (even)
-  uint16_t n2;  // phase 2: tau = 1 + c Y entries (even)
+  uint16_t n1;  // phase 2: tau = 1 + c X entries (even); `off` addresses the .x float of the opponent row
+  uint16_t n2;  // phase 2: tau = 1 + c Y entries (even); `off` addresses the .y float
   uint16_t team;
 };
 static_assert(sizeof(ListHdr) == 16, "ListHdr must be 16 bytes");
@@ -113,6 +113,7 @@ struct KernelParams {
   int has1, has0;  // venue classes present
   uint32_t tabP1, tabQ1, tabP0;  // byte offsets of the tables (row V of each = zero row)
   uint32_t tab_bytes;            // table area (reused by the epilogue)
+  uint32_t stage_bytes;          // TMA stage size of the per-warp rings
   uint32_t smem_ring, smem_bar, smem_red, smem_total;  // carve-up (bytes)
   uint32_t epi_team, epi_part;   // epilogue reuse of the table area: team rows, per-warp partials
   ThetaOffsets off;
@@ -136,7 +137,7 @@ struct KernelParams {
   float const_term;  // -sum w (lgamma(yh+1) + lgamma(ya+1)) + every normalising constant of the priors
   // call arguments
   int C;
-  long long sd, sc;  // element strides of theta/grad: index = d*sd + c*sc
+  int sd, sc;  // element strides of theta/grad: index = d*sd + c*sc (api.cu checks that it fits 31 bits)
   const float* theta;
   float* lp;
   float* grad;
