@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
       const uint32_t a0 = ring.acquire(k, &bytes);
       uint32_t a = a0;
       const uint32_t aend = a0 + bytes;
-      while (a < aend) {
+      while (a + kp.min_piece1 <= aend) {
         const uint32_t hoff = b1_0 + k * ring.S + (a - a0);
         const Hdr L = unpack_hdr(lds128u(a));
         a += 16;
@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
       const uint32_t a0 = ring.acquire(k, &bytes);
       uint32_t a = a0;
       const uint32_t aend = a0 + bytes;
-      while (a < aend) {
+      while (a + kp.min_piece2 <= aend) {
         const Hdr L = unpack_hdr(lds128u(a));
         a += 16;
         if (L.flags & kTeamFirst) {
@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
         {  // tau = 1 - c X Y
           const float Pxy = own.x * own.y;
           const uint32_t e_end = a + L.n0 * (uint32_t)sizeof(Entry);
-#pragma unroll 2
+#pragma unroll 1
           for (; a < e_end; a += 16) {
             const uint4 q = lds128u(a);  // two entries (opponent row offset, w)
 #pragma unroll
@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
           const float oc = c == 0 ? own.x : own.y;
           const uint32_t e_end = a + (c == 0 ? L.n1 : L.n2) * (uint32_t)sizeof(Entry);
           float u = 0.0f, sm = 0.0f;
-#pragma unroll 2
+#pragma unroll 1
           for (; a < e_end; a += 16) {
             const uint4 q = lds128u(a);
 #pragma unroll

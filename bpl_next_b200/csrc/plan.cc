@@ -412,6 +412,9 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err, int 
     std::vector<unsigned char>& S = phase == 1 ? P.stream1 : P.stream2;
     std::vector<uint32_t>& wb = phase == 1 ? P.warp_b1 : P.warp_b2;
     const size_t esz = (phase == 1 && kp.clip) ? sizeof(EntryClip) : sizeof(Entry);
+    const size_t gran = 16;  // bytes of entries a piece grows by
+    const size_t min_piece = sizeof(ListHdr) + gran;
+    (phase == 1 ? kp.min_piece1 : kp.min_piece2) = (uint32_t)min_piece;
     S.clear();
     for (int w = 0; w < W; w++) {
       const size_t wstart = S.size();
@@ -438,7 +441,7 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err, int 
                 }
                 cls.push_back(0);
               }
-              if (!kp.clip && (r.size() & 1)) {  // pad to an even count with a zero-row entry
+              while (!kp.clip && (cls.size() & 1)) {  // pad to an even count with a zero-row entry
                 Entry x{opp_base(k) + zero_row, 0.0f};
                 put(&body, &x, sizeof x);
                 cls.push_back(0);
@@ -461,12 +464,16 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err, int 
               }
             }
             (phase == 1 ? P.n1_padded : P.n2_padded) += (long long)cls.size();
-            // cut into pieces that stay inside a stage
+            // cut into pieces that stay inside a stage; a stage tail shorter than the smallest piece is dead
             size_t done = 0;  // entries emitted
             while (done < cls.size()) {
-              const size_t in_stage = (S.size() - wstart) % stage;
-              const size_t space = stage - in_stage - sizeof(ListHdr);  // a multiple of 16, possibly 0
-              const size_t take = std::min(cls.size() - done, space / esz);
+              size_t in_stage = (S.size() - wstart) % stage;
+              if (stage - in_stage < min_piece) {
+                S.resize(S.size() + (stage - in_stage), 0);
+                in_stage = 0;
+              }
+              const size_t space = stage - in_stage - sizeof(ListHdr);
+              const size_t take = std::min(cls.size() - done, space / gran * gran / esz);
               ListHdr H{};
               H.own_off = own_off(v, k);
               H.vteam = (uint16_t)v;

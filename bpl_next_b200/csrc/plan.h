@@ -114,6 +114,7 @@ struct KernelParams {
   uint32_t tabP1, tabQ1, tabP0;  // byte offsets of the tables (row V of each = zero row)
   uint32_t tab_bytes;            // table area (reused by the epilogue)
   uint32_t stage_bytes;          // TMA stage size of the per-warp rings
+  uint32_t min_piece1, min_piece2;  // a stage tail shorter than this holds no piece (phase 1 / phase 2)
   uint32_t smem_ring, smem_bar, smem_red, smem_total;  // carve-up (bytes)
   uint32_t epi_team, epi_part;   // epilogue reuse of the table area: team rows, per-warp partials
   ThetaOffsets off;

@@ -119,9 +119,13 @@ extern "C" int bplx_plancheck_eval(const bplx_problem_desc* desc, const double* 
   std::vector<int> seen_first(T, 0), seen_last(T, 0);
   for (int w = 0; w < kp.nwarps; w++) {
     size_t pos = P.warp_b1[w];
-    const size_t end = P.warp_b1[w + 1];
+    const size_t end = P.warp_b1[w + 1], wstart = pos;
     double g[6] = {0, 0, 0, 0, 0, 0};
     while (pos < end) {
+      {  // dead stage tail
+        const size_t in_stage = (pos - wstart) % kp.stage_bytes;
+        if (kp.stage_bytes - in_stage < kp.min_piece1) { pos += kp.stage_bytes - in_stage; continue; }
+      }
       const size_t hoff = pos;
       const ListHdr& L = *hdr_at(P.stream1, pos);
       pos += sizeof(ListHdr);
@@ -192,8 +196,12 @@ extern "C" int bplx_plancheck_eval(const bplx_problem_desc* desc, const double* 
   double Gc = 0;
   for (int w = 0; w < kp.nwarps; w++) {
     size_t pos = P.warp_b2[w];
-    const size_t end = P.warp_b2[w + 1];
+    const size_t end = P.warp_b2[w + 1], wstart = pos;
     while (pos < end) {
+      {
+        const size_t in_stage = (pos - wstart) % kp.stage_bytes;
+        if (kp.stage_bytes - in_stage < kp.min_piece2) { pos += kp.stage_bytes - in_stage; continue; }
+      }
       const ListHdr& L = *hdr_at(P.stream2, pos);
       pos += sizeof(ListHdr);
       if ((L.n0 | L.n1 | L.n2) & 1) return -120;
