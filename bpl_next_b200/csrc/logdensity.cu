@@ -239,7 +239,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
   unsigned long long* red_best = reinterpret_cast<unsigned long long*>(smem + kp.smem_red);  // [3][32]
   uint32_t* red_found = reinterpret_cast<uint32_t*>(smem + kp.smem_red + 768);               // [2][32]
   uint32_t* red_info = reinterpret_cast<uint32_t*>(smem + kp.smem_red + 1024);               // [2][32]
-  float* red_gc = reinterpret_cast<float*>(smem + kp.smem_red + 1280);                        // [W][32]
+  float* red_hyp = reinterpret_cast<float*>(smem + kp.smem_red + 1280);                       // [12][32]
+  float* red_gc = reinterpret_cast<float*>(smem + kp.smem_red + 1280 + 12 * 128);             // [W][32]
   constexpr uint32_t ESZ = CLIP ? (uint32_t)sizeof(EntryClip) : (uint32_t)sizeof(Entry);
   Ring ring;
   ring.init(smem_u32(smem) + kp.smem_ring + warp * (kStages * kp.stage_bytes),
@@ -276,8 +277,15 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
     red_best[lane] = red_best[32 + lane] = red_best[64 + lane] = 0ull;
     red_found[lane] = red_found[32 + lane] = 0xffffffffu;
   }
+  const float r = sigmoid_clipped(ln.ld(o.raw));
   {
     const Hyp hy = load_hyp(kp, ln);
+    if (warp == 0) {  // the team pass reads them back from shared memory
+      red_hyp[0 * 32 + lane] = hy.mu_d; red_hyp[1 * 32 + lane] = hy.sig_a; red_hyp[2 * 32 + lane] = hy.sig_d;
+#pragma unroll
+      for (int i = 0; i < 4; i++) { red_hyp[(3 + i) * 32 + lane] = hy.mu[i]; red_hyp[(7 + i) * 32 + lane] = hy.sig[i]; }
+      red_hyp[11 * 32 + lane] = dc ? 0.5f : sigmoid_clipped(ln.ld(o.u));
+    }
     for (int t = warp; t < kp.T; t += W) {
       float am = 0.0f, dm = hy.mu_d;
       for (int k = 0; k < kp.K; k++) {
@@ -439,7 +447,6 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
   const int qlam = best[0] >= best[1] ? 0 : 1;
   const float LB = -1.0f / Lam;
   const float UB = fminf(1.0f / best[2], 1.0f);
-  const float r = sigmoid_clipped(ln.ld(o.raw));
   const float cc = fmaf(r, UB - LB, LB);
 
   // ---- arg-max search: warp w looks at entries w, w+W, ... of each chain's two arg-max pieces -----------
@@ -623,7 +630,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
   const bool has_rho = !dc;
   float u = 0.5f, rho = 0.0f, inv_s2 = 1.0f;
   if (has_rho) {
-    u = sigmoid_clipped(ln.ld(o.u));
+    u = red_hyp[11 * 32 + lane];
     rho = 2.0f * u - 1.0f;
     inv_s2 = 1.0f / (1.0f - rho * rho);
   }
@@ -631,7 +638,10 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
 #pragma unroll
   for (int i = 0; i < 4; i++) a_mu[i] = a_ls[i] = 0.0f;
   {
-    const Hyp hy = load_hyp(kp, ln);
+    Hyp hy;
+    hy.mu_d = red_hyp[0 * 32 + lane]; hy.sig_a = red_hyp[1 * 32 + lane]; hy.sig_d = red_hyp[2 * 32 + lane];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { hy.mu[i] = red_hyp[(3 + i) * 32 + lane]; hy.sig[i] = red_hyp[(7 + i) * 32 + lane]; }
     float* team_rows = reinterpret_cast<float*>(smem + kp.epi_team);
     for (int t = warp; t < kp.T; t += W) {
       const float za = ln.ld(o.za + t), zd = ln.ld(o.zd + t);

@@ -365,7 +365,7 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err, int 
     const uint32_t epi = (K > 0 ? (uint32_t)T * kRowBytes : 0u) + (uint32_t)W * kPartRows * 128u;
     const uint32_t tabb = (std::max(table_bytes, epi) + 127u) / 128u * 128u;
     return tabb + (uint32_t)W * kStages * stage + 128u + (uint32_t)W * kStages * 8u + 3u * 256u + 2u * 128u + 2u * 128u +
-           (uint32_t)W * 128u;
+           12u * 128u + (uint32_t)W * 128u;
   };
   const uint32_t kSmemMax = 227u * 1024u;
   int W = 0;
@@ -513,8 +513,8 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err, int 
   kp.smem_ring = kp.tab_bytes;
   kp.smem_bar = kp.smem_ring + (uint32_t)W * kStages * stage;
   kp.smem_red = (kp.smem_bar + (uint32_t)W * kStages * 8u + 127u) / 128u * 128u;
-  // red area: best[3][32] u64 | found[2][32] u32 | info[2][32] u32 | gc / lp parts [W][32] f32
-  kp.smem_total = kp.smem_red + 3u * 256u + 2u * 128u + 2u * 128u + (uint32_t)W * 128u;
+  // red area: best[3][32] u64 | found[2][32] u32 | info[2][32] u32 | hyper values [12][32] f32 | gc / lp parts [W][32] f32
+  kp.smem_total = kp.smem_red + 3u * 256u + 2u * 128u + 2u * 128u + 12u * 128u + (uint32_t)W * 128u;
   if (kp.smem_total > kSmemMax)
     FAIL(BPLX_E_UNSUPPORTED, "problem needs %u bytes of shared memory per CTA (max %u): too many (team, confederation) pairs (%d)",
          kp.smem_total, kSmemMax, V);
