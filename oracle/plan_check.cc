@@ -376,3 +376,13 @@ extern "C" int bplx_plancheck_eval(const bplx_problem_desc* desc, const double* 
   *lp_out = lp;
   return 0;
 }
+
+// the flat layout string and D the product reports for a problem (no GPU needed)
+extern "C" int bplx_plancheck_layout(const bplx_problem_desc* desc, char* buf, int buflen) {
+  HostPlan P;
+  std::string err;
+  int rc = build_plan(*desc, &P, &err);
+  if (rc != BPLX_OK) return rc;
+  snprintf(buf, buflen, "%s", P.layout.c_str());
+  return P.kp.D;
+}

@@ -1,0 +1,121 @@
+"""CPU: the oracle restatement against its pins (SURVEY.md Appendix E anchors, finite differences, layout).
+
+The reference cannot run in this image (no jax / numpyro): these are the pins the "parity unpinned"
+note of oracle/__init__.py refers to."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import datasets, models as om, predict as op
+from tests import helpers as H
+
+
+def _dc_dummy():
+    arr = H.from_training_data("dixon_coles", datasets.dummy_data())
+    return H.to_oracle(arr)
+
+
+def test_fixture_counts_match_reference_conftest():
+    # low-score counts of conftest.dummy_data / neutral_dummy_data (seed 42)
+    td = datasets.dummy_data()
+    hg, ag = np.asarray(td["home_goals"]), np.asarray(td["away_goals"])
+    assert [int(((hg == a) & (ag == b)).sum()) for a, b in ((0, 0), (1, 0), (0, 1), (1, 1))] == [7, 21, 16, 18]
+    assert int(hg.sum()) == 782 and int(ag.sum()) == 645
+    td = datasets.neutral_dummy_data()
+    hg, ag = np.asarray(td["home_goals"]), np.asarray(td["away_goals"])
+    assert [int(((hg == a) & (ag == b)).sum()) for a, b in ((0, 0), (1, 0), (0, 1), (1, 1))] == [14, 33, 28, 46]
+
+
+def test_appendix_e_anchor_zero():
+    d = _dc_dummy()
+    lp, g, cc = om.log_density_and_grad(d, np.zeros((1, 45)))
+    assert lp[0] == pytest.approx(-1547.9659390103925, rel=1e-13)
+    assert cc[0] == pytest.approx(0.0, abs=1e-15)
+    assert g[0, 44] == pytest.approx(6.0, rel=1e-12)  # d lp / d logit(raw) = 0.5 * (-7 + 21 + 16 - 18) * ... (B.3)
+
+
+def test_appendix_e_anchor_sine():
+    d = _dc_dummy()
+    theta = (0.3 * np.sin(1.0 + np.arange(45)))[None, :]
+    lp, g, cc = om.log_density_and_grad(d, theta)
+    assert lp[0] == pytest.approx(-1689.4267185765793, rel=1e-13)
+    assert cc[0] == pytest.approx(0.1544682575346078, rel=1e-12)
+    assert np.linalg.norm(g[0]) == pytest.approx(883.2262464523642, rel=1e-11)
+    np.testing.assert_allclose(g[0, :6], [398.018838, -751.890614, -53.139403, -20.919260, 61.070526, 39.937883],
+                               rtol=2e-8)
+    assert g[0, 44] == pytest.approx(-0.0310368820, rel=1e-8)
+
+
+CASES = [("dixon_coles", {}), ("extended", dict(K=2)), ("neutral", {}), ("neutral_wc", dict(multi_conf=True, K=1))]
+
+
+@pytest.mark.parametrize("model,kw", CASES)
+def test_gradient_matches_finite_differences(model, kw):
+    arr = H.small_problem(model, seed=5, T=5, M=40, **kw)
+    d = H.to_oracle(arr)
+    D = om.num_params(model, arr.num_teams, arr.num_covariates, arr.num_conferences)
+    theta = H.random_theta(D, 1, seed=2, radius=0.7)
+    lp, g, _ = om.log_density_and_grad(d, theta)
+    eps = 1e-6
+    num = np.zeros(D)
+    for i in range(D):
+        tp, tm = theta.copy(), theta.copy()
+        tp[0, i] += eps
+        tm[0, i] -= eps
+        num[i] = (om.log_density(d, torch.as_tensor(tp))[0].item() - om.log_density(d, torch.as_tensor(tm))[0].item()) / (2 * eps)
+    np.testing.assert_allclose(g[0], num, rtol=2e-6, atol=2e-6 * np.abs(g).max())
+
+
+def test_dynamic_walks():
+    rng = np.random.default_rng(0)
+    T, G, M = 4, 3, 30
+    h = rng.integers(0, T, M)
+    a = (h + rng.integers(1, T, M)) % T
+    d = om.MatchData(model="dynamic", num_teams=T, home_team=h, away_team=a, home_goals=rng.poisson(1.0, M),
+                     away_goals=rng.poisson(1.0, M), neutral_venue=(rng.random(M) < 0.3).astype(np.int64),
+                     gameweek=rng.integers(0, G, M), num_gameweeks=G)
+    D = om.num_params("dynamic", T, 0, 0, G)
+    assert D == 10 * G + 2 + 7 * G * T
+    theta = H.random_theta(D, 2, seed=1, radius=0.5)
+    lp_i, g_i, _ = om.log_density_and_grad(d, theta)
+    d.walk = "as_written"
+    lp_w, g_w, _ = om.log_density_and_grad(d, theta)
+    assert np.all(np.isfinite(lp_i)) and np.all(np.isfinite(lp_w)) and not np.allclose(lp_i, lp_w)
+    # as written (dynamic_dixon_coles.py:192-218) attack/defence never reach the rates: mean_defence only has its prior
+    lay = om.layout_offsets(om.site_layout("dynamic", T, 0, 0, G))
+    md = lay["mean_defence"][0]
+    np.testing.assert_allclose(g_w[:, md], -theta[:, md], rtol=1e-12)
+
+
+def test_layout_matches_library():
+    """The oracle's site order is the order the C library reports (numpyro's declaration order)."""
+    import ctypes as C
+    from bpl_next_b200 import _abi
+
+    lib = H.plancheck_lib()
+    lib.bplx_plancheck_layout.argtypes = [C.POINTER(_abi.ProblemDesc), C.c_char_p, C.c_int]
+    lib.bplx_plancheck_layout.restype = C.c_int
+    for model, kw in CASES:
+        arr = H.small_problem(model, seed=1, **kw)
+        buf = C.create_string_buffer(4096)
+        D = lib.bplx_plancheck_layout(C.byref(arr.desc()), buf, 4096)
+        recs = [r.split(":") for r in buf.value.decode().split(";") if r]
+        exp = om.site_layout(model, arr.num_teams, arr.num_covariates, arr.num_conferences)
+        exp = [(n, int(np.prod(s)) if s else 1, t) for n, s, t in exp if (int(np.prod(s)) if s else 1) > 0]
+        got = [(r[0], int(r[2]), r[3]) for r in recs if int(r[2]) > 0]
+        assert got == exp
+        assert D == om.num_params(model, arr.num_teams, arr.num_covariates, arr.num_conferences)
+
+
+def test_predict_oracle_properties():
+    """Reference assertions (tests/test_base_models.py:16-47): 0 <= p <= 1, W + D + L = 1."""
+    rng = np.random.default_rng(3)
+    S, T, F = 200, 6, 9
+    s = {"attack": rng.normal(0, 0.3, (S, T)), "defence": rng.normal(0, 0.3, (S, T)),
+         "home_advantage": rng.normal(0.25, 0.1, (S, T)), "corr_coef": rng.uniform(-0.1, 0.1, S)}
+    h = rng.integers(0, T, F)
+    a = (h + 1) % T
+    grid, HG, AG = op.predict_score_grid_proba("extended", s, h, a, 15)
+    assert np.all(grid >= 0) and np.all(grid <= 1)
+    out = op.predict_outcome_proba("extended", s, h, a, 15)
+    np.testing.assert_allclose(out["home_win"] + out["draw"] + out["away_win"], 1.0, atol=1e-5)
