@@ -30,7 +30,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 L2_BYTES = 126e6
-FLOPS_PER_EVAL = {"dixon_coles": 26, "extended": 30, "neutral": 40, "neutral_wc": 46}
+FLOPS_PER_EVAL = {"dixon_coles": 26, "extended": 30, "neutral": 40, "neutral_wc": 46, "dynamic": 40}
 METRIC = "logdensity_grad_match_evals_per_s"
 UNIT = "match-evals/s"
 
@@ -50,6 +50,10 @@ def workload(name):
         arr, _ = bdata.prepare("neutral_wc", datasets.config_3(), epsilon=0.1)
         desc = "configs[2]: NeutralDixonColesWC T=220, M=40000 weighted, Cf=6"
         return arr, 32768, desc
+    if name == "cfg4":
+        arr, _ = bdata.prepare("dynamic", datasets.config_4())
+        desc = "configs[3]: DynamicDixonColes T=20, 30 seasons M=11400, G=30 (intended random walk)"
+        return arr, 8192, desc
     if name == "cfg1":
         arr, _ = bdata.prepare("dixon_coles", datasets.dummy_data())
         return arr, 4096, "configs[0] data: DixonColes T=20 M=380"
@@ -215,7 +219,7 @@ def cpu_port(arr, C_sample, min_seconds, radius, seed, max_calls=1000):
     d = H.to_oracle(arr)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    D = om.num_params(arr.model, arr.num_teams, arr.num_covariates, arr.num_conferences)
+    D = om.num_params(arr.model, arr.num_teams, arr.num_covariates, arr.num_conferences, arr.num_gameweeks)
     theta = np.random.default_rng(seed).uniform(-radius, radius, (C_sample, D)).astype(np.float32)
     om.log_density_and_grad(d, theta, dtype=torch.float32)  # warm-up
     calls, t0 = 0, time.perf_counter()
@@ -246,7 +250,7 @@ def run_reference(args, rank, world):
 
     d = H.to_oracle(arr)
     torch.set_num_threads(os.cpu_count() or 1)
-    D = om.num_params(arr.model, arr.num_teams, arr.num_covariates, arr.num_conferences)
+    D = om.num_params(arr.model, arr.num_teams, arr.num_covariates, arr.num_conferences, arr.num_gameweeks)
     theta = np.random.default_rng(args.seed + 1).uniform(-args.radius, args.radius, (C_sample, D)).astype(np.float32)
     for _ in range(max(args.warmup, 1)):
         om.log_density_and_grad(d, theta, dtype=torch.float32)
@@ -288,6 +292,18 @@ def extras(args, pk):
     p.close()
     del p
     torch.cuda.empty_cache()
+    # configs[3]: Dynamic, 8,192 chains (theta radius 0.5: a 30-step walk of U(-2,2) steps overflows float32 rates)
+    arr, C, desc = workload("cfg4")
+    p = Problem(arr)
+    ms, reps, nb, set_bytes, finite = time_logdensity(p, C, 3, 2, 0.5, args.seed + 4, use_graph=False, target_s=0.5)
+    evals = C * arr.num_matches * 3 / (ms * 1e-3)
+    out.append({"workload": desc + f", {C} chains on 1 GPU, theta U(-0.5,0.5)", "metric": METRIC, "value": evals,
+                "unit": UNIT, "ms_per_call": ms / 3, "finite": finite, "plan": p.stats(),
+                "fp32_frac": FLOPS_PER_EVAL["dynamic"] * evals / 1e12 / pk["fp32_tflops"],
+                "hbm_frac": (8.0 * p.D * C) / (ms / 3 * 1e-3) / 1e9 / pk["hbm_gbs"]})
+    p.close()
+    del p
+    torch.cuda.empty_cache()
     # configs[4]: predictive grid S=16,384 x F=10,000 x 11x11 (whole job on one GPU here)
     s, fx = datasets.config_5()
     ds = {k: torch.from_numpy(v).cuda() for k, v in s.items()}
@@ -322,7 +338,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="bplx", choices=["bplx", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4"])
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the workload's)")
     ap.add_argument("--radius", type=float, default=2.0, help="theta ~ U(-radius, radius) (numpyro init_to_uniform)")
     ap.add_argument("--seed", type=int, default=1002)

@@ -36,8 +36,9 @@ static int upload(bplx_problem* p, const std::vector<T>& h, const T** out) {
 }
 
 static size_t workspace_bytes(const KernelParams& kp, int C) {
-  if (kp.Cf <= 0) return 0;
   const size_t Cpad = ((size_t)C + 31) / 32 * 32;
+  if (kp.model == BPLX_DYNAMIC) return (size_t)kp.G * kp.T * 2 * Cpad * sizeof(float);  // the walk's prefix sums
+  if (kp.Cf <= 0) return 0;
   return (size_t)kp.V * Cpad * sizeof(float);
 }
 
@@ -70,7 +71,7 @@ static int enqueue(const bplx_problem* p, int C, int layout, int ld, const float
   kp.grad = grad;
   kp.corr_coef = corr_coef;
   kp.scratch = static_cast<float*>(ws);
-  return launch_logdensity(kp, stream);
+  return kp.model == BPLX_DYNAMIC ? launch_logdensity_dynamic(kp, stream) : launch_logdensity(kp, stream);
 }
 
 }  // namespace bplx
@@ -118,8 +119,11 @@ int bplx_problem_create(const bplx_problem_desc* desc, bplx_problem** out) {
   UP(yteam, kp.yteam);
   UP(yconf, kp.yconf);
   UP(Xs, kp.Xs);
+  UP(gw_tptr, kp.gw_tptr);
+  UP(gw_tlist, kp.gw_tlist);
 #undef UP
-  if ((rc = logdensity_set_attributes(kp)) != BPLX_OK) return fail(rc);
+  rc = kp.model == BPLX_DYNAMIC ? logdensity_dynamic_set_attributes() : logdensity_set_attributes(kp);
+  if (rc != BPLX_OK) return fail(rc);
   p->stats[0] = desc->num_matches;
   p->stats[1] = hp.n1;
   p->stats[2] = hp.n1_padded;

@@ -86,6 +86,21 @@ int make_layout(int model, int T, int K, int Cf, ThetaOffsets* o, std::string* s
     for (int i = 0; i < 4; i++) z.dec[i] = vec((std::string(nm[i]) + "_decentered").c_str(), T, "real");
     if (model == BPLX_NEUTRAL_WC) z.conf = vec("confederation_strength_decentered", Cf, "real");
     z.raw = scalar("corr_coef_raw", "sigmoid");
+  } else if (model == BPLX_DYNAMIC) {  // dynamic_dixon_coles.py:74-241; T here is G * T for the per-(gameweek, team) sites
+    static const char* nm[4] = {"home_attack", "away_attack", "home_defence", "away_defence"};
+    const int G = Cf;  // (the caller passes G in the Cf slot)
+    for (int i = 0; i < 4; i++) z.mean[i] = vec((std::string("mean_") + nm[i]).c_str(), G, "real");
+    for (int i = 0; i < 4; i++) z.log_std[i] = vec((std::string("std_") + nm[i]).c_str(), G, "exp");
+    z.log_std_attack = vec("std_attack", G, "exp");
+    z.log_std_defence = vec("std_defence", G, "exp");
+    z.mean_defence = scalar("mean_defence", "real");
+    z.beta_a = vec("attack_coefficients", K, "real");
+    z.beta_d = vec("defence_coefficients", K, "real");
+    z.u = vec("u", G * T, "sigmoid");
+    z.za = vec("standardised_attack", G * T, "real");
+    z.zd = vec("standardised_defence", G * T, "real");
+    for (int i = 0; i < 4; i++) z.dec[i] = vec((std::string(nm[i]) + "_decentered").c_str(), G * T, "real");
+    z.raw = scalar("corr_coef_raw", "sigmoid");
   } else {
     return -1;
   }
@@ -95,6 +110,8 @@ int make_layout(int model, int T, int K, int Cf, ThetaOffsets* o, std::string* s
 }
 
 }  // namespace
+
+static int build_plan_dynamic(const bplx_problem_desc& d, HostPlan* out, std::string* err, int force_warps);
 
 int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err, int force_warps) {
   const int model = d.model, M = d.num_matches, T = d.num_teams, K = d.num_covariates;
@@ -106,8 +123,8 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err, int 
     *err = fmt(__VA_ARGS__); \
     return (code);           \
   } while (0)
-  if (model == BPLX_DYNAMIC) FAIL(BPLX_E_UNSUPPORTED, "BPLX_DYNAMIC is not implemented by this build");
   if (model < 0 || model > BPLX_DYNAMIC) FAIL(BPLX_E_INVALID, "unknown model %d", model);
+  if (model == BPLX_DYNAMIC) return build_plan_dynamic(d, out, err, force_warps);
   if (M <= 0) FAIL(BPLX_E_INVALID, "num_matches must be positive (got %d)", M);
   if (T <= 0 || T > 65535) FAIL(BPLX_E_INVALID, "num_teams out of range (%d)", T);
   if (K < 0 || K > kMaxCov) FAIL(BPLX_E_UNSUPPORTED, "num_covariates %d outside [0, %d]", K, kMaxCov);
@@ -521,5 +538,7 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err, int 
 #undef FAIL
   return BPLX_OK;
 }
+
+#include "plan_dynamic.inc"
 
 }  // namespace bplx

@@ -56,6 +56,7 @@ enum Exponent : int { eAh1 = 0, eBh1 = 1, eBa1 = 2, eAa1 = 3, eA0 = 4, eB0 = 5 }
 constexpr uint8_t kTeamFirst = 1;  // first piece of its team in this warp's stream: clear the accumulators
 constexpr uint8_t kTeamLast = 2;   // last one: write the team's raw slots
 constexpr uint8_t kVteamLast = 4;  // last piece of its virtual team: write the confederation scratch
+constexpr uint8_t kGwFirst = 8;    // DYNAMIC: marker piece (no entries) in front of a gameweek: rebuild the warp's tables
 
 // phase-1 entry (plain) and phase-2 entry: 8 bytes
 struct Entry {
@@ -72,7 +73,7 @@ struct EntryClip {
 
 struct ListHdr {  // 16 bytes, in front of the entries of every list piece
   uint32_t own_off;  // byte offset of the own row
-  uint16_t vteam;
+  uint16_t vteam;  // DYNAMIC: the gameweek
   uint8_t kind;
   uint8_t flags;
   uint16_t n0;  // phase 1: entries (even for 8-byte entries) | phase 2: tau = 1 - c X Y entries (even)
@@ -107,12 +108,14 @@ struct HyperDesc {
 // everything the kernel needs; device pointers are filled by api.cu after upload
 struct KernelParams {
   int model, T, K, Cf, V;
+  int G;           // DYNAMIC: gameweeks (else 0)
+  int as_written;  // DYNAMIC: reproduce dynamic_dixon_coles.py:192-218 literally (attack = defence = 0 in the rates)
   int D, nwarps;
   int ndec;        // decentred per-team venue sites: 0 (DC), 1 (EXT), 4 (NEU, WC)
   int clip;        // Extended: rates clipped at 15
   int has1, has0;  // venue classes present
   uint32_t tabP1, tabQ1, tabP0;  // byte offsets of the tables (row V of each = zero row)
-  uint32_t tab_bytes;            // table area (reused by the epilogue)
+  uint32_t tab_bytes;            // table area (reused by the epilogue); DYNAMIC: per-warp table bytes
   uint32_t stage_bytes;          // TMA stage size of the per-warp rings
   uint32_t min_piece1, min_piece2;  // a stage tail shorter than this holds no piece (phase 1 / phase 2)
   uint32_t smem_ring, smem_bar, smem_red, smem_total;  // carve-up (bytes)
@@ -132,6 +135,8 @@ struct KernelParams {
   const float* yteam;            // [T*8] the same folded per team: d/d att, d/d def, d/d venue effect[4], 0, 0
   const float* yconf;            // [Cf]  ... and per confederation
   const float* Xs;               // [T*K]
+  const int32_t* gw_tptr;        // DYNAMIC [G+1]: teams with matches in each gameweek (CSR)
+  const uint16_t* gw_tlist;      // DYNAMIC
   HyperDesc hyper[12];           // scalar hyper-parameter sites (priors + chain rule in the epilogue)
   int nhyper;
   float w11;         // sum of weights of 1-1 matches
@@ -144,6 +149,7 @@ struct KernelParams {
   float* grad;
   float* corr_coef;
   float* scratch;  // [V][Cpad] per-virtual-team A-B gradient (confederation models)
+                   // DYNAMIC: [G*T*2][Cpad] attack / defence of every (gameweek, team) (the random walk's prefix sums)
   int Cpad;
 };
 
@@ -156,6 +162,8 @@ struct HostPlan {
   std::vector<uint16_t> v_team;
   std::vector<uint8_t> v_conf;
   std::vector<float> yexp, yteam, yconf, Xs;
+  std::vector<int32_t> gw_tptr;
+  std::vector<uint16_t> gw_tlist;
   std::string layout;  // "name:offset:count:transform;" records
   // statistics
   long long n1 = 0, n2 = 0, n1_padded = 0, n2_padded = 0, nlists1 = 0, nlists2 = 0;

@@ -27,4 +27,6 @@ struct bplx_problem {
 namespace bplx {
 int launch_logdensity(const KernelParams& kp, cudaStream_t stream);
 int logdensity_set_attributes(const KernelParams& kp);
+int launch_logdensity_dynamic(const KernelParams& kp, cudaStream_t stream);
+int logdensity_dynamic_set_attributes();
 }  // namespace bplx

@@ -56,6 +56,7 @@ class MatchArrays:
     covariates: Optional[np.ndarray] = None     # float32 [T, K], already standardised
     gameweek: Optional[np.ndarray] = None
     num_gameweeks: int = 0
+    as_written: bool = False                    # dynamic only: BPLX_FLAG_DYNAMIC_AS_WRITTEN
     _keep: list = field(default_factory=list, repr=False)
 
     @property
@@ -75,7 +76,7 @@ class MatchArrays:
         d.num_covariates = self.num_covariates
         d.num_conferences = self.num_conferences
         d.num_gameweeks = self.num_gameweeks
-        d.flags = 0
+        d.flags = 1 if (self.model == "dynamic" and self.as_written) else 0
 
         def ptr(a, dtype, ctype):
             if a is None:
@@ -151,5 +152,13 @@ def prepare(model: str, training_data: Dict[str, Any], epsilon=None, rescale_wei
             arr.num_conferences = len(confs)
             meta["conferences"], meta["conferences_dict"] = confs, cdict
         arr.weights = w.astype(np.float32)
+        return arr, meta
+    if model == "dynamic":  # dynamic_dixon_coles.py:262-296 (gameweeks 0-based, G = max + 1: SURVEY D2)
+        arr.neutral_venue = np.asarray(training_data["neutral_venue"]).astype(DTYPES["venue"])
+        gw = np.asarray(training_data["gameweek"], dtype=np.int32)
+        if gw.size and gw.min() < 0:
+            raise ValueError("gameweek must be >= 0")
+        arr.gameweek = gw
+        arr.num_gameweeks = int(gw.max()) + 1
         return arr, meta
     raise ValueError(f"unknown model {model!r}")

@@ -28,6 +28,8 @@ def to_oracle(arr: bdata.MatchArrays) -> om.MatchData:
         home_conf=None if arr.home_conf is None else arr.home_conf.astype(np.int64),
         away_conf=None if arr.away_conf is None else arr.away_conf.astype(np.int64),
         num_conferences=arr.num_conferences, covariates=cov,
+        gameweek=None if arr.gameweek is None else arr.gameweek.astype(np.int64),
+        num_gameweeks=arr.num_gameweeks, walk="as_written" if getattr(arr, "as_written", False) else "intended",
     )
     d.covariates_prestandardised = True
     return d
@@ -45,7 +47,7 @@ def small_problem(model: str, seed: int = 0, T: int = 7, M: int = 60, K: int = 0
     ag = rng.poisson(lam, M)
     arr = bdata.MatchArrays(model=model, num_teams=T, home_team=h.astype(np.uint16), away_team=a.astype(np.uint16),
                             home_goals=hg.astype(np.uint8), away_goals=ag.astype(np.uint8))
-    if weighted and model != "dixon_coles":
+    if weighted and model not in ("dixon_coles", "dynamic"):
         arr.weights = rng.uniform(0.1, 3.0, M).astype(np.float32)
     if model in ("neutral", "neutral_wc"):
         arr.neutral_venue = (rng.random(M) < neutral_frac).astype(np.uint8)
@@ -58,6 +60,13 @@ def small_problem(model: str, seed: int = 0, T: int = 7, M: int = 60, K: int = 0
             flip = rng.random(M) < 0.15
             hc = np.where(flip, (hc + 1) % Cf, hc)
         arr.home_conf, arr.away_conf, arr.num_conferences = hc.astype(np.uint8), ac.astype(np.uint8), Cf
+    if model == "dynamic":
+        G = Cf  # (gameweeks travel in the Cf argument)
+        arr.neutral_venue = (rng.random(M) < neutral_frac).astype(np.uint8)
+        arr.gameweek = rng.integers(0, G, M).astype(np.int32)
+        arr.gameweek[0] = G - 1  # make sure the last gameweek exists
+        arr.num_gameweeks = G
+        arr.weights = None
     if K and model != "dixon_coles":
         X = rng.normal(0, 1, (T, K))
         arr.covariates = ((X - X.mean(0)) / X.std(0)).astype(np.float32)

@@ -32,6 +32,10 @@ CASES = [
     ("neutral", dict(neutral_frac=1.0)),
     ("neutral_wc", dict()),
     ("neutral_wc", dict(multi_conf=True, K=2, T=13, M=400)),
+    ("dynamic", dict(Cf=4, T=5, M=90)),
+    ("dynamic", dict(Cf=3, T=6, M=120, K=2, neutral_frac=0.0)),
+    ("dynamic", dict(Cf=5, T=4, M=40, as_written=True)),
+    ("dynamic", dict(Cf=33, T=23, M=3000, neutral_frac=0.2)),
 ]
 
 
@@ -42,7 +46,12 @@ def test_small_problems(model, kw, radius, chain_minor):
     import torch
     from bpl_next_b200 import Problem
 
+    kw = dict(kw)
+    as_written = kw.pop("as_written", False)
     arr = H.small_problem(model, seed=3, **kw)
+    arr.as_written = as_written
+    if model == "dynamic" and arr.num_gameweeks > 8 and radius > 1.0:
+        pytest.skip("a 33-step walk of U(-2,2) steps overflows float32 rates (the reference's float32 path would too)")
     p = Problem(arr)
     C = 45  # not a multiple of 32: exercises the ragged last CTA
     theta = H.random_theta(p.D, C, seed=11, radius=radius, dtype=np.float32)
@@ -83,7 +92,7 @@ def test_survey_anchor():
     assert abs(np.linalg.norm(grad[0]) - 883.2262464523642) < 1e-4 * 883.3
 
 
-@pytest.mark.parametrize("cfg", ["config_2", "config_3"])
+@pytest.mark.parametrize("cfg", ["config_2", "config_3", "config_4"])
 def test_baseline_configs(cfg):
     """BASELINE.json configs at full match count, a handful of chains against the oracle."""
     import torch
@@ -91,11 +100,13 @@ def test_baseline_configs(cfg):
 
     if cfg == "config_2":
         arr = H.from_training_data("extended", datasets.config_2(), epsilon=0.01)
+    elif cfg == "config_4":
+        arr = H.from_training_data("dynamic", datasets.config_4())
     else:
         arr = H.from_training_data("neutral_wc", datasets.config_3(), epsilon=0.1)
     p = Problem(arr)
     C = 40
-    for radius in (0.3, 2.0):
+    for radius in ((0.3, 0.8) if cfg == "config_4" else (0.3, 2.0)):  # a 30-step walk of U(-2,2) steps overflows float32 rates
         theta = H.random_theta(p.D, C, seed=21, radius=radius, dtype=np.float32)
         lp, grad, cc = p.logdensity(torch.from_numpy(theta).cuda())
         torch.cuda.synchronize()

@@ -14,15 +14,21 @@ CASES = [
     ("neutral", dict(neutral_frac=1.0)),
     ("neutral_wc", dict()),
     ("neutral_wc", dict(multi_conf=True, K=2)),
+    ("dynamic", dict(Cf=4, T=5, M=90)),
+    ("dynamic", dict(Cf=3, T=6, M=120, K=2, neutral_frac=0.0)),
+    ("dynamic", dict(Cf=5, T=4, M=40, as_written=True)),
 ]
 
 
 @pytest.mark.parametrize("model,kw", CASES)
 @pytest.mark.parametrize("radius", [0.5, 2.0])
 def test_plan_matches_oracle(model, kw, radius):
+    kw = dict(kw)
+    as_written = kw.pop("as_written", False)
     arr = H.small_problem(model, seed=3, **kw)
+    arr.as_written = as_written
     d = H.to_oracle(arr)
-    D = om.num_params(model, arr.num_teams, arr.num_covariates, arr.num_conferences)
+    D = om.num_params(model, arr.num_teams, arr.num_covariates, arr.num_conferences, arr.num_gameweeks)
     theta = H.random_theta(D, 6, seed=11, radius=radius)
     lp_o, g_o, cc_o = om.log_density_and_grad(d, theta)
     lp_p, g_p, cc_p = H.plancheck_eval(arr, theta)
