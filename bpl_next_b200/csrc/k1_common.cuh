@@ -45,11 +45,7 @@ __device__ __forceinline__ float lg2_approx(float x) {
 __device__ __forceinline__ void red_add(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
-__device__ __forceinline__ float ld_cg(const float* p) {
-  float v;
-  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
-  return v;
-}
+__device__ __forceinline__ float ld_cg(const float* p) { return __ldcg(p); }  // L2 only: the line is red.add'ed
 
 __device__ __forceinline__ Hyp load_hyp(const KernelParams& kp, const Lane& ln) {
   const ThetaOffsets& o = kp.off;

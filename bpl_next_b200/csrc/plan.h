@@ -46,6 +46,7 @@ constexpr int kChains = 32;       // chains per CTA: one lane per chain
 constexpr int kRowBytes = 256;    // one table row: float2 x 32 lanes
 constexpr int kMaxCov = 16;       // covariates supported by the kernel
 constexpr int kMaxWarps = 24;     // warps per CTA (register budget: 65536 / (24*32) = 85 per thread)
+constexpr int kMaxWarpsDyn = 16;  // DYNAMIC kernel: 128 registers per thread
 constexpr int kStages = 2;        // ring depth per warp (stage size: KernelParams::stage_bytes, 512 or 1024)
 constexpr int kAccRows = 13;      // hyper accumulators: lp, mu_d, ls_a, ls_d, mu[4], ls[4], rho
 constexpr int kPartRows = 16;     // rows per warp in the final cross-warp reduction
