@@ -1,0 +1,348 @@
+// nuts.cu -- batched NUTS transition bookkeeping on the GPU, one thread per chain.
+//
+// The caller of the log-density kernel in the reference is numpyro's NUTS (`NUTS(self._model)` + `MCMC.run`,
+// bpl/dixon_coles.py:100-116 and siblings): iterative tree doubling with multinomial sampling, biased progressive
+// sampling at the top level, the generalised U-turn criterion on momentum sums, divergence at dH > 1000, dual
+// averaging of the step size (t0 = 10, kappa = 0.75, gamma = 0.05, mu = log(10 eps)) and Stan-style windowed
+// diagonal mass-matrix adaptation with Welford variances.  This kernel restates that
+// algorithm so that, between two log-density evaluations, everything a chain has to do happens in ONE launch:
+//
+//     loop:  bplx_nuts_step  (finish the pending leapfrog, grow / merge trees, adapt, collect, start the next
+//                             leapfrog: theta_eval = z + eps * M^-1 (r + eps/2 * grad))
+//            bplx_logdensity_fwdbwd(theta_eval) -> lp, grad
+//
+// Chains do not run in lock step: a chain that finishes its tree starts its next transition in the same launch,
+// so the number of launches is the longest chain's total leapfrog count, not the sum of per-draw maxima that a
+// vmapped `while_loop` pays.  All vectors are chain-minor ([D][ld], lane = chain: every access is coalesced).
+#include <curand_kernel.h>
+#include <math_constants.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "nuts.h"
+
+namespace bplx {
+
+namespace {
+
+struct Vec {  // one per-chain vector of length D inside a chain-minor array
+  float* p;
+  size_t ld;
+  __device__ __forceinline__ float& operator[](int d) const { return p[(size_t)d * ld]; }
+};
+
+__device__ __forceinline__ float log_add_exp(float a, float b) {
+  const float m = fmaxf(a, b);
+  if (m == -CUDART_INF_F) return m;
+  return m + log1pf(expf(-fabsf(a - b)));
+}
+
+// generalised U-turn (numpyro `_is_turning`, diagonal mass): v = M^-1 r; s = r_sum - (r_left + r_right)/2
+__device__ __forceinline__ bool is_turning(int D, const Vec& imm, const Vec& rl, const Vec& rr, const Vec& rs) {
+  float dl = 0.0f, dr = 0.0f;
+  for (int d = 0; d < D; d++) {
+    const float a = rl[d], b = rr[d], m = imm[d];
+    const float s = rs[d] - 0.5f * (a + b);
+    dl = fmaf(m * a, s, dl);
+    dr = fmaf(m * b, s, dr);
+  }
+  return dl <= 0.0f || dr <= 0.0f;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(128) nuts_step_kernel(const bplx_nuts_params P) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= P.C) return;
+  const int D = P.D;
+  const size_t ld = (size_t)P.ld;
+  auto vec = [&](float* base) { return Vec{base + c, ld}; };
+  auto vec_k = [&](float* base, int k) { return Vec{base + (size_t)k * D * ld + c, ld}; };
+  const Vec th = vec(P.theta_eval), gr = vec(P.grad), ph = vec(P.p_half), imm = vec(P.inv_mass);
+  const Vec zL = vec(P.zL), rL = vec(P.rL), gL = vec(P.gL), zR = vec(P.zR), rR = vec(P.rR), gR = vec(P.gR);
+  const Vec zP = vec(P.zP), gP = vec(P.gP), rS = vec(P.r_sum);
+  const Vec zQ = vec(P.zQ), gQ = vec(P.gQ), rSq = vec(P.r_sum_sub);
+  NutsChain* chains = static_cast<NutsChain*>(P.chain);
+  NutsChain st = chains[c];
+  if (st.stage == kNutsDone) return;
+  curandStatePhilox4_32_10_t rng;
+  curand_init(P.seed, (unsigned long long)(P.chain_offset + c), st.rng_offset, &rng);
+  unsigned draws = 0;
+  auto uniform = [&]() { draws++; return curand_uniform(&rng); };
+  const float lp_new = P.lp[c];
+
+  if (st.stage == kNutsInitEval) {  // gradient at the initial position has just been computed
+    for (int d = 0; d < D; d++) {
+      zP[d] = th[d];
+      gP[d] = gr[d];
+    }
+    st.pe = -lp_new;
+    st.stage = kNutsNewTransition;
+  } else if (st.stage == kNutsEvalPending) {
+    // ---- finish the leapfrog: r1 = r_half + eps/2 * grad(lp) ; the new leaf replaces the outer leaf ---------
+    const float eps = st.going_right ? st.step_size : -st.step_size;
+    const Vec zE = st.going_right ? zR : zL, rE = st.going_right ? rR : rL, gE = st.going_right ? gR : gL;
+    float ke = 0.0f;
+    for (int d = 0; d < D; d++) {
+      const float g = gr[d];
+      const float r1 = fmaf(0.5f * eps, g, ph[d]);
+      ke = fmaf(imm[d] * r1, r1, ke);
+      rE[d] = r1;
+      zE[d] = th[d];
+      gE[d] = g;
+    }
+    const float pe1 = -lp_new;
+    float delta = pe1 + 0.5f * ke - st.energy_current;
+    if (!(delta == delta)) delta = CUDART_INF_F;  // NaN -> reject
+    const float w_leaf = -delta;
+    const bool div_leaf = delta > P.max_delta_energy;
+    const float acc = fminf(1.0f, expf(-delta));
+    // ---- merge the leaf into the subtree (uniform transition kernel inside a subtree) -----------------------------
+    bool take;
+    if (st.sub_num == 0) {
+      take = true;
+      st.sub_weight = w_leaf;
+    } else {
+      const float pr = 1.0f / (1.0f + expf(-(w_leaf - st.sub_weight)));
+      take = uniform() < pr;
+      st.sub_weight = log_add_exp(st.sub_weight, w_leaf);
+    }
+    for (int d = 0; d < D; d++) {
+      const float r1 = rE[d];
+      rSq[d] = st.sub_num == 0 ? r1 : rSq[d] + r1;
+      if (take) {
+        zQ[d] = th[d];
+        gQ[d] = gr[d];
+      }
+    }
+    if (take) st.sub_pe = pe1;
+    st.sub_div = div_leaf;
+    st.sub_sum_accept += acc;
+    // checkpoints for the iterative U-turn test (numpyro `_leaf_idx_to_ckpt_idxs`, `_is_iterative_turning`)
+    const unsigned leaf = (unsigned)st.sub_num;
+    const int idx_max = __popc(leaf >> 1);
+    const int ntrail = __ffs(~leaf) - 1;  // number of trailing one bits
+    const int idx_min = idx_max - ntrail + 1;
+    if ((leaf & 1u) == 0u) {
+      const Vec ck = vec_k(P.r_ckpts, idx_max), cks = vec_k(P.r_sum_ckpts, idx_max);
+      for (int d = 0; d < D; d++) {
+        ck[d] = rE[d];
+        cks[d] = rSq[d];
+      }
+    }
+    bool turning = false;
+    for (int i = idx_max; i >= idx_min && !turning; i--) {
+      const Vec ck = vec_k(P.r_ckpts, i), cks = vec_k(P.r_sum_ckpts, i);
+      float dl = 0.0f, dr = 0.0f;
+      for (int d = 0; d < D; d++) {
+        const float a = ck[d], b = rE[d], m = imm[d];
+        const float sub = rSq[d] - cks[d] + a;  // momentum sum of the subtree that starts at checkpoint i
+        const float s = sub - 0.5f * (a + b);
+        dl = fmaf(m * a, s, dl);
+        dr = fmaf(m * b, s, dr);
+      }
+      turning = dl <= 0.0f || dr <= 0.0f;
+    }
+    st.sub_turning = turning;
+    st.sub_num += 1;
+    st.stage = kNutsInTree;
+    if (st.sub_num == (1 << st.depth) || st.sub_turning || st.sub_div) {
+      // ---- subtree complete: merge into the trajectory (biased progressive sampling, numpyro `_combine_tree`) ----
+      float pr = fminf(1.0f, expf(st.sub_weight - st.weight));
+      if (st.sub_turning || st.sub_div) pr = 0.0f;
+      const bool move = uniform() < pr;
+      for (int d = 0; d < D; d++) {
+        rS[d] += rSq[d];
+        if (move) {
+          zP[d] = zQ[d];
+          gP[d] = gQ[d];
+        }
+      }
+      if (move) st.pe = st.sub_pe;
+      st.turning = st.sub_turning || is_turning(D, imm, rL, rR, rS);
+      st.depth += 1;
+      st.weight = log_add_exp(st.weight, st.sub_weight);
+      st.diverging = st.sub_div;
+      st.sum_accept += st.sub_sum_accept;
+      st.num_prop += st.sub_num;
+      st.sub_active = 0;
+      if (st.depth >= P.max_tree_depth || st.turning || st.diverging) {
+        // ---- transition complete ----------------------------------------------------------------------------------
+        const float accept = st.sum_accept / (float)st.num_prop;
+        st.num_leapfrog_total += st.num_prop;
+        if (st.diverging && st.t >= P.num_warmup) st.num_divergent += 1;
+        if (st.t < P.num_warmup) {
+          // dual averaging (numpyro `dual_averaging`) on g = target - accept
+          const float g = P.target_accept - accept;
+          st.da_t += 1;
+          const float t = (float)st.da_t;
+          st.da_g_avg = (1.0f - 1.0f / (t + 10.0f)) * st.da_g_avg + g / (t + 10.0f);
+          st.da_x = st.da_mu - sqrtf(t) / 0.05f * st.da_g_avg;
+          const float wt = powf(t, -0.75f);
+          st.da_x_avg = (1.0f - wt) * st.da_x_avg + wt * st.da_x;
+          st.step_size = fmaxf(expf(st.t == P.num_warmup - 1 ? st.da_x_avg : st.da_x), 1.1754944e-38f);
+          const bplx_window win = P.windows[st.window];  // the current adaptation window
+          const bool middle = st.window > 0 && st.window < P.num_windows - 1;
+          const bool at_end = st.t == win.end;
+          if (middle) {  // Welford on the new position
+            const Vec mean = vec(P.wf_mean), m2 = vec(P.wf_m2);
+            st.wf_n += 1;
+            const float inv_n = 1.0f / (float)st.wf_n;
+            for (int d = 0; d < D; d++) {
+              const float x = zP[d], pre = x - mean[d];
+              const float mnew = fmaf(pre, inv_n, mean[d]);
+              mean[d] = mnew;
+              m2[d] = fmaf(pre, x - mnew, m2[d]);
+            }
+            if (at_end) {  // regularised variance -> inverse mass; restart the step-size search around 10 eps
+              const Vec mean2 = vec(P.wf_mean), m22 = vec(P.wf_m2);
+              const float n = (float)st.wf_n;
+              for (int d = 0; d < D; d++) {
+                const float var = m22[d] / (n - 1.0f);
+                imm[d] = (n / (n + 5.0f)) * var + 1e-3f * (5.0f / (n + 5.0f));
+                mean2[d] = 0.0f;
+                m22[d] = 0.0f;
+              }
+              st.wf_n = 0;
+              st.da_mu = logf(10.0f * st.step_size);
+              st.da_x = st.da_x_avg = st.da_g_avg = 0.0f;
+              st.da_t = 0;
+            }
+          }
+          if (at_end) st.window += 1;
+        } else {
+          const int k = st.t - P.num_warmup;
+          if (k % P.thin == 0) {
+            const int slot = k / P.thin;
+            if (slot < P.num_keep) {
+              float* out = P.samples + (size_t)slot * D * ld + c;
+              for (int d = 0; d < D; d++) out[(size_t)d * ld] = zP[d];
+              P.sample_lp[(size_t)slot * ld + c] = -st.pe;
+              P.sample_accept[(size_t)slot * ld + c] = accept;
+            }
+          }
+        }
+        st.t += 1;
+        st.stage = st.t >= P.num_warmup + P.num_samples ? kNutsDone : kNutsNewTransition;
+      }
+    }
+  }
+
+  if (st.stage == kNutsNewTransition) {
+    // ---- momentum refresh: r ~ N(0, M), M = 1 / inv_mass -------------------------------------------------------
+    float ke = 0.0f;
+    for (int d = 0; d < D; d += 4) {
+      const float4 n4 = curand_normal4(&rng);
+      draws += 4;
+      const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        if (d + i < D) {
+          const float m = imm[d + i];
+          const float r = nn[i] * rsqrtf(m);
+          ke = fmaf(m * r, r, ke);
+          rL[d + i] = r;
+          rR[d + i] = r;
+          rS[d + i] = r;
+          const float z = zP[d + i], g = gP[d + i];
+          zL[d + i] = z;
+          zR[d + i] = z;
+          gL[d + i] = g;
+          gR[d + i] = g;
+        }
+      }
+    }
+    st.energy_current = st.pe + 0.5f * ke;
+    st.depth = 0;
+    st.weight = 0.0f;
+    st.turning = st.diverging = 0;
+    st.sum_accept = 0.0f;
+    st.num_prop = 0;
+    st.sub_active = 0;
+    st.stage = kNutsInTree;
+  }
+
+  if (st.stage == kNutsInTree) {
+    if (!st.sub_active) {  // next doubling: direction, empty subtree
+      st.going_right = uniform() < 0.5f ? 1 : 0;
+      st.sub_active = 1;
+      st.sub_num = 0;
+      st.sub_weight = 0.0f;
+      st.sub_sum_accept = 0.0f;
+      st.sub_turning = st.sub_div = 0;
+    }
+    // ---- start the next leapfrog from the outer leaf: r_half = r + eps/2 grad(lp); theta = z + eps M^-1 r_half ------
+    const float eps = st.going_right ? st.step_size : -st.step_size;
+    const Vec zE = st.going_right ? zR : zL, rE = st.going_right ? rR : rL, gE = st.going_right ? gR : gL;
+    for (int d = 0; d < D; d++) {
+      const float rh = fmaf(0.5f * eps, gE[d], rE[d]);
+      ph[d] = rh;
+      th[d] = fmaf(eps * imm[d], rh, zE[d]);
+    }
+    st.stage = kNutsEvalPending;
+  }
+  st.rng_offset += (draws + 7u) & ~3u;  // curand_init's offset counts 32-bit outputs; keep calls on disjoint ranges
+  chains[c] = st;
+  if (st.stage != kNutsDone) atomicAdd(P.active_count, 1);
+}
+
+__global__ void nuts_init_kernel(const bplx_nuts_params P) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= P.C) return;
+  NutsChain st{};
+  st.stage = kNutsInitEval;
+  st.step_size = P.init_step_size;
+  st.da_mu = logf(10.0f * P.init_step_size);
+  st.rng_offset = 0;
+  static_cast<NutsChain*>(P.chain)[c] = st;
+  for (int d = 0; d < P.D; d++) {
+    P.inv_mass[(size_t)d * P.ld + c] = 1.0f;
+    P.wf_mean[(size_t)d * P.ld + c] = 0.0f;
+    P.wf_m2[(size_t)d * P.ld + c] = 0.0f;
+  }
+}
+
+}  // namespace bplx
+
+using namespace bplx;
+
+extern "C" {
+
+size_t bplx_nuts_chain_bytes(void) { return sizeof(NutsChain); }
+
+int bplx_nuts_init(const bplx_nuts_params* p, void* stream) {
+  BPLX_REQUIRE(p && p->C > 0 && p->D > 0 && p->ld >= p->C, BPLX_E_INVALID, "nuts: bad C / D / ld");
+  nuts_init_kernel<<<(p->C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(*p);
+  BPLX_CUDA(cudaGetLastError());
+  note_launch(1);
+  return BPLX_OK;
+}
+
+int bplx_nuts_summary(const bplx_nuts_params* p, float* out_host) {
+  BPLX_REQUIRE(p && out_host && p->C > 0, BPLX_E_INVALID, "nuts summary: bad arguments");
+  std::vector<NutsChain> h((size_t)p->C);
+  BPLX_CUDA(cudaMemcpy(h.data(), p->chain, h.size() * sizeof(NutsChain), cudaMemcpyDeviceToHost));
+  for (int c = 0; c < p->C; c++) {
+    float* o = out_host + (size_t)c * 8;
+    o[0] = (float)h[c].t;
+    o[1] = h[c].step_size;
+    o[2] = (float)h[c].num_divergent;
+    o[3] = (float)h[c].num_leapfrog_total;
+    o[4] = (float)h[c].depth;
+    o[5] = o[6] = o[7] = 0.0f;
+  }
+  return BPLX_OK;
+}
+
+int bplx_nuts_step(const bplx_nuts_params* p, void* stream) {
+  BPLX_REQUIRE(p && p->C > 0 && p->D > 0 && p->ld >= p->C, BPLX_E_INVALID, "nuts: bad C / D / ld");
+  BPLX_REQUIRE(p->max_tree_depth >= 1 && p->max_tree_depth <= 12 && p->thin >= 1, BPLX_E_INVALID,
+               "nuts: max_tree_depth must be in [1, 12] and thin >= 1");
+  nuts_step_kernel<<<(p->C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(*p);
+  BPLX_CUDA(cudaGetLastError());
+  note_launch(1);
+  return BPLX_OK;
+}
+
+}  // extern "C"

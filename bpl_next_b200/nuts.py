@@ -1,0 +1,153 @@
+"""Driver of the batched GPU NUTS transition (``include/bplx_nuts.h``) -- stands in for numpyro's ``NUTS`` +
+``MCMC(chain_method="vectorized")`` as every reference ``fit`` builds them (``bpl/dixon_coles.py:100-116``).
+
+    run = sample(potential, theta0, num_warmup=500, num_samples=1000)
+
+``potential(theta_eval, lp, grad)`` evaluates log density and gradient in place on chain-minor ``[D, C]`` tensors
+(for the models: ``Problem.logdensity(..., chain_minor=True)``).  torch provides device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Callable, Optional
+
+import numpy as np
+import torch
+
+from . import _abi
+
+
+class Window(C.Structure):
+    _fields_ = [("start", C.c_int32), ("end", C.c_int32)]
+
+
+class NutsParams(C.Structure):
+    _fields_ = [
+        ("C", C.c_int32), ("D", C.c_int32), ("ld", C.c_int32),
+        ("num_warmup", C.c_int32), ("num_samples", C.c_int32), ("thin", C.c_int32), ("num_keep", C.c_int32),
+        ("max_tree_depth", C.c_int32), ("num_windows", C.c_int32),
+        ("windows", C.c_void_p),
+        ("target_accept", C.c_float), ("init_step_size", C.c_float), ("max_delta_energy", C.c_float),
+        ("seed", C.c_uint64), ("chain_offset", C.c_int64),
+        ("theta_eval", C.c_void_p), ("lp", C.c_void_p), ("grad", C.c_void_p),
+        ("chain", C.c_void_p),
+    ] + [(n, C.c_void_p) for n in ("p_half", "inv_mass", "zL", "rL", "gL", "zR", "rR", "gR", "zP", "gP", "r_sum", "zQ",
+                                   "gQ", "r_sum_sub", "r_ckpts", "r_sum_ckpts", "wf_mean", "wf_m2", "samples",
+                                   "sample_lp", "sample_accept", "active_count")]
+
+
+def adaptation_schedule(num_steps: int):
+    """numpyro ``build_adaptation_schedule`` (Stan's windows): init buffer 75, base window 25 doubling, end buffer 50;
+    15 % / 75 % / 10 % when they do not fit; a single window below 20 steps."""
+    if num_steps <= 0:
+        return [(0, -1)]
+    if num_steps < 20:
+        return [(0, num_steps - 1)]
+    start_buffer, end_buffer, init_window = 75, 50, 25
+    if start_buffer + end_buffer + init_window > num_steps:
+        start_buffer = int(0.15 * num_steps)
+        end_buffer = int(0.1 * num_steps)
+        init_window = num_steps - start_buffer - end_buffer
+    sched = [(0, start_buffer - 1)]
+    end_window_start = num_steps - end_buffer
+    next_size, next_start = init_window, start_buffer
+    while next_start < end_window_start:
+        cur_start, cur_size = next_start, next_size
+        if 3 * cur_size <= end_window_start - cur_start:
+            next_size = 2 * cur_size
+        else:
+            cur_size = end_window_start - cur_start
+        next_start = cur_start + cur_size
+        sched.append((cur_start, next_start - 1))
+    sched.append((end_window_start, num_steps - 1))
+    return sched
+
+
+def _declare(lib):
+    if getattr(lib, "_nuts_declared", False):
+        return lib
+    lib.bplx_nuts_chain_bytes.argtypes = []
+    lib.bplx_nuts_chain_bytes.restype = C.c_size_t
+    for f in (lib.bplx_nuts_init, lib.bplx_nuts_step):
+        f.argtypes = [C.POINTER(NutsParams), C.c_void_p]
+        f.restype = C.c_int
+    lib.bplx_nuts_summary.argtypes = [C.POINTER(NutsParams), C.c_void_p]
+    lib.bplx_nuts_summary.restype = C.c_int
+    lib._nuts_declared = True
+    return lib
+
+
+@dataclass
+class NutsRun:
+    samples: torch.Tensor        # [num_keep, D, C] unconstrained draws (chain-minor)
+    lp: torch.Tensor             # [num_keep, C]
+    accept: torch.Tensor         # [num_keep, C]
+    step_size: np.ndarray        # [C]
+    num_divergent: np.ndarray    # [C]
+    num_leapfrog: np.ndarray     # [C] over warm-up + sampling
+    launches: int                # log-density evaluations = kernel launches of the potential
+    inv_mass: torch.Tensor       # [D, C]
+
+
+def sample(potential: Callable[[torch.Tensor, torch.Tensor, torch.Tensor], None], theta0: torch.Tensor,
+           num_warmup: int = 500, num_samples: int = 1000, thin: int = 1, seed: int = 42, max_tree_depth: int = 10,
+           target_accept: float = 0.8, step_size: float = 1.0, chain_offset: int = 0, check_every: int = 16,
+           max_launches: Optional[int] = None) -> NutsRun:
+    """``theta0``: ``[D, C]`` float32 CUDA tensor (chain-minor) of initial unconstrained positions."""
+    if not theta0.is_cuda:
+        raise RuntimeError("bpl_next_b200.nuts needs CUDA tensors: there is no CPU fallback")
+    lib = _declare(_abi.lib())
+    D, Cn = theta0.shape
+    dev = theta0.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    num_keep = (num_samples + thin - 1) // thin
+    vecs = {n: torch.zeros((D, Cn), **f32) for n in ("p_half", "inv_mass", "zL", "rL", "gL", "zR", "rR", "gR", "zP", "gP",
+                                                      "r_sum", "zQ", "gQ", "r_sum_sub", "wf_mean", "wf_m2")}
+    r_ckpts = torch.zeros((max_tree_depth, D, Cn), **f32)
+    r_sum_ckpts = torch.zeros((max_tree_depth, D, Cn), **f32)
+    theta_eval = theta0.clone().contiguous()
+    grad = torch.zeros((D, Cn), **f32)
+    lp = torch.zeros(Cn, **f32)
+    samples = torch.zeros((num_keep, D, Cn), **f32)
+    sample_lp = torch.zeros((num_keep, Cn), **f32)
+    sample_accept = torch.zeros((num_keep, Cn), **f32)
+    chain = torch.zeros(Cn * int(lib.bplx_nuts_chain_bytes()), dtype=torch.uint8, device=dev)
+    active = torch.zeros(1, dtype=torch.int32, device=dev)
+    sched = adaptation_schedule(num_warmup)
+    windows = torch.tensor(sched, dtype=torch.int32, device=dev).contiguous()
+
+    p = NutsParams()
+    p.C, p.D, p.ld = Cn, D, Cn
+    p.num_warmup, p.num_samples, p.thin, p.num_keep = num_warmup, num_samples, thin, num_keep
+    p.max_tree_depth, p.num_windows = max_tree_depth, len(sched)
+    p.windows = windows.data_ptr()
+    p.target_accept, p.init_step_size, p.max_delta_energy = target_accept, step_size, 1000.0
+    p.seed, p.chain_offset = seed, chain_offset
+    p.theta_eval, p.lp, p.grad = theta_eval.data_ptr(), lp.data_ptr(), grad.data_ptr()
+    p.chain = chain.data_ptr()
+    for n, t in vecs.items():
+        setattr(p, n, t.data_ptr())
+    p.r_ckpts, p.r_sum_ckpts = r_ckpts.data_ptr(), r_sum_ckpts.data_ptr()
+    p.samples, p.sample_lp, p.sample_accept = samples.data_ptr(), sample_lp.data_ptr(), sample_accept.data_ptr()
+    p.active_count = active.data_ptr()
+
+    stream = torch.cuda.current_stream().cuda_stream
+    _abi.check(lib.bplx_nuts_init(C.byref(p), stream))
+    launches = 0
+    limit = max_launches if max_launches is not None else (num_warmup + num_samples + 1) * (2 ** max_tree_depth) + 8
+    while launches < limit:
+        for k in range(check_every):
+            potential(theta_eval, lp, grad)
+            if k == check_every - 1:
+                active.zero_()
+            _abi.check(lib.bplx_nuts_step(C.byref(p), stream))
+        launches += check_every
+        if int(active.item()) == 0:
+            break
+    summ = np.zeros((Cn, 8), dtype=np.float32)
+    torch.cuda.synchronize()
+    _abi.check(lib.bplx_nuts_summary(C.byref(p), summ.ctypes.data))
+    return NutsRun(samples=samples, lp=sample_lp, accept=sample_accept, step_size=summ[:, 1].copy(),
+                   num_divergent=summ[:, 2].astype(np.int64), num_leapfrog=summ[:, 3].astype(np.int64),
+                   launches=launches, inv_mass=vecs["inv_mass"])

@@ -1,0 +1,80 @@
+"""GPU: the batched NUTS transition (bplx_nuts_step) on targets with known answers, and on the Dixon-Coles kernel."""
+import numpy as np
+import pytest
+
+from bpl_next_b200 import nuts as bn
+
+pytestmark = pytest.mark.gpu
+
+
+def test_adaptation_schedule_matches_numpyro_defaults():
+    assert bn.adaptation_schedule(500) == [(0, 74), (75, 99), (100, 149), (150, 249), (250, 449), (450, 499)]
+    assert bn.adaptation_schedule(10) == [(0, 9)]
+    s = bn.adaptation_schedule(100)
+    assert s[0] == (0, 14) and s[-1] == (90, 99) and s[1][0] == 15 and s[-2][1] == 89
+
+
+def test_gaussian_target_moments():
+    """Independent normals with very different scales: means / sds must come out within Monte-Carlo error."""
+    import torch
+    from bpl_next_b200 import diagnostics as dg
+
+    D, C = 6, 512
+    mu = torch.tensor([0.0, 1.0, -2.0, 3.0, 0.5, -0.5], device="cuda")[:, None]
+    sd = torch.tensor([1.0, 0.1, 10.0, 2.0, 0.5, 5.0], device="cuda")[:, None]
+
+    def potential(theta, lp, grad):
+        z = (theta - mu) / sd
+        lp.copy_(-0.5 * (z * z).sum(0))
+        grad.copy_(-z / sd)
+
+    g = torch.Generator(device="cuda").manual_seed(0)
+    theta0 = (torch.rand((D, C), generator=g, device="cuda") * 4 - 2)
+    run = bn.sample(potential, theta0, num_warmup=300, num_samples=200, seed=1)
+    x = run.samples.double()  # [N, D, C]
+    mean = x.mean(dim=(0, 2)).cpu().numpy()
+    std = x.permute(1, 0, 2).reshape(D, -1).std(dim=1).cpu().numpy()
+    ess = dg.effective_sample_size(run.samples).cpu().numpy()
+    assert ess.min() > 5000, ess
+    mcse = sd[:, 0].cpu().numpy() / np.sqrt(ess)
+    assert np.all(np.abs(mean - mu[:, 0].cpu().numpy()) < 5 * mcse), (mean, mcse)
+    np.testing.assert_allclose(std, sd[:, 0].cpu().numpy(), rtol=0.03)
+    rhat = dg.split_rhat(run.samples).cpu().numpy()
+    assert np.all(rhat < 1.02), rhat
+    assert run.num_divergent.sum() == 0
+    # the adapted inverse mass matrix is the posterior variance (diagonal), chain by chain
+    imm = run.inv_mass.mean(dim=1).cpu().numpy()
+    np.testing.assert_allclose(imm, (sd[:, 0] ** 2).cpu().numpy(), rtol=0.35)
+    assert 0.6 < run.accept.mean().item() < 0.95
+
+
+def test_dixon_coles_posterior_is_stationary_across_seeds():
+    """Two independent runs on the reference's dummy league agree within Monte-Carlo error, and the chains mix."""
+    import torch
+    from bpl_next_b200 import Problem, diagnostics as dg
+    from oracle import datasets
+    from tests import helpers as H
+
+    arr = H.from_training_data("dixon_coles", datasets.dummy_data())
+    p = Problem(arr)
+    C = 256
+
+    def potential(theta, lp, grad):
+        p.logdensity(theta, chain_minor=True, lp=lp, grad=grad)
+
+    means = []
+    for seed in (3, 4):
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        theta0 = torch.rand((p.D, C), generator=g, device="cuda") * 4 - 2  # init_to_uniform(radius=2)
+        run = bn.sample(potential, theta0, num_warmup=300, num_samples=150, seed=seed)
+        assert dg.split_rhat(run.samples).max().item() < 1.05
+        ess = dg.effective_sample_size(run.samples)
+        sd = run.samples.permute(1, 0, 2).reshape(p.D, -1).std(dim=1)
+        means.append((run.samples.double().mean(dim=(0, 2)), sd.double() / ess.sqrt()))
+        assert run.num_divergent.mean() < 1.0
+    diff = (means[0][0] - means[1][0]).abs()
+    tol = 6 * torch.sqrt(means[0][1] ** 2 + means[1][1] ** 2)
+    assert bool((diff < tol).all()), (diff / tol).max().item()
+    # home advantage posterior mean: log(782/645) ~ 0.19 is the data's home/away goal ratio (prior N(0.1, 0.2))
+    ha = means[0][0][0].item()
+    assert 0.1 < ha < 0.3, ha
