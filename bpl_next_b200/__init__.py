@@ -12,4 +12,8 @@ def __getattr__(name):  # lazy: importing torch is slow and not needed for host-
     if name in ("Problem", "score_grid", "score_grid_host"):
         from . import problem
         return getattr(problem, name)
+    if name in ("DixonColesMatchPredictor", "ExtendedDixonColesMatchPredictor", "NeutralDixonColesMatchPredictor",
+                "NeutralDixonColesMatchPredictorWC"):  # the four classes bpl/__init__.py:4-7 exports
+        from . import predictors
+        return getattr(predictors, name)
     raise AttributeError(name)

@@ -1,0 +1,299 @@
+"""The reference's predictor classes on top of the CUDA path: same names, ``fit`` / ``predict_*`` signatures and
+fitted attribute names as ``bpl/dixon_coles.py``, ``bpl/extended_dixon_coles.py``, ``bpl/neutral_dixon_coles.py`` and
+``bpl/neutral_dixon_coles_WC.py`` (+ ``bpl/base.py``), so the reference's tests read the same against this package.
+
+``fit`` = host prep (``data.prepare``) -> ``Problem`` (K1) -> batched GPU NUTS (``nuts.sample``, standing in for
+``numpyro.infer.NUTS`` / ``MCMC``) -> constrained samples cut by the library's site layout -> the deterministic sites the
+reference records (``attack``, ``defence``, venue effects, ``rho``, ``corr_coef``).  ``predict_*`` = K3.
+``mcmc_kwargs`` understands ``num_chains`` (default 1 like numpyro; use hundreds on a GPU) and ``thin``.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Iterable, Optional, Union
+
+import numpy as np
+import torch
+
+from . import data as bdata
+from . import nuts as bnuts
+from .problem import Problem, score_grid_host
+
+MAX_GOALS = bdata.MAX_GOALS
+
+
+def _str_to_list(*args):
+    return tuple([a] if isinstance(a, (str, int, np.integer)) else list(a) for a in args)  # bpl/_util.py:10-14
+
+
+def constrain(flat: np.ndarray, layout: Dict[str, tuple]) -> Dict[str, np.ndarray]:
+    """Flat unconstrained draws ``[S, D]`` -> dict of constrained sites (numpyro ``biject_to``: exp / clipped sigmoid)."""
+    out = {}
+    fi = np.finfo(np.float32)
+    for name, (off, cnt, tr) in layout.items():
+        x = flat[:, off:off + cnt].astype(np.float32)
+        if tr == "exp":
+            x = np.exp(x)
+        elif tr == "sigmoid":
+            x = np.clip(1.0 / (1.0 + np.exp(-x)), fi.tiny, 1.0 - fi.eps).astype(np.float32)
+        out[name] = x[:, 0] if cnt == 1 and not name.endswith(("_decentered", "coefficients")) and name not in (
+            "standardised_attack", "standardised_defence") else x
+    return out
+
+
+class _BplxPredictor:
+    model = ""
+
+    def __init__(self):
+        self.teams = None
+        self._teams_dict = None
+        self.problem: Optional[Problem] = None
+        self.nuts_run = None
+
+    # ---- fit ----------------------------------------------------------------------------------------------
+    def _fit(self, training_data, random_state, num_warmup, num_samples, mcmc_kwargs, epsilon=None,
+             rescale_weights=False):
+        kw = dict(mcmc_kwargs or {})
+        num_chains = int(kw.pop("num_chains", 1))
+        thin = int(kw.pop("thin", kw.pop("thinning", 1)))
+        kw.pop("chain_method", None)
+        kw.pop("progress_bar", None)
+        arr, meta = bdata.prepare(self.model, training_data, epsilon=epsilon, rescale_weights=rescale_weights)
+        self.teams, self._teams_dict = meta["teams"], meta["teams_dict"]
+        self._meta = meta
+        self.problem = p = Problem(arr)
+        g = torch.Generator(device="cuda").manual_seed(int(random_state))
+        theta0 = torch.rand((p.D, num_chains), generator=g, device="cuda") * 4.0 - 2.0  # numpyro init_to_uniform(radius=2)
+
+        def potential(theta, lp, grad):
+            p.logdensity(theta, chain_minor=True, lp=lp, grad=grad)
+
+        run = bnuts.sample(potential, theta0, num_warmup=num_warmup, num_samples=num_samples, thin=thin,
+                           seed=int(random_state), **kw)
+        self.nuts_run = run
+        K, D, C = run.samples.shape
+        flat_dev = run.samples.permute(2, 0, 1).reshape(C * K, D).contiguous()  # chains concatenated like get_samples()
+        _, _, cc = p.logdensity(flat_dev)  # the deterministic site "corr_coef" of every draw
+        torch.cuda.synchronize()
+        s = constrain(flat_dev.cpu().numpy(), p.layout)
+        s["corr_coef"] = cc.cpu().numpy()
+        return arr, s
+
+    @staticmethod
+    def _prior_means(arr, s):
+        S = len(s["mean_defence"])
+        if arr.covariates is not None:  # extended_dixon_coles.py:138-143
+            Xs = arr.covariates.astype(np.float32)
+            return s["attack_coefficients"] @ Xs.T, s["mean_defence"][:, None] + s["defence_coefficients"] @ Xs.T
+        return np.zeros((S, 1), np.float32), s["mean_defence"][:, None]
+
+    # ---- predict (bpl/base.py:62-348) -------------------------------------------------------------------------
+    def _parse_fixture_args(self, home_team, away_team):
+        home_team, away_team = _str_to_list(home_team, away_team)
+        if isinstance(home_team[0], str):
+            home_team = [self._teams_dict[t] for t in home_team]
+        if isinstance(away_team[0], str):
+            away_team = [self._teams_dict[t] for t in away_team]
+        return np.asarray(home_team, dtype=np.uint16), np.asarray(away_team, dtype=np.uint16)
+
+    def _samples(self) -> Dict[str, np.ndarray]:
+        raise NotImplementedError
+
+    def _fixture_extras(self, n, **kw) -> Dict[str, np.ndarray]:
+        return {}
+
+    def _grid(self, home_team, away_team, max_goals, **kw):
+        h, a = self._parse_fixture_args(home_team, away_team)
+        fx = {"home_team": h, "away_team": a, **self._fixture_extras(len(h), **kw)}
+        grid, outcome = score_grid_host(self.model, self._samples(), fx, max_goals)
+        return grid, outcome
+
+    def predict_score_grid_proba(self, home_team, away_team, *args, max_goals: int = MAX_GOALS, **kw):
+        grid, _ = self._grid(home_team, away_team, max_goals, **self._extras_from_args(args, kw))
+        n = np.arange(0, max_goals + 1)
+        hg, ag = np.meshgrid(n, n, indexing="ij")
+        return grid, hg, ag
+
+    def predict_outcome_proba(self, home_team, away_team, *args, max_goals: int = MAX_GOALS, knockout: bool = False, **kw):
+        _, out = self._grid(home_team, away_team, max_goals, **self._extras_from_args(args, kw))
+        hw, dr, aw = out[:, 0], out[:, 1], out[:, 2]
+        if knockout:  # neutral_dixon_coles.py:650-653
+            norm = hw + aw
+            return {"home_win": hw / norm, "away_win": aw / norm}
+        return {"home_win": hw, "draw": dr, "away_win": aw}
+
+    def predict_score_proba(self, home_team, away_team, home_goals, away_goals, *args, **kw):
+        home_goals, away_goals = _str_to_list(home_goals, away_goals)
+        hg, ag = np.asarray(home_goals, dtype=np.int64), np.asarray(away_goals, dtype=np.int64)
+        mg = int(max(hg.max(), ag.max(), 1))
+        grid, _ = self._grid(home_team, away_team, mg, **self._extras_from_args(args, kw))
+        if len(hg) == 1 and grid.shape[0] > 1:
+            hg, ag = np.repeat(hg, grid.shape[0]), np.repeat(ag, grid.shape[0])
+        return grid[np.arange(grid.shape[0]), hg, ag]
+
+    def _n_proba(self, n, team, opponent, home, max_goals, scored, **kw):
+        n = [n] if isinstance(n, (int, np.integer)) else list(np.asarray(n))
+        grid, _ = self._grid(team, opponent, max_goals, **kw) if home else self._grid(opponent, team, max_goals, **kw)
+        # marginal of the grid: sum over the other side's goals (bpl/base.py:248-348)
+        team_axis_is_home = home if scored else not home
+        marg = grid.sum(axis=2) if team_axis_is_home else grid.sum(axis=1)  # [F, g]
+        return marg[0, np.asarray(n, dtype=np.int64)]
+
+    def predict_score_n_proba(self, n, team, opponent, home: bool = True, max_goals: int = MAX_GOALS, **kw):
+        return self._n_proba(n, team, opponent, home, max_goals, True, **kw)
+
+    def predict_concede_n_proba(self, n, team, opponent, home: bool = True, max_goals: int = MAX_GOALS, **kw):
+        return self._n_proba(n, team, opponent, home, max_goals, False, **kw)
+
+    def _extras_from_args(self, args, kw):
+        return kw
+
+
+class DixonColesMatchPredictor(_BplxPredictor):
+    """``bpl/dixon_coles.py:26-163``."""
+    model = "dixon_coles"
+
+    def fit(self, training_data, random_state: int = 42, num_warmup: int = 500, num_samples: int = 1000,
+            mcmc_kwargs: Optional[Dict[str, Any]] = None, run_kwargs: Optional[Dict[str, Any]] = None):
+        arr, s = self._fit(training_data, random_state, num_warmup, num_samples, mcmc_kwargs)
+        self.attack = s["std_attack"][:, None] * s["attack_decentered"]  # dixon_coles.py:52-61
+        self.defence = s["mean_defence"][:, None] + s["std_defence"][:, None] * s["defence_decentered"]
+        self.home_advantage = s["home_advantage"]
+        self.corr_coef = s["corr_coef"]
+        return self
+
+    def _samples(self):
+        return {"attack": self.attack, "defence": self.defence, "home_advantage": self.home_advantage,
+                "corr_coef": self.corr_coef}
+
+
+class ExtendedDixonColesMatchPredictor(_BplxPredictor):
+    """``bpl/extended_dixon_coles.py:28-399`` (``add_new_team`` is out of scope)."""
+    model = "extended"
+
+    def fit(self, training_data, random_state: int = 42, num_warmup: int = 500, num_samples: int = 1000,
+            epsilon: Optional[float] = None, rescale_weights: bool = False,
+            mcmc_kwargs: Optional[Dict[str, Any]] = None, run_kwargs: Optional[Dict[str, Any]] = None):
+        arr, s = self._fit(training_data, random_state, num_warmup, num_samples, mcmc_kwargs, epsilon, rescale_weights)
+        am, dm = self._prior_means(arr, s)
+        self.attack = am + s["standardised_attack"] * s["std_attack"][:, None]  # :182-187
+        self.defence = dm + s["standardised_defence"] * s["std_defence"][:, None]
+        self.home_advantage = s["mean_home_advantage"][:, None] + s["std_home_advantage"][:, None] * s["home_advantage_decentered"]
+        self.corr_coef = s["corr_coef"]
+        self.u = s["u"]
+        self.rho = 2.0 * s["u"] - 1.0
+        self.mean_defence, self.std_attack, self.std_defence = s["mean_defence"], s["std_attack"], s["std_defence"]
+        self.mean_home_advantage, self.std_home_advantage = s["mean_home_advantage"], s["std_home_advantage"]
+        self.standardised_attack, self.standardised_defence = s["standardised_attack"], s["standardised_defence"]
+        self.attack_coefficients = s.get("attack_coefficients") if arr.covariates is not None else None
+        self.defence_coefficients = s.get("defence_coefficients") if arr.covariates is not None else None
+        return self
+
+    def _samples(self):
+        return {"attack": self.attack, "defence": self.defence, "home_advantage": self.home_advantage,
+                "corr_coef": self.corr_coef}
+
+
+class NeutralDixonColesMatchPredictor(_BplxPredictor):
+    """``bpl/neutral_dixon_coles.py:31-902`` (signatures as there: ``neutral_venue`` is a positional fixture argument)."""
+    model = "neutral"
+    _effects = ("home_attack", "away_attack", "home_defence", "away_defence")
+
+    def fit(self, training_data, epsilon: Optional[float] = None, rescale_weights: bool = False, random_state: int = 42,
+            num_warmup: int = 500, num_samples: int = 1000, mcmc_kwargs: Optional[Dict[str, Any]] = None,
+            run_kwargs: Optional[Dict[str, Any]] = None):
+        arr, s = self._fit(training_data, random_state, num_warmup, num_samples, mcmc_kwargs, epsilon, rescale_weights)
+        am, dm = self._prior_means(arr, s)
+        self.attack = am + s["standardised_attack"] * s["std_attack"][:, None]
+        self.defence = dm + s["standardised_defence"] * s["std_defence"][:, None]
+        for nm in self._effects:  # neutral_dixon_coles.py:205-224
+            setattr(self, nm, s["mean_" + nm][:, None] + s["std_" + nm][:, None] * s[nm + "_decentered"])
+            setattr(self, "mean_" + nm, s["mean_" + nm])
+            setattr(self, "std_" + nm, s["std_" + nm])
+        self.corr_coef = s["corr_coef"]
+        self.u = s["u"]
+        self.rho = 2.0 * s["u"] - 1.0
+        self.mean_defence, self.std_attack, self.std_defence = s["mean_defence"], s["std_attack"], s["std_defence"]
+        self.standardised_attack, self.standardised_defence = s["standardised_attack"], s["standardised_defence"]
+        self.attack_coefficients = s.get("attack_coefficients") if arr.covariates is not None else None
+        self.defence_coefficients = s.get("defence_coefficients") if arr.covariates is not None else None
+        if self.model == "neutral_wc":
+            self.confederation_strength = s["confederation_strength_decentered"]  # LocScaleReparam of N(0,1): identity
+            self.conferences, self._conferences_dict = self._meta["conferences"], self._meta["conferences_dict"]
+        return self
+
+    def _samples(self):
+        d = {"attack": self.attack, "defence": self.defence, "corr_coef": self.corr_coef}
+        for nm in self._effects:
+            d[nm] = getattr(self, nm)
+        return d
+
+    def _fixture_extras(self, n, neutral_venue=0, **kw):
+        nv = np.asarray(_str_to_list(neutral_venue)[0], dtype=np.uint8)
+        return {"neutral_venue": np.resize(nv, n).astype(np.uint8)}
+
+    def predict_score_proba(self, home_team, away_team, home_goals, away_goals, neutral_venue):
+        return super().predict_score_proba(home_team, away_team, home_goals, away_goals, neutral_venue=neutral_venue)
+
+    def predict_score_grid_proba(self, home_team, away_team, neutral_venue, max_goals: int = MAX_GOALS):
+        return super().predict_score_grid_proba(home_team, away_team, max_goals=max_goals, neutral_venue=neutral_venue)
+
+    def predict_outcome_proba(self, home_team, away_team, neutral_venue, knockout: bool = False, max_goals: int = MAX_GOALS):
+        return super().predict_outcome_proba(home_team, away_team, max_goals=max_goals, knockout=knockout,
+                                             neutral_venue=neutral_venue)
+
+    def predict_score_n_proba(self, n, team, opponent, home: bool = True, neutral_venue: int = 0, max_goals: int = MAX_GOALS):
+        return self._n_proba(n, team, opponent, home, max_goals, True, neutral_venue=neutral_venue)
+
+    def predict_concede_n_proba(self, n, team, opponent, home: bool = True, neutral_venue: int = 0,
+                                max_goals: int = MAX_GOALS):
+        return self._n_proba(n, team, opponent, home, max_goals, False, neutral_venue=neutral_venue)
+
+
+class NeutralDixonColesMatchPredictorWC(NeutralDixonColesMatchPredictor):
+    """``bpl/neutral_dixon_coles_WC.py:31-968``: neutral model + per-confederation strength."""
+    model = "neutral_wc"
+
+    def fit(self, training_data, epsilon: float = 0.0, rescale_weights: bool = False, random_state: int = 42,
+            num_warmup: int = 500, num_samples: int = 1000, mcmc_kwargs: Optional[Dict[str, Any]] = None,
+            run_kwargs: Optional[Dict[str, Any]] = None):
+        return super().fit(training_data, epsilon, rescale_weights, random_state, num_warmup, num_samples, mcmc_kwargs,
+                           run_kwargs)
+
+    def _samples(self):
+        d = super()._samples()
+        d["confederation_strength"] = self.confederation_strength
+        return d
+
+    def _fixture_extras(self, n, home_conf=None, away_conf=None, neutral_venue=0, **kw):
+        out = super()._fixture_extras(n, neutral_venue=neutral_venue)
+        for key, val in (("home_conf", home_conf), ("away_conf", away_conf)):
+            v = _str_to_list(val)[0]
+            if isinstance(v[0], str):
+                v = [self._conferences_dict[c] for c in v]
+            out[key] = np.resize(np.asarray(v, dtype=np.uint8), n)
+        return out
+
+    def predict_score_proba(self, home_team, away_team, home_conf, away_conf, home_goals, away_goals, neutral_venue):
+        return _BplxPredictor.predict_score_proba(self, home_team, away_team, home_goals, away_goals, home_conf=home_conf,
+                                                  away_conf=away_conf, neutral_venue=neutral_venue)
+
+    def predict_score_grid_proba(self, home_team, away_team, home_conf, away_conf, neutral_venue, max_goals: int = MAX_GOALS):
+        return _BplxPredictor.predict_score_grid_proba(self, home_team, away_team, max_goals=max_goals, home_conf=home_conf,
+                                                       away_conf=away_conf, neutral_venue=neutral_venue)
+
+    def predict_outcome_proba(self, home_team, away_team, home_conf, away_conf, neutral_venue, knockout: bool = False,
+                              max_goals: int = MAX_GOALS):
+        return _BplxPredictor.predict_outcome_proba(self, home_team, away_team, max_goals=max_goals, knockout=knockout,
+                                                    home_conf=home_conf, away_conf=away_conf, neutral_venue=neutral_venue)
+
+    def _conf_kw(self, team_conf, opponent_conf, home, neutral_venue):
+        hc, ac = (team_conf, opponent_conf) if home else (opponent_conf, team_conf)
+        return dict(home_conf=hc, away_conf=ac, neutral_venue=neutral_venue)
+
+    def predict_score_n_proba(self, n, team, opponent, team_conf, opponent_conf, home: bool = True, neutral_venue: int = 0,
+                              max_goals: int = MAX_GOALS):
+        return self._n_proba(n, team, opponent, home, max_goals, True, **self._conf_kw(team_conf, opponent_conf, home, neutral_venue))
+
+    def predict_concede_n_proba(self, n, team, opponent, team_conf, opponent_conf, home: bool = True, neutral_venue: int = 0,
+                                max_goals: int = MAX_GOALS):
+        return self._n_proba(n, team, opponent, home, max_goals, False, **self._conf_kw(team_conf, opponent_conf, home, neutral_venue))
