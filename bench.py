@@ -304,6 +304,29 @@ def extras(args, pk):
     p.close()
     del p
     torch.cuda.empty_cache()
+    # configs[0]: DixonColesMatchPredictor.fit on the 20-team / 380-match season -> ESS/s (whole fit, warm-up included)
+    try:
+        from bpl_next_b200 import DixonColesMatchPredictor, diagnostics as dg
+        for chains, nw, ns in ((1, 500, 1000), (1024, 500, 250)):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            m = DixonColesMatchPredictor().fit(datasets.dummy_data(), num_warmup=nw, num_samples=ns,
+                                               mcmc_kwargs={"num_chains": chains})
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - t0
+            run = m.nuts_run
+            ess = dg.effective_sample_size(run.samples)
+            rhat = dg.split_rhat(run.samples) if ns >= 4 else None
+            out.append({"workload": f"configs[0]: DixonColesMatchPredictor.fit T=20 M=380, {chains} chain(s), {nw} warmup + {ns} draws",
+                        "metric": "ess_per_s", "value": float(ess.min().item()) / wall, "unit": "min-over-parameters bulk ESS / s",
+                        "fit_wall_s": wall, "ess_min": float(ess.min().item()), "ess_median": float(ess.median().item()),
+                        "rhat_max": None if rhat is None else float(rhat.max().item()),
+                        "logdensity_launches": int(run.launches), "leapfrogs_total": int(run.num_leapfrog.sum()),
+                        "divergences": int(run.num_divergent.sum()),
+                        "match_evals_per_s_inside_fit": float(run.num_leapfrog.sum()) * 380 / wall})
+            del m
+    except Exception as e:  # never lose the main line
+        out.append({"workload": "configs[0] fit", "error": repr(e)})
     # configs[4]: predictive grid S=16,384 x F=10,000 x 11x11 (whole job on one GPU here)
     s, fx = datasets.config_5()
     ds = {k: torch.from_numpy(v).cuda() for k, v in s.items()}

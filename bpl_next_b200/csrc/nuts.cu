@@ -26,6 +26,8 @@ namespace bplx {
 
 namespace {
 
+constexpr int kNutsMaxY = 16;  // threads that share one chain (slices of the parameter axis)
+
 struct Vec {  // one per-chain vector of length D inside a chain-minor array
   float* p;
   size_t ld;
@@ -38,23 +40,32 @@ __device__ __forceinline__ float log_add_exp(float a, float b) {
   return m + log1pf(expf(-fabsf(a - b)));
 }
 
-// generalised U-turn (numpyro `_is_turning`, diagonal mass): v = M^-1 r; s = r_sum - (r_left + r_right)/2
-__device__ __forceinline__ bool is_turning(int D, const Vec& imm, const Vec& rl, const Vec& rr, const Vec& rs) {
-  float dl = 0.0f, dr = 0.0f;
-  for (int d = 0; d < D; d++) {
-    const float a = rl[d], b = rr[d], m = imm[d];
-    const float s = rs[d] - 0.5f * (a + b);
-    dl = fmaf(m * a, s, dl);
-    dr = fmaf(m * b, s, dr);
+// sum over the threadIdx.y slices of every chain of the block (all threads of the block must call it)
+template <int N>
+__device__ __forceinline__ void reduce_y(float (&v)[N], float* red) {
+  const int Y = blockDim.y, x = threadIdx.x, y = threadIdx.y;
+  __syncthreads();  // the previous use of `red` is over
+#pragma unroll
+  for (int i = 0; i < N; i++) red[(i * kNutsMaxY + y) * 32 + x] = v[i];
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    float s = 0.0f;
+    for (int k = 0; k < Y; k++) s += red[(i * kNutsMaxY + k) * 32 + x];  // same order in every slice: identical results
+    v[i] = s;
   }
-  return dl <= 0.0f || dr <= 0.0f;
 }
 
 }  // namespace
 
-__global__ void __launch_bounds__(128) nuts_step_kernel(const bplx_nuts_params P) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= P.C) return;
+// block = (32 chains, Y slices).  Thread (x, y) owns parameters d = y, y+Y, ... of chain x; the scalar state machine
+// is replicated in the Y threads of a chain (same inputs, same random numbers -> same decisions); only y == 0 writes it.
+__global__ void __launch_bounds__(32 * kNutsMaxY) nuts_step_kernel(const bplx_nuts_params P) {
+  __shared__ float red[2 * kNutsMaxY * 32];
+  const int Y = blockDim.y, y = threadIdx.y;
+  const int c_raw = blockIdx.x * 32 + threadIdx.x;
+  const bool valid = c_raw < P.C;
+  const int c = valid ? c_raw : P.C - 1;
   const int D = P.D;
   const size_t ld = (size_t)P.ld;
   auto vec = [&](float* base) { return Vec{base + c, ld}; };
@@ -65,38 +76,44 @@ __global__ void __launch_bounds__(128) nuts_step_kernel(const bplx_nuts_params P
   const Vec zQ = vec(P.zQ), gQ = vec(P.gQ), rSq = vec(P.r_sum_sub);
   NutsChain* chains = static_cast<NutsChain*>(P.chain);
   NutsChain st = chains[c];
-  if (st.stage == kNutsDone) return;
+  const bool live = valid && st.stage != kNutsDone;  // threads of finished / padding chains only take part in barriers
   curandStatePhilox4_32_10_t rng;
   curand_init(P.seed, (unsigned long long)(P.chain_offset + c), st.rng_offset, &rng);
   unsigned draws = 0;
   auto uniform = [&]() { draws++; return curand_uniform(&rng); };
   const float lp_new = P.lp[c];
 
-  if (st.stage == kNutsInitEval) {  // gradient at the initial position has just been computed
-    for (int d = 0; d < D; d++) {
+  // ======== A. finish the pending leapfrog: r1 = r_half + eps/2 grad(lp); the new leaf replaces the outer leaf ========
+  const bool pending = live && st.stage == kNutsEvalPending;
+  if (live && st.stage == kNutsInitEval) {  // gradient at the initial position has just been computed
+    for (int d = y; d < D; d += Y) {
       zP[d] = th[d];
       gP[d] = gr[d];
     }
     st.pe = -lp_new;
     st.stage = kNutsNewTransition;
-  } else if (st.stage == kNutsEvalPending) {
-    // ---- finish the leapfrog: r1 = r_half + eps/2 * grad(lp) ; the new leaf replaces the outer leaf ---------
-    const float eps = st.going_right ? st.step_size : -st.step_size;
-    const Vec zE = st.going_right ? zR : zL, rE = st.going_right ? rR : rL, gE = st.going_right ? gR : gL;
-    float ke = 0.0f;
-    for (int d = 0; d < D; d++) {
+  }
+  const float eps = st.going_right ? st.step_size : -st.step_size;
+  const Vec zE = st.going_right ? zR : zL, rE = st.going_right ? rR : rL, gE = st.going_right ? gR : gL;
+  float acc1[1] = {0.0f};
+  if (pending) {
+    for (int d = y; d < D; d += Y) {
       const float g = gr[d];
       const float r1 = fmaf(0.5f * eps, g, ph[d]);
-      ke = fmaf(imm[d] * r1, r1, ke);
+      acc1[0] = fmaf(imm[d] * r1, r1, acc1[0]);
       rE[d] = r1;
       zE[d] = th[d];
       gE[d] = g;
     }
+  }
+  reduce_y(acc1, red);
+  bool sub_done = false;
+  int idx_min = 1, idx_max = 0;
+  if (pending) {
     const float pe1 = -lp_new;
-    float delta = pe1 + 0.5f * ke - st.energy_current;
+    float delta = pe1 + 0.5f * acc1[0] - st.energy_current;
     if (!(delta == delta)) delta = CUDART_INF_F;  // NaN -> reject
     const float w_leaf = -delta;
-    const bool div_leaf = delta > P.max_delta_energy;
     const float acc = fminf(1.0f, expf(-delta));
     // ---- merge the leaf into the subtree (uniform transition kernel inside a subtree) -----------------------------
     bool take;
@@ -108,162 +125,185 @@ __global__ void __launch_bounds__(128) nuts_step_kernel(const bplx_nuts_params P
       take = uniform() < pr;
       st.sub_weight = log_add_exp(st.sub_weight, w_leaf);
     }
-    for (int d = 0; d < D; d++) {
+    // checkpoints for the iterative U-turn test (numpyro `_leaf_idx_to_ckpt_idxs`, `_is_iterative_turning`)
+    const unsigned leaf = (unsigned)st.sub_num;
+    idx_max = __popc(leaf >> 1);
+    idx_min = idx_max - (__ffs(~leaf) - 1) + 1;  // minus the number of trailing one bits
+    const bool ckpt = (leaf & 1u) == 0u;
+    const Vec ck = vec_k(P.r_ckpts, idx_max), cks = vec_k(P.r_sum_ckpts, idx_max);
+    for (int d = y; d < D; d += Y) {
       const float r1 = rE[d];
-      rSq[d] = st.sub_num == 0 ? r1 : rSq[d] + r1;
+      const float rs = st.sub_num == 0 ? r1 : rSq[d] + r1;
+      rSq[d] = rs;
       if (take) {
         zQ[d] = th[d];
         gQ[d] = gr[d];
       }
+      if (ckpt) {
+        ck[d] = r1;
+        cks[d] = rs;
+      }
     }
     if (take) st.sub_pe = pe1;
-    st.sub_div = div_leaf;
+    st.sub_div = delta > P.max_delta_energy;
     st.sub_sum_accept += acc;
-    // checkpoints for the iterative U-turn test (numpyro `_leaf_idx_to_ckpt_idxs`, `_is_iterative_turning`)
-    const unsigned leaf = (unsigned)st.sub_num;
-    const int idx_max = __popc(leaf >> 1);
-    const int ntrail = __ffs(~leaf) - 1;  // number of trailing one bits
-    const int idx_min = idx_max - ntrail + 1;
-    if ((leaf & 1u) == 0u) {
-      const Vec ck = vec_k(P.r_ckpts, idx_max), cks = vec_k(P.r_sum_ckpts, idx_max);
-      for (int d = 0; d < D; d++) {
-        ck[d] = rE[d];
-        cks[d] = rSq[d];
-      }
-    }
-    bool turning = false;
-    for (int i = idx_max; i >= idx_min && !turning; i--) {
+  }
+  // ======== B. iterative U-turn test against the checkpoints (levels idx_max .. idx_min, stop at the first turn) =======
+  bool turning = false;
+  for (int i = P.max_tree_depth - 1; i >= 0; i--) {
+    const bool need = pending && i <= idx_max && i >= idx_min && !turning;
+    if (!__syncthreads_or(need)) continue;
+    float dots[2] = {0.0f, 0.0f};
+    if (need) {
       const Vec ck = vec_k(P.r_ckpts, i), cks = vec_k(P.r_sum_ckpts, i);
-      float dl = 0.0f, dr = 0.0f;
-      for (int d = 0; d < D; d++) {
+      for (int d = y; d < D; d += Y) {
         const float a = ck[d], b = rE[d], m = imm[d];
-        const float sub = rSq[d] - cks[d] + a;  // momentum sum of the subtree that starts at checkpoint i
-        const float s = sub - 0.5f * (a + b);
-        dl = fmaf(m * a, s, dl);
-        dr = fmaf(m * b, s, dr);
+        const float s = (rSq[d] - cks[d] + a) - 0.5f * (a + b);  // momentum sum of the subtree that starts at checkpoint i
+        dots[0] = fmaf(m * a, s, dots[0]);
+        dots[1] = fmaf(m * b, s, dots[1]);
       }
-      turning = dl <= 0.0f || dr <= 0.0f;
     }
+    reduce_y(dots, red);
+    if (need) turning = dots[0] <= 0.0f || dots[1] <= 0.0f;
+  }
+  // ======== C. subtree complete: merge into the trajectory (biased progressive sampling, numpyro `_combine_tree`) =======
+  bool move = false;
+  if (pending) {
     st.sub_turning = turning;
     st.sub_num += 1;
     st.stage = kNutsInTree;
-    if (st.sub_num == (1 << st.depth) || st.sub_turning || st.sub_div) {
-      // ---- subtree complete: merge into the trajectory (biased progressive sampling, numpyro `_combine_tree`) ----
+    sub_done = st.sub_num == (1 << st.depth) || st.sub_turning || st.sub_div;
+    if (sub_done) {
       float pr = fminf(1.0f, expf(st.sub_weight - st.weight));
       if (st.sub_turning || st.sub_div) pr = 0.0f;
-      const bool move = uniform() < pr;
-      for (int d = 0; d < D; d++) {
-        rS[d] += rSq[d];
+      move = uniform() < pr;
+    }
+  }
+  {
+    float dots[2] = {0.0f, 0.0f};  // generalised U-turn of the whole trajectory (numpyro `_is_turning`, diagonal mass)
+    if (sub_done) {
+      for (int d = y; d < D; d += Y) {
+        const float rs = rS[d] + rSq[d];
+        rS[d] = rs;
         if (move) {
           zP[d] = zQ[d];
           gP[d] = gQ[d];
         }
+        const float a = rL[d], b = rR[d], m = imm[d];
+        const float s = rs - 0.5f * (a + b);
+        dots[0] = fmaf(m * a, s, dots[0]);
+        dots[1] = fmaf(m * b, s, dots[1]);
       }
+    }
+    if (__syncthreads_or(sub_done)) reduce_y(dots, red);
+    if (sub_done) {
       if (move) st.pe = st.sub_pe;
-      st.turning = st.sub_turning || is_turning(D, imm, rL, rR, rS);
+      st.turning = st.sub_turning || dots[0] <= 0.0f || dots[1] <= 0.0f;
       st.depth += 1;
       st.weight = log_add_exp(st.weight, st.sub_weight);
       st.diverging = st.sub_div;
       st.sum_accept += st.sub_sum_accept;
       st.num_prop += st.sub_num;
       st.sub_active = 0;
-      if (st.depth >= P.max_tree_depth || st.turning || st.diverging) {
-        // ---- transition complete ----------------------------------------------------------------------------------
-        const float accept = st.sum_accept / (float)st.num_prop;
-        st.num_leapfrog_total += st.num_prop;
-        if (st.diverging && st.t >= P.num_warmup) st.num_divergent += 1;
-        if (st.t < P.num_warmup) {
-          // dual averaging (numpyro `dual_averaging`) on g = target - accept
-          const float g = P.target_accept - accept;
-          st.da_t += 1;
-          const float t = (float)st.da_t;
-          st.da_g_avg = (1.0f - 1.0f / (t + 10.0f)) * st.da_g_avg + g / (t + 10.0f);
-          st.da_x = st.da_mu - sqrtf(t) / 0.05f * st.da_g_avg;
-          const float wt = powf(t, -0.75f);
-          st.da_x_avg = (1.0f - wt) * st.da_x_avg + wt * st.da_x;
-          st.step_size = fmaxf(expf(st.t == P.num_warmup - 1 ? st.da_x_avg : st.da_x), 1.1754944e-38f);
-          const bplx_window win = P.windows[st.window];  // the current adaptation window
-          const bool middle = st.window > 0 && st.window < P.num_windows - 1;
-          const bool at_end = st.t == win.end;
-          if (middle) {  // Welford on the new position
-            const Vec mean = vec(P.wf_mean), m2 = vec(P.wf_m2);
-            st.wf_n += 1;
-            const float inv_n = 1.0f / (float)st.wf_n;
-            for (int d = 0; d < D; d++) {
-              const float x = zP[d], pre = x - mean[d];
-              const float mnew = fmaf(pre, inv_n, mean[d]);
-              mean[d] = mnew;
-              m2[d] = fmaf(pre, x - mnew, m2[d]);
-            }
-            if (at_end) {  // regularised variance -> inverse mass; restart the step-size search around 10 eps
-              const Vec mean2 = vec(P.wf_mean), m22 = vec(P.wf_m2);
-              const float n = (float)st.wf_n;
-              for (int d = 0; d < D; d++) {
-                const float var = m22[d] / (n - 1.0f);
-                imm[d] = (n / (n + 5.0f)) * var + 1e-3f * (5.0f / (n + 5.0f));
-                mean2[d] = 0.0f;
-                m22[d] = 0.0f;
-              }
-              st.wf_n = 0;
-              st.da_mu = logf(10.0f * st.step_size);
-              st.da_x = st.da_x_avg = st.da_g_avg = 0.0f;
-              st.da_t = 0;
-            }
-          }
-          if (at_end) st.window += 1;
-        } else {
-          const int k = st.t - P.num_warmup;
-          if (k % P.thin == 0) {
-            const int slot = k / P.thin;
-            if (slot < P.num_keep) {
-              float* out = P.samples + (size_t)slot * D * ld + c;
-              for (int d = 0; d < D; d++) out[(size_t)d * ld] = zP[d];
-              P.sample_lp[(size_t)slot * ld + c] = -st.pe;
-              P.sample_accept[(size_t)slot * ld + c] = accept;
-            }
-          }
-        }
-        st.t += 1;
-        st.stage = st.t >= P.num_warmup + P.num_samples ? kNutsDone : kNutsNewTransition;
-      }
     }
   }
-
-  if (st.stage == kNutsNewTransition) {
-    // ---- momentum refresh: r ~ N(0, M), M = 1 / inv_mass -------------------------------------------------------
-    float ke = 0.0f;
-    for (int d = 0; d < D; d += 4) {
-      const float4 n4 = curand_normal4(&rng);
-      draws += 4;
-      const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        if (d + i < D) {
-          const float m = imm[d + i];
-          const float r = nn[i] * rsqrtf(m);
-          ke = fmaf(m * r, r, ke);
-          rL[d + i] = r;
-          rR[d + i] = r;
-          rS[d + i] = r;
-          const float z = zP[d + i], g = gP[d + i];
-          zL[d + i] = z;
-          zR[d + i] = z;
-          gL[d + i] = g;
-          gR[d + i] = g;
+  // ======== D. transition complete: adaptation during warm-up, collection afterwards ===============================
+  if (sub_done && (st.depth >= P.max_tree_depth || st.turning || st.diverging)) {
+    const float accept = st.sum_accept / (float)st.num_prop;
+    st.num_leapfrog_total += st.num_prop;
+    if (st.diverging && st.t >= P.num_warmup) st.num_divergent += 1;
+    if (st.t < P.num_warmup) {
+      // dual averaging (numpyro `dual_averaging`) on g = target - accept
+      const float g = P.target_accept - accept;
+      st.da_t += 1;
+      const float t = (float)st.da_t;
+      st.da_g_avg = (1.0f - 1.0f / (t + 10.0f)) * st.da_g_avg + g / (t + 10.0f);
+      st.da_x = st.da_mu - sqrtf(t) / 0.05f * st.da_g_avg;
+      const float wt = powf(t, -0.75f);
+      st.da_x_avg = (1.0f - wt) * st.da_x_avg + wt * st.da_x;
+      st.step_size = fmaxf(expf(st.t == P.num_warmup - 1 ? st.da_x_avg : st.da_x), 1.1754944e-38f);
+      const bplx_window win = P.windows[st.window];  // the current adaptation window
+      const bool middle = st.window > 0 && st.window < P.num_windows - 1;
+      const bool at_end = st.t == win.end;
+      if (middle) {  // Welford on the new position; at the window's end: regularised variance -> inverse mass
+        const Vec mean = vec(P.wf_mean), m2 = vec(P.wf_m2);
+        st.wf_n += 1;
+        const float n = (float)st.wf_n, inv_n = 1.0f / n;
+        for (int d = y; d < D; d += Y) {
+          const float x = zP[d], pre = x - mean[d];
+          const float mnew = fmaf(pre, inv_n, mean[d]);
+          const float m2new = fmaf(pre, x - mnew, m2[d]);
+          if (at_end) {
+            imm[d] = (n / (n + 5.0f)) * (m2new / (n - 1.0f)) + 1e-3f * (5.0f / (n + 5.0f));
+            mean[d] = 0.0f;
+            m2[d] = 0.0f;
+          } else {
+            mean[d] = mnew;
+            m2[d] = m2new;
+          }
+        }
+        if (at_end) {  // restart the step-size search around 10 eps
+          st.wf_n = 0;
+          st.da_mu = logf(10.0f * st.step_size);
+          st.da_x = st.da_x_avg = st.da_g_avg = 0.0f;
+          st.da_t = 0;
+        }
+      }
+      if (at_end) st.window += 1;
+    } else {
+      const int k = st.t - P.num_warmup;
+      if (k % P.thin == 0 && k / P.thin < P.num_keep) {
+        const int slot = k / P.thin;
+        float* out = P.samples + (size_t)slot * D * ld + c;
+        for (int d = y; d < D; d += Y) out[(size_t)d * ld] = zP[d];
+        if (y == 0) {
+          P.sample_lp[(size_t)slot * ld + c] = -st.pe;
+          P.sample_accept[(size_t)slot * ld + c] = accept;
         }
       }
     }
-    st.energy_current = st.pe + 0.5f * ke;
-    st.depth = 0;
-    st.weight = 0.0f;
-    st.turning = st.diverging = 0;
-    st.sum_accept = 0.0f;
-    st.num_prop = 0;
-    st.sub_active = 0;
-    st.stage = kNutsInTree;
+    st.t += 1;
+    st.stage = st.t >= P.num_warmup + P.num_samples ? kNutsDone : kNutsNewTransition;
   }
-
-  if (st.stage == kNutsInTree) {
+  // ======== E. momentum refresh: r ~ N(0, M), M = 1 / inv_mass ==========================================================
+  const bool fresh = live && st.stage == kNutsNewTransition;
+  {
+    float ke[1] = {0.0f};
+    if (fresh) {
+      // normals come from their own stretch of the chain's Philox sequence, addressed by d: every slice sees the same r[d]
+      const unsigned long long base = st.rng_offset + 64ull;
+      for (int d = y; d < D; d += Y) {
+        curandStatePhilox4_32_10_t rn;
+        curand_init(P.seed, (unsigned long long)(P.chain_offset + c), base + 4ull * (unsigned long long)(d >> 1), &rn);
+        const float2 n2 = curand_normal2(&rn);
+        const float m = imm[d];
+        const float r = ((d & 1) ? n2.y : n2.x) * rsqrtf(m);
+        ke[0] = fmaf(m * r, r, ke[0]);
+        rL[d] = r;
+        rR[d] = r;
+        rS[d] = r;
+        const float z = zP[d], g = gP[d];
+        zL[d] = z;
+        zR[d] = z;
+        gL[d] = g;
+        gR[d] = g;
+      }
+    }
+    if (__syncthreads_or(fresh)) reduce_y(ke, red);
+    if (fresh) {
+      draws += 64u + 2u * (unsigned)D + 8u;
+      st.energy_current = st.pe + 0.5f * ke[0];
+      st.depth = 0;
+      st.weight = 0.0f;
+      st.turning = st.diverging = 0;
+      st.sum_accept = 0.0f;
+      st.num_prop = 0;
+      st.sub_active = 0;
+      st.stage = kNutsInTree;
+    }
+  }
+  // ======== F. start the next leapfrog from the outer leaf: r_half = r + eps/2 grad(lp); theta = z + eps M^-1 r_half ====
+  if (live && st.stage == kNutsInTree) {
     if (!st.sub_active) {  // next doubling: direction, empty subtree
       st.going_right = uniform() < 0.5f ? 1 : 0;
       st.sub_active = 1;
@@ -272,19 +312,20 @@ __global__ void __launch_bounds__(128) nuts_step_kernel(const bplx_nuts_params P
       st.sub_sum_accept = 0.0f;
       st.sub_turning = st.sub_div = 0;
     }
-    // ---- start the next leapfrog from the outer leaf: r_half = r + eps/2 grad(lp); theta = z + eps M^-1 r_half ------
-    const float eps = st.going_right ? st.step_size : -st.step_size;
-    const Vec zE = st.going_right ? zR : zL, rE = st.going_right ? rR : rL, gE = st.going_right ? gR : gL;
-    for (int d = 0; d < D; d++) {
-      const float rh = fmaf(0.5f * eps, gE[d], rE[d]);
+    const float e2 = st.going_right ? st.step_size : -st.step_size;
+    const Vec zF = st.going_right ? zR : zL, rF = st.going_right ? rR : rL, gF = st.going_right ? gR : gL;
+    for (int d = y; d < D; d += Y) {
+      const float rh = fmaf(0.5f * e2, gF[d], rF[d]);
       ph[d] = rh;
-      th[d] = fmaf(eps * imm[d], rh, zE[d]);
+      th[d] = fmaf(e2 * imm[d], rh, zF[d]);
     }
     st.stage = kNutsEvalPending;
   }
-  st.rng_offset += (draws + 7u) & ~3u;  // curand_init's offset counts 32-bit outputs; keep calls on disjoint ranges
-  chains[c] = st;
-  if (st.stage != kNutsDone) atomicAdd(P.active_count, 1);
+  if (live && y == 0) {
+    st.rng_offset += (draws + 7u) & ~3u;  // curand_init's offset counts 32-bit outputs; keep calls on disjoint ranges
+    chains[c] = st;
+    if (st.stage != kNutsDone) atomicAdd(P.active_count, 1);
+  }
 }
 
 __global__ void nuts_init_kernel(const bplx_nuts_params P) {
@@ -339,7 +380,9 @@ int bplx_nuts_step(const bplx_nuts_params* p, void* stream) {
   BPLX_REQUIRE(p && p->C > 0 && p->D > 0 && p->ld >= p->C, BPLX_E_INVALID, "nuts: bad C / D / ld");
   BPLX_REQUIRE(p->max_tree_depth >= 1 && p->max_tree_depth <= 12 && p->thin >= 1, BPLX_E_INVALID,
                "nuts: max_tree_depth must be in [1, 12] and thin >= 1");
-  nuts_step_kernel<<<(p->C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(*p);
+  int Y = (p->D + 3) / 4;  // about four parameters per thread, at most kNutsMaxY slices per chain
+  Y = Y < 1 ? 1 : (Y > kNutsMaxY ? kNutsMaxY : Y);
+  nuts_step_kernel<<<(p->C + 31) / 32, dim3(32, Y), 0, static_cast<cudaStream_t>(stream)>>>(*p);
   BPLX_CUDA(cudaGetLastError());
   note_launch(1);
   return BPLX_OK;

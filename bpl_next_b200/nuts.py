@@ -92,8 +92,8 @@ class NutsRun:
 
 def sample(potential: Callable[[torch.Tensor, torch.Tensor, torch.Tensor], None], theta0: torch.Tensor,
            num_warmup: int = 500, num_samples: int = 1000, thin: int = 1, seed: int = 42, max_tree_depth: int = 10,
-           target_accept: float = 0.8, step_size: float = 1.0, chain_offset: int = 0, check_every: int = 16,
-           max_launches: Optional[int] = None) -> NutsRun:
+           target_accept: float = 0.8, step_size: float = 1.0, chain_offset: int = 0, check_every: int = 32,
+           max_launches: Optional[int] = None, use_graph: bool = True) -> NutsRun:
     """``theta0``: ``[D, C]`` float32 CUDA tensor (chain-minor) of initial unconstrained positions."""
     if not theta0.is_cuda:
         raise RuntimeError("bpl_next_b200.nuts needs CUDA tensors: there is no CPU fallback")
@@ -132,19 +132,34 @@ def sample(potential: Callable[[torch.Tensor, torch.Tensor, torch.Tensor], None]
     p.samples, p.sample_lp, p.sample_accept = samples.data_ptr(), sample_lp.data_ptr(), sample_accept.data_ptr()
     p.active_count = active.data_ptr()
 
-    stream = torch.cuda.current_stream().cuda_stream
-    _abi.check(lib.bplx_nuts_init(C.byref(p), stream))
-    launches = 0
     limit = max_launches if max_launches is not None else (num_warmup + num_samples + 1) * (2 ** max_tree_depth) + 8
-    while launches < limit:
+
+    def block():  # check_every x (log-density, NUTS step); the last step counts the chains that are not finished
+        st = torch.cuda.current_stream().cuda_stream
         for k in range(check_every):
             potential(theta_eval, lp, grad)
             if k == check_every - 1:
                 active.zero_()
-            _abi.check(lib.bplx_nuts_step(C.byref(p), stream))
-        launches += check_every
-        if int(active.item()) == 0:
-            break
+            _abi.check(lib.bplx_nuts_step(C.byref(p), st))
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        _abi.check(lib.bplx_nuts_init(C.byref(p), side.cuda_stream))
+        block()  # eager once: lazy allocations inside `potential` happen outside the capture
+        launches = check_every
+        graph = None
+        if use_graph and int(active.item()) != 0:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                block()
+        while launches < limit and int(active.item()) != 0:
+            if graph is not None:
+                graph.replay()
+            else:
+                block()
+            launches += check_every
+    torch.cuda.current_stream().wait_stream(side)
     summ = np.zeros((Cn, 8), dtype=np.float32)
     torch.cuda.synchronize()
     _abi.check(lib.bplx_nuts_summary(C.byref(p), summ.ctypes.data))
