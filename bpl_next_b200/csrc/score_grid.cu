@@ -12,7 +12,8 @@
 //
 //   grid = (F / 256 fixture blocks, grid tiles, sample splits); partial sums per split go to the
 //   workspace and a finalize kernel sums the splits in a fixed order (deterministic), applies
-//   `scale` and reduces the W/D/L masks of bpl/base.py:140-142.
+//   `scale` and the 1 / (hg! ag!) of the two pmfs, and a third kernel reduces the W/D/L masks of
+//   bpl/base.py:140-142.
 #include "score_grid.h"
 
 namespace bplx {
@@ -124,66 +125,74 @@ __global__ void __launch_bounds__(kGridThreads, 1) score_grid_kernel(const __gri
     cp_async_wait<1>();
     __syncthreads();
     const int ns = min(kGridStage, s_end - (s_begin + st * kGridStage));
-    for (int j = 0; j < ns; j++) {
-      const float* A = cur + L.att + j * gp.T;
-      const float* Dd = cur + L.def + j * gp.T;
-      float eh = A[h] - Dd[a], ea = A[a] - Dd[h];
-      if (gp.model == BPLX_DIXON_COLES) {
-        eh += cur[L.ha + j];
-      } else if (gp.model == BPLX_EXTENDED) {
-        eh += cur[L.ha + j * gp.T + h];
-      } else {
-        if (gp.model == BPLX_NEUTRAL_WC) {
-          const float* cs = cur + L.conf + j * gp.Cf;
-          const float dcf = cs[hc] - cs[ac];
-          eh += dcf;
-          ea -= dcf;
+    // two samples per trip: their gathers / exps overlap.  The accumulators hold sum_s e^-lh lh^i e^-la la^j; the
+    // 1 / (i! j!) of the two Poisson pmfs is applied once, by the finalize kernel.
+#pragma unroll 1
+    for (int j0 = 0; j0 < ns; j0 += 2) {
+      float ph[2][R], pa[2][CC], t00[2], t01[2], t10[2], t11[2];
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const int j = min(j0 + u, ns - 1);
+        const float* A = cur + L.att + j * gp.T;
+        const float* Dd = cur + L.def + j * gp.T;
+        float eh = A[h] - Dd[a], ea = A[a] - Dd[h];
+        if (gp.model == BPLX_DIXON_COLES) {
+          eh += cur[L.ha + j];
+        } else if (gp.model == BPLX_EXTENDED) {
+          eh += cur[L.ha + j * gp.T + h];
+        } else {
+          if (gp.model == BPLX_NEUTRAL_WC) {
+            const float* cs = cur + L.conf + j * gp.Cf;
+            const float dcf = cs[hc] - cs[ac];
+            eh += dcf;
+            ea -= dcf;
+          }
+          eh += n * cur[L.ha + j * gp.T + h] - n * cur[L.ad + j * gp.T + a];
+          ea += n * cur[L.aa + j * gp.T + a] - n * cur[L.hd + j * gp.T + h];
         }
-        eh += n * cur[L.ha + j * gp.T + h] - n * cur[L.ad + j * gp.T + a];
-        ea += n * cur[L.aa + j * gp.T + a] - n * cur[L.hd + j * gp.T + h];
-      }
-      const float lh = __expf(eh), la = __expf(ea);
-      const float c = cur[L.corr + j];
-      // Poisson pmfs by recurrence
-      float ph[R], pa[CC];
-      {
-        float p = __expf(-lh);
+        const float lh = __expf(eh), la = __expf(ea);
+        const float c = cur[L.corr + j];
+        // e^-lambda lambda^k by recurrence (k! is applied at the end); a duplicated last sample gets weight 0
+        float p = (j0 + u < ns) ? __expf(-lh) : 0.0f;
         if (!SINGLE)
-          for (int k = 1; k <= r0; k++) p *= lh * __frcp_rn((float)k);
-        ph[0] = p;
+          for (int k = 1; k <= r0; k++) p *= lh;
+        ph[u][0] = p;
 #pragma unroll
         for (int i = 1; i < R; i++) {
-          p *= SINGLE ? lh * (1.0f / (float)i) : lh * __frcp_rn((float)(r0 + i));
-          ph[i] = p;
+          p *= lh;
+          ph[u][i] = p;
         }
         p = __expf(-la);
         if (!SINGLE)
-          for (int k = 1; k <= c0; k++) p *= la * __frcp_rn((float)k);
-        pa[0] = p;
+          for (int k = 1; k <= c0; k++) p *= la;
+        pa[u][0] = p;
 #pragma unroll
         for (int i = 1; i < CC; i++) {
-          p *= SINGLE ? la * (1.0f / (float)i) : la * __frcp_rn((float)(c0 + i));
-          pa[i] = p;
+          p *= la;
+          pa[u][i] = p;
+        }
+        // tau on the four low-score cells, clipped at 0 (bpl/_util.py:62-68)
+        t00[u] = t01[u] = t10[u] = t11[u] = 1.0f;
+        if (corner) {
+          t00[u] = fmaxf(1.0f - (c * lh) * la, 0.0f);
+          t10[u] = fmaxf(fmaf(c, la, 1.0f), 0.0f);  // home 1, away 0
+          t01[u] = fmaxf(fmaf(c, lh, 1.0f), 0.0f);  // home 0, away 1
+          t11[u] = fmaxf(1.0f - c, 0.0f);
         }
       }
-      // tau on the four low-score cells, clipped at 0 (bpl/_util.py:62-68)
-      float t00 = 1.0f, t01 = 1.0f, t10 = 1.0f, t11 = 1.0f;
-      if (corner) {
-        t00 = fmaxf(1.0f - (c * lh) * la, 0.0f);
-        t10 = fmaxf(fmaf(c, la, 1.0f), 0.0f);  // home 1, away 0
-        t01 = fmaxf(fmaf(c, lh, 1.0f), 0.0f);  // home 0, away 1
-        t11 = fmaxf(1.0f - c, 0.0f);
-      }
 #pragma unroll
-      for (int i = 0; i < R; i++) {
+      for (int u = 0; u < 2; u++) {
 #pragma unroll
-        for (int jj = 0; jj < CC; jj++) {
-          float w = ph[i];
-          if (i == 0 && jj == 0) w *= t00;
-          if (i == 0 && jj == 1) w *= t01;
-          if (i == 1 && jj == 0) w *= t10;
-          if (i == 1 && jj == 1) w *= t11;
-          acc[i][jj] = fmaf(w, pa[jj], acc[i][jj]);
+        for (int i = 0; i < R; i++) {
+#pragma unroll
+          for (int jj = 0; jj < CC; jj++) {
+            float w = ph[u][i];
+            if (i == 0 && jj == 0) w *= t00[u];
+            if (i == 0 && jj == 1) w *= t01[u];
+            if (i == 1 && jj == 0) w *= t10[u];
+            if (i == 1 && jj == 1) w *= t11[u];
+            acc[i][jj] = fmaf(w, pa[u][jj], acc[i][jj]);
+          }
         }
       }
     }
@@ -207,7 +216,12 @@ __global__ void score_grid_finalize(const GridParams gp) {
   if (i >= n) return;
   float s = 0.0f;
   for (int k = 0; k < gp.nsplit; k++) s += gp.partial[(size_t)k * n + i];
-  gp.grid[i] = s * gp.scale;
+  // the kernel accumulates e^-lh lh^i e^-la la^j: the pmfs' 1 / (i! j!) goes here (double: 63! overflows float)
+  const int cell = (int)(i % (size_t)(gp.g * gp.g)), hg = cell / gp.g, ag = cell % gp.g;
+  double f = 1.0;
+  for (int k = 2; k <= hg; k++) f *= (double)k;
+  for (int k = 2; k <= ag; k++) f *= (double)k;
+  gp.grid[i] = (float)((double)s * (double)gp.scale / f);
 }
 
 // home_win / draw / away_win = masked sums of the grid (bpl/base.py:140-142); one warp per fixture
