@@ -438,7 +438,7 @@ def main():
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             with open(tp) as f:
-                traffic = json.load(f).get(args.workload)
+                traffic = (json.load(f).get(args.workload) or {}).get("traffic")  # dram read + write bytes of one launch (ncu --set full)
         roofline = {
             "bound": "fp32", "kernel": "bplx::logdensity_kernel",
             "achieved": flops / t_launch / 1e12, "peak": pk["fp32_tflops"], "unit": "TFLOP/s",
