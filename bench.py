@@ -453,7 +453,8 @@ def main():
                      "frac": smem_bytes / t_launch / 1e12 / pk["smem_tbs"],
                      "peak_source": "LDS.64 peak measured in this run"},
         }
-        cpu = cpu_port(arr, args.cpu_chains, args.cpu_seconds, args.radius, args.seed + 1)
+        # the CPU baseline is a reported number of the N=1 run only
+        cpu = cpu_port(arr, args.cpu_chains, args.cpu_seconds, args.radius, args.seed + 1) if world == 1 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

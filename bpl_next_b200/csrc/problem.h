@@ -19,7 +19,9 @@ struct bplx_problem {
   float *d_theta = nullptr, *d_out = nullptr;
   void* d_ws = nullptr;
   size_t d_ws_bytes = 0;
-  cudaStream_t host_stream = nullptr;
+  cudaStream_t host_stream = nullptr;            // compute
+  cudaStream_t host_in = nullptr, host_out = nullptr;  // H2D / D2H copies of the host variant (pipelined by chunk)
+  cudaEvent_t host_ev[16] = {};                     // [2 * chunk]: chunk uploaded, chunk computed
   // plan statistics (for DESIGN/bench reporting)
   long long stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
