@@ -13,7 +13,8 @@ def __getattr__(name):  # lazy: importing torch is slow and not needed for host-
         from . import problem
         return getattr(problem, name)
     if name in ("DixonColesMatchPredictor", "ExtendedDixonColesMatchPredictor", "NeutralDixonColesMatchPredictor",
-                "NeutralDixonColesMatchPredictorWC"):  # the four classes bpl/__init__.py:4-7 exports
+                "NeutralDixonColesMatchPredictorWC",  # the four classes bpl/__init__.py:4-7 exports
+                "DynamicNeutralDixonColesMatchPredictor"):  # not exported by the reference; fit only
         from . import predictors
         return getattr(predictors, name)
     raise AttributeError(name)

@@ -297,3 +297,82 @@ class NeutralDixonColesMatchPredictorWC(NeutralDixonColesMatchPredictor):
     def predict_concede_n_proba(self, n, team, opponent, team_conf, opponent_conf, home: bool = True, neutral_venue: int = 0,
                                 max_goals: int = MAX_GOALS):
         return self._n_proba(n, team, opponent, home, max_goals, False, **self._conf_kw(team_conf, opponent_conf, home, neutral_venue))
+
+
+class DynamicNeutralDixonColesMatchPredictor(_BplxPredictor):
+    """``bpl/dynamic_dixon_coles.py:23-334`` -- ``fit`` only.  The reference's predict methods index a Python list with a
+    tuple and cannot run, so they are not mirrored.  ``walk="intended"`` (default) makes attack / defence the
+    cumulative random walk the model describes; ``walk="as_written"`` reproduces ``:192-218`` literally.
+    Gameweeks are 0-based and G = max + 1 (the reference passes ``max``)."""
+    model = "dynamic"
+
+    def __init__(self, walk: str = "intended"):
+        super().__init__()
+        if walk not in ("intended", "as_written"):
+            raise ValueError(walk)
+        self.walk = walk
+
+    def fit(self, training_data, random_state: int = 42, num_warmup: int = 500, num_samples: int = 1000,
+            mcmc_kwargs: Optional[Dict[str, Any]] = None, run_kwargs: Optional[Dict[str, Any]] = None):
+        kw = dict(mcmc_kwargs or {})
+        num_chains = int(kw.pop("num_chains", 1))
+        thin = int(kw.pop("thin", kw.pop("thinning", 1)))
+        kw.pop("chain_method", None)
+        kw.pop("progress_bar", None)
+        arr, meta = bdata.prepare("dynamic", training_data)
+        arr.as_written = self.walk == "as_written"
+        self.teams, self._teams_dict = list(meta["teams"]), meta["teams_dict"]
+        self.problem = p = Problem(arr)
+        G, T = arr.num_gameweeks, arr.num_teams
+        g = torch.Generator(device="cuda").manual_seed(int(random_state))
+        theta0 = torch.rand((p.D, num_chains), generator=g, device="cuda") * 4.0 - 2.0
+
+        def potential(theta, lp, grad):
+            p.logdensity(theta, chain_minor=True, lp=lp, grad=grad)
+
+        run = bnuts.sample(potential, theta0, num_warmup=num_warmup, num_samples=num_samples, thin=thin,
+                           seed=int(random_state), **kw)
+        self.nuts_run = run
+        K, D, C = run.samples.shape
+        flat_dev = run.samples.permute(2, 0, 1).reshape(C * K, D).contiguous()
+        _, _, cc = p.logdensity(flat_dev)
+        torch.cuda.synchronize()
+        flat = flat_dev.cpu().numpy()
+        fi = np.finfo(np.float32)
+        s = {}
+        for name, (off, cnt, tr) in p.layout.items():
+            x = flat[:, off:off + cnt]
+            if tr == "exp":
+                x = np.exp(x)
+            elif tr == "sigmoid":
+                x = np.clip(1.0 / (1.0 + np.exp(-x)), fi.tiny, 1.0 - fi.eps)
+            s[name] = x.astype(np.float32)
+        S = flat.shape[0]
+        gt = lambda k: s[k].reshape(S, G, T)  # noqa: E731
+        self.corr_coef = cc.cpu().numpy()
+        self.u, self.rho = gt("u"), 2.0 * gt("u") - 1.0
+        self.standardised_attack, self.standardised_defence = gt("standardised_attack"), gt("standardised_defence")
+        self.mean_defence = s["mean_defence"][:, 0]
+        self.std_attack, self.std_defence = s["std_attack"], s["std_defence"]  # [S, G]
+        for nm in ("home_attack", "away_attack", "home_defence", "away_defence"):
+            setattr(self, "mean_" + nm, s["mean_" + nm])
+            setattr(self, "std_" + nm, s["std_" + nm])
+            setattr(self, nm, s["mean_" + nm][:, :, None] + s["std_" + nm][:, :, None] * gt(nm + "_decentered"))
+        am, dm = np.zeros((S, 1), np.float32), self.mean_defence[:, None]
+        if arr.covariates is not None:
+            Xs = arr.covariates.astype(np.float32)
+            am, dm = s["attack_coefficients"] @ Xs.T, dm + s["defence_coefficients"] @ Xs.T
+            self.attack_coefficients, self.defence_coefficients = s["attack_coefficients"], s["defence_coefficients"]
+        else:
+            self.attack_coefficients = self.defence_coefficients = None
+        step_a = self.standardised_attack * self.std_attack[:, :, None]
+        step_d = self.standardised_defence * self.std_defence[:, :, None]
+        if self.walk == "intended":
+            att, dfn = am[:, None, :] + np.cumsum(step_a, axis=1), dm[:, None, :] + np.cumsum(step_d, axis=1)
+        else:  # the recorded deterministics attack_j = 0 + z[j] std[j] for j >= 1 (SURVEY D1)
+            att, dfn = step_a.copy(), step_d.copy()
+            att[:, 0] += am
+            dfn[:, 0] += dm
+        self.attack = [att[:, j] for j in range(G)]  # the reference stores lists of [S, T] arrays (:308-309)
+        self.defence = [dfn[:, j] for j in range(G)]
+        return self

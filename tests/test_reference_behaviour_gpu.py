@@ -103,3 +103,30 @@ def test_neutral_models(wc):  # tests/test_neutral_dixon_coles.py, tests/test_ne
     assert out["away_win"][nv == 1].mean() > out["away_win"][nv == 0].mean()
     ko = model.predict_outcome_proba("0", "1", *one_conf, 1, knockout=True)
     assert ko["home_win"] + ko["away_win"] == pytest.approx(1.0, abs=1e-6)
+
+
+def test_dynamic_fit_runs_and_tracks_a_drifting_team():
+    """The dynamic class has no tests in the reference (and its predict methods cannot run): fit a small league in
+    which one team's attack climbs over the seasons and check that the fitted walk follows it."""
+    import itertools
+    from bpl_next_b200 import DynamicNeutralDixonColesMatchPredictor
+
+    rng = np.random.default_rng(0)
+    T, G = 6, 5
+    names = [f"T{i}" for i in range(T)]
+    ht, at, hg, ag, gw = [], [], [], [], []
+    for g in range(G):
+        att = np.zeros(T)
+        att[0] = -0.6 + 0.3 * g  # team 0 improves every season
+        for _ in range(3):
+            for h, a in itertools.permutations(range(T), 2):
+                ht.append(names[h]); at.append(names[a]); gw.append(g)
+                hg.append(rng.poisson(np.exp(0.2 + att[h]))); ag.append(rng.poisson(np.exp(att[a])))
+    td = {"home_team": ht, "away_team": at, "home_goals": np.array(hg), "away_goals": np.array(ag),
+          "gameweek": np.array(gw), "neutral_venue": np.zeros(len(ht), dtype=int)}
+    m = DynamicNeutralDixonColesMatchPredictor().fit(td, num_warmup=300, num_samples=30, mcmc_kwargs={"num_chains": 64})
+    assert len(m.attack) == G and m.attack[0].shape == (64 * 30, T)
+    a0 = np.array([m.attack[g][:, 0].mean() - m.attack[g][:, 1:].mean() for g in range(G)])
+    assert a0[-1] - a0[0] > 0.25 and a0[-1] > a0[2] > a0[0], a0  # heavily shrunk (six sites per team and week share the signal)
+    assert np.all(np.isfinite(m.corr_coef))
+    assert m.nuts_run.num_divergent.mean() < 2
