@@ -122,3 +122,38 @@ def test_errors():
     with pytest.raises(_abi.BplxError) as e:
         Problem(arr)
     assert e.value.status == _abi.E_INVALID
+
+
+def test_edge_cases():
+    """One match, idle teams, zero weights / double-digit goals, single confederation with every venue neutral;
+    1 chain and 31 chains (less than one warp of chains)."""
+    import torch
+    from bpl_next_b200 import Problem
+    from tests.test_plan import _edge_cases
+
+    for name, arr in _edge_cases():
+        p = Problem(arr)
+        for C in (1, 31):
+            theta = H.random_theta(p.D, C, seed=17, radius=1.0, dtype=np.float32)
+            for minor in (False, True):
+                t = torch.from_numpy(theta).cuda()
+                lp, grad, cc = p.logdensity(t.t().contiguous() if minor else t, chain_minor=minor)
+                torch.cuda.synchronize()
+                g = grad.t().contiguous() if minor else grad
+                _check(arr, theta.astype(np.float64), lp.cpu().numpy(), g.cpu().numpy(), cc.cpu().numpy())
+        p.close()
+
+
+def test_results_are_bit_reproducible():
+    """No atomics between warps on the gradient path: two calls on the same input give identical bits."""
+    import torch
+    from bpl_next_b200 import Problem
+
+    arr = H.from_training_data("neutral_wc", datasets.neutral_dummy_data(), epsilon=0.2)
+    p = Problem(arr)
+    t = torch.from_numpy(H.random_theta(p.D, 96, seed=3, radius=1.5, dtype=np.float32)).cuda()
+    a = [x.clone() for x in p.logdensity(t)]
+    b = [x.clone() for x in p.logdensity(t)]
+    torch.cuda.synchronize()
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)

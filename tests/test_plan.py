@@ -54,3 +54,41 @@ def test_plan_reference_fixtures():
         np.testing.assert_allclose(cc_p, cc_o, rtol=1e-9, atol=1e-12)
         scale = np.abs(g_o).max(axis=1, keepdims=True)
         np.testing.assert_allclose(g_p / scale, g_o / scale, rtol=0, atol=2e-7)
+
+
+def _edge_cases():
+    """Ragged inputs the reference's data prep can produce: one match, a team that never plays, zero weights,
+    double-digit goals, every match at a neutral venue, a single confederation."""
+    import numpy as np
+    from bpl_next_b200 import data as bdata
+    out = []
+    one = bdata.MatchArrays(model="dixon_coles", num_teams=2, home_team=np.array([1], np.uint16),
+                            away_team=np.array([0], np.uint16), home_goals=np.array([0], np.uint8),
+                            away_goals=np.array([0], np.uint8))
+    out.append(("one_match", one))
+    idle = H.small_problem("extended", seed=4, T=6, M=30, K=2)
+    idle.num_teams = 9  # teams 6..8 never play
+    idle.covariates = np.vstack([idle.covariates, np.zeros((3, 2), np.float32)])
+    out.append(("idle_teams", idle))
+    zw = H.small_problem("neutral", seed=5, T=5, M=40)
+    zw.weights = zw.weights.copy()
+    zw.weights[::3] = 0.0
+    zw.home_goals = zw.home_goals.copy()
+    zw.home_goals[1] = 12
+    out.append(("zero_weights_big_score", zw))
+    wc1 = H.small_problem("neutral_wc", seed=6, T=4, M=25, Cf=1, neutral_frac=1.0)
+    out.append(("wc_single_conf_all_neutral", wc1))
+    return out
+
+
+@pytest.mark.parametrize("name,arr", _edge_cases(), ids=[n for n, _ in _edge_cases()])
+def test_plan_edge_cases(name, arr):
+    d = H.to_oracle(arr)
+    D = om.num_params(arr.model, arr.num_teams, arr.num_covariates, arr.num_conferences, arr.num_gameweeks)
+    theta = H.random_theta(D, 4, seed=13, radius=1.0)
+    lp_o, g_o, cc_o = om.log_density_and_grad(d, theta)
+    lp_p, g_p, cc_p = H.plancheck_eval(arr, theta)
+    np.testing.assert_allclose(lp_p, lp_o, rtol=1e-7)
+    np.testing.assert_allclose(cc_p, cc_o, rtol=1e-9, atol=1e-12)
+    scale = np.abs(g_o).max(axis=1, keepdims=True)
+    np.testing.assert_allclose(g_p / scale, g_o / scale, rtol=0, atol=2e-7)
