@@ -16,6 +16,7 @@ import torch
 
 from . import data as bdata
 from . import nuts as bnuts
+from . import parallel
 from .problem import Problem, score_grid_host
 
 MAX_GOALS = bdata.MAX_GOALS
@@ -40,6 +41,38 @@ def constrain(flat: np.ndarray, layout: Dict[str, tuple]) -> Dict[str, np.ndarra
     return out
 
 
+def _run_chains(p: Problem, num_chains: int, random_state: int, num_warmup: int, num_samples: int, thin: int, kw: dict,
+                owner) -> tuple:
+    """NUTS on ``num_chains`` chains of problem ``p``.  Under ``torch.distributed`` (one process per GPU) the chains are
+    partitioned over the ranks -- no collective while sampling -- and the draws are all-gathered at the end, so every
+    rank ends with the same ``[num_chains * num_keep, D]`` array (chains concatenated like ``MCMC.get_samples()``)."""
+    rank, nranks = parallel.world()
+    c0, cn = parallel.shard(num_chains, rank, nranks)
+    if cn == 0:
+        raise ValueError(f"num_chains={num_chains} is smaller than the number of ranks ({nranks})")
+    g = torch.Generator(device="cuda").manual_seed(int(random_state))
+    theta0 = torch.rand((p.D, num_chains), generator=g, device="cuda") * 4.0 - 2.0  # numpyro init_to_uniform(radius=2)
+    theta0 = theta0[:, c0:c0 + cn].contiguous()
+
+    def potential(theta, lp, grad):
+        p.logdensity(theta, chain_minor=True, lp=lp, grad=grad)
+
+    run = bnuts.sample(potential, theta0, num_warmup=num_warmup, num_samples=num_samples, thin=thin,
+                       seed=int(random_state), chain_offset=c0, **kw)
+    owner.nuts_run = run
+    K, D, C = run.samples.shape
+    flat_dev = run.samples.permute(2, 0, 1).reshape(C * K, D).contiguous()
+    if nranks > 1:
+        import torch.distributed as dist
+        sizes = [parallel.shard(num_chains, r, nranks)[1] * K for r in range(nranks)]
+        parts = [torch.empty((n, D), dtype=flat_dev.dtype, device=flat_dev.device) for n in sizes]
+        dist.all_gather(parts, flat_dev)  # the final sample gather (NCCL)
+        flat_dev = torch.cat(parts, dim=0)
+    _, _, cc = p.logdensity(flat_dev)  # the deterministic site "corr_coef" of every draw
+    torch.cuda.synchronize()
+    return flat_dev, cc
+
+
 class _BplxPredictor:
     model = ""
 
@@ -61,19 +94,7 @@ class _BplxPredictor:
         self.teams, self._teams_dict = meta["teams"], meta["teams_dict"]
         self._meta = meta
         self.problem = p = Problem(arr)
-        g = torch.Generator(device="cuda").manual_seed(int(random_state))
-        theta0 = torch.rand((p.D, num_chains), generator=g, device="cuda") * 4.0 - 2.0  # numpyro init_to_uniform(radius=2)
-
-        def potential(theta, lp, grad):
-            p.logdensity(theta, chain_minor=True, lp=lp, grad=grad)
-
-        run = bnuts.sample(potential, theta0, num_warmup=num_warmup, num_samples=num_samples, thin=thin,
-                           seed=int(random_state), **kw)
-        self.nuts_run = run
-        K, D, C = run.samples.shape
-        flat_dev = run.samples.permute(2, 0, 1).reshape(C * K, D).contiguous()  # chains concatenated like get_samples()
-        _, _, cc = p.logdensity(flat_dev)  # the deterministic site "corr_coef" of every draw
-        torch.cuda.synchronize()
+        flat_dev, cc = _run_chains(p, num_chains, random_state, num_warmup, num_samples, thin, kw, self)
         s = constrain(flat_dev.cpu().numpy(), p.layout)
         s["corr_coef"] = cc.cpu().numpy()
         return arr, s
@@ -324,19 +345,7 @@ class DynamicNeutralDixonColesMatchPredictor(_BplxPredictor):
         self.teams, self._teams_dict = list(meta["teams"]), meta["teams_dict"]
         self.problem = p = Problem(arr)
         G, T = arr.num_gameweeks, arr.num_teams
-        g = torch.Generator(device="cuda").manual_seed(int(random_state))
-        theta0 = torch.rand((p.D, num_chains), generator=g, device="cuda") * 4.0 - 2.0
-
-        def potential(theta, lp, grad):
-            p.logdensity(theta, chain_minor=True, lp=lp, grad=grad)
-
-        run = bnuts.sample(potential, theta0, num_warmup=num_warmup, num_samples=num_samples, thin=thin,
-                           seed=int(random_state), **kw)
-        self.nuts_run = run
-        K, D, C = run.samples.shape
-        flat_dev = run.samples.permute(2, 0, 1).reshape(C * K, D).contiguous()
-        _, _, cc = p.logdensity(flat_dev)
-        torch.cuda.synchronize()
+        flat_dev, cc = _run_chains(p, num_chains, random_state, num_warmup, num_samples, thin, kw, self)
         flat = flat_dev.cpu().numpy()
         fi = np.finfo(np.float32)
         s = {}

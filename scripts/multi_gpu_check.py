@@ -51,6 +51,16 @@ between = sm2 / n - mean ** 2              # variance of the chain means
 out.update({"fit_chains_total": n, "fit_wall_s_rank": wall, "home_advantage_mean": float(mean[0].item()),
             "max_between_over_total_var": float((between / var_total).max().item()),
             "local_rhat_max": float(dg.split_rhat(run.samples).max().item())})
+# ---- fit through the predictor class: chains partitioned over the ranks, draws all-gathered at the end -------------
+from bpl_next_b200 import DixonColesMatchPredictor
+m = DixonColesMatchPredictor().fit(datasets.dummy_data(), num_warmup=200, num_samples=50, mcmc_kwargs={"num_chains": 64})
+out["predictor_fit_draws"] = int(m.attack.shape[0])
+chk = torch.tensor([float(m.attack.sum()), float(m.corr_coef.sum())], device="cuda", dtype=torch.float64)
+lo, hi = chk.clone(), chk.clone()
+dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+out["predictor_fit_ranks_agree"] = bool(torch.equal(lo, hi))
+probs = m.predict_outcome_proba("0", "1")
+out["predictor_outcome_sum"] = float(probs["home_win"][0] + probs["draw"][0] + probs["away_win"][0])
 if rank == 0:
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(out, open("gpurun_out/multi_gpu_check.json", "w"))
