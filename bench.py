@@ -289,6 +289,16 @@ def extras(args, pk):
     out.append({"workload": desc + f", {C} chains on 1 GPU", "metric": METRIC, "value": evals, "unit": UNIT,
                 "ms_per_call": ms / 3, "finite": finite, "plan": p.stats(),
                 "fp32_frac": FLOPS_PER_EVAL["neutral_wc"] * evals / 1e12 / pk["fp32_tflops"]})
+    # the few-chain ("streaming") regime on the same data: one CTA walks the whole static plan
+    st = p.stats()
+    plan_bytes = 8 * (st["entries1_padded"] + st["entries2_padded"]) + 16 * 2600
+    for Cs in (1, 32):
+        ms1, _, _, _, fin1 = time_logdensity(p, Cs, 20, 3, args.radius, args.seed + 5, use_graph=True, target_s=0.3)
+        out.append({"workload": desc + f", {Cs} chain(s): few-chain regime, one CTA", "metric": METRIC,
+                    "value": Cs * arr.num_matches * 20 / (ms1 * 1e-3), "unit": UNIT, "ms_per_call": ms1 / 20, "finite": fin1,
+                    "plan_stream_gbs": plan_bytes / (ms1 / 20 * 1e-3) / 1e9,
+                    "note": "latency-bound by design: the plan (0.8 MB) is read once per CTA through the TMA ring; a "
+                            "match-parallel streaming kernel (K1s) only pays above ~1e6 matches and is not built"})
     p.close()
     del p
     torch.cuda.empty_cache()
