@@ -1,5 +1,6 @@
 // api.cu -- the extern "C" surface declared in include/bplx.h.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -71,6 +72,24 @@ static int enqueue(const bplx_problem* p, int C, int layout, int ld, const float
   kp.grad = grad;
   kp.corr_coef = corr_coef;
   kp.scratch = static_cast<float*>(ws);
+  // few chains: several CTAs (one cluster) share a group of 32 chains, as many as the device holds at once
+  int si = 0;
+  const int groups = (C + kChains - 1) / kChains;
+  for (int i = kNumSplits - 1; i >= 1; i--)
+    if (p->s1[i] && groups <= p->max_clusters[i]) {
+      si = i;
+      break;
+    }
+  if (const char* e = getenv("BPLX_SPLIT")) {  // testing / tuning: force 1, 2, 4 or 8 CTAs per group
+    const int want = atoi(e);
+    for (int i = 0; i < kNumSplits; i++)
+      if ((1 << i) == want && p->s1[i] && (i == 0 || p->max_clusters[i] > 0)) si = i;
+  }
+  kp.split = 1 << si;
+  kp.stream1 = p->s1[si];
+  kp.stream2 = p->s2[si];
+  kp.warp_b1 = p->wb1[si];
+  kp.warp_b2 = p->wb2[si];
   return kp.model == BPLX_DYNAMIC ? launch_logdensity_dynamic(kp, stream) : launch_logdensity(kp, stream);
 }
 
@@ -105,10 +124,22 @@ int bplx_problem_create(const bplx_problem_desc* desc, bplx_problem** out) {
   KernelParams& kp = p->kp;
 #define UP(vec, ptr)                                 \
   if ((rc = upload(p, hp.vec, &(ptr))) != BPLX_OK) return fail(rc)
-  UP(stream1, kp.stream1);
-  UP(stream2, kp.stream2);
-  UP(warp_b1, kp.warp_b1);
-  UP(warp_b2, kp.warp_b2);
+  UP(stream1, p->s1[0]);
+  UP(stream2, p->s2[0]);
+  UP(warp_b1, p->wb1[0]);
+  UP(warp_b2, p->wb2[0]);
+  for (int i = 1; i < kNumSplits; i++) {
+    if (hp.more[i - 1].stream1.empty()) continue;  // (DYNAMIC has no split plans)
+    UP(more[i - 1].stream1, p->s1[i]);
+    UP(more[i - 1].stream2, p->s2[i]);
+    UP(more[i - 1].warp_b1, p->wb1[i]);
+    UP(more[i - 1].warp_b2, p->wb2[i]);
+  }
+  kp.stream1 = p->s1[0];
+  kp.stream2 = p->s2[0];
+  kp.warp_b1 = p->wb1[0];
+  kp.warp_b2 = p->wb2[0];
+  kp.split = 1;
   UP(team_vptr, kp.team_vptr);
   UP(team_flags, kp.team_flags);
   UP(v_team, kp.v_team);
@@ -124,6 +155,9 @@ int bplx_problem_create(const bplx_problem_desc* desc, bplx_problem** out) {
 #undef UP
   rc = kp.model == BPLX_DYNAMIC ? logdensity_dynamic_set_attributes() : logdensity_set_attributes(kp);
   if (rc != BPLX_OK) return fail(rc);
+  p->max_clusters[0] = 1 << 30;
+  if (kp.model != BPLX_DYNAMIC)
+    for (int i = 1; i < kNumSplits; i++) p->max_clusters[i] = p->s1[i] ? logdensity_max_clusters(kp, 1 << i) : 0;
   p->stats[0] = desc->num_matches;
   p->stats[1] = hp.n1;
   p->stats[2] = hp.n1_padded;

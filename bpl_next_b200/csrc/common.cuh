@@ -55,6 +55,49 @@ __device__ __forceinline__ uint4 lds128u(uint32_t addr) {
   return v;
 }
 
+// distributed shared memory (thread-block clusters): 32-bit shared::cluster addresses ----------------------
+// (generic-pointer atomics on a mapped address compile to a LOCAL shared-memory CAS loop -- address the remote CTA
+//  explicitly.  A launch without a cluster attribute is an implicit cluster of one: rank 0 is the CTA itself.)
+__device__ __forceinline__ uint32_t cluster_map(uint32_t cta_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void dsm_st_f32(uint32_t a, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void dsm_st_u32(uint32_t a, uint32_t v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ float dsm_ld_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t dsm_ld_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long dsm_ld_u64(uint32_t a) {
+  unsigned long long v;
+  asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void dsm_st_u64(uint32_t a, unsigned long long v) {
+  asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
+}
+// 32-bit max is a native shared-memory atomic for local and remote requesters alike (the 64-bit one is a local CAS loop
+// on one side and a remote atomic on the other, which do not exclude each other: measured lost updates)
+__device__ __forceinline__ void dsm_atom_min_u32(uint32_t a, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared::cluster.min.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void dsm_atom_max_u32(uint32_t a, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared::cluster.max.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+}
+
 // mbarrier (shared::cta) -------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

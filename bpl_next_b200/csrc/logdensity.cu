@@ -20,8 +20,17 @@
 //   epilogue  cross-warp reduction, hyper priors + Jacobians, covariate coefficients; lp, corr_coef.
 // A raw slot is written by the one thread that owns (team, chain) in a phase and red.add'ed by one
 // thread per later stage, in program order: the result is deterministic.
+//
+// Few chains (fewer groups of 32 than SMs): kp.split = 2, 4 or 8 CTAs form a thread-block cluster on ONE group of
+// chains.  Every CTA builds all tables, the list streams are dealt over split * W virtual warps, the CTA-wide barriers
+// become cluster barriers and the cross-warp reductions (maxima, arg-max search, d/d corr_coef, hyper sums) land in the
+// shared memory of cluster rank 0 through distributed shared memory.
+#include <cooperative_groups.h>
+
 #include "k1_common.cuh"
 #include "problem.h"
+
+namespace cg = cooperative_groups;
 
 namespace bplx {
 
@@ -30,7 +39,15 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
   extern __shared__ __align__(1024) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = kp.nwarps;
   const ThetaOffsets& o = kp.off;
-  const int chain_raw = blockIdx.x * kChains + lane;
+  const int S = kp.split;  // CTAs of the cluster that shares this group of chains (1: no cluster)
+  const int crank = S > 1 ? (int)cg::this_cluster().block_rank() : 0;
+  const int group = (int)blockIdx.x / S;
+  const int vwarp = crank * W + warp, VW = S * W;  // virtual warp: owner of teams / streams across the cluster
+  auto sync_all = [&]() {
+    if (S > 1) cg::this_cluster().sync();
+    else __syncthreads();
+  };
+  const int chain_raw = group * kChains + lane;
   const int chain = min(chain_raw, kp.C - 1);
   Lane ln;
   ln.th = kp.theta + (size_t)chain * (size_t)kp.sc;
@@ -39,28 +56,33 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
   ln.sd = kp.sd;
   ln.active = chain_raw < kp.C;
   const uint32_t tab = smem_u32(smem) + lane * 8;  // + row byte offset
-  unsigned long long* red_best = reinterpret_cast<unsigned long long*>(smem + kp.smem_red);  // [3][32]
-  uint32_t* red_found = reinterpret_cast<uint32_t*>(smem + kp.smem_red + 768);               // [2][32]
-  uint32_t* red_info = reinterpret_cast<uint32_t*>(smem + kp.smem_red + 1024);               // [2][32]
+  // one CTA: [3][32] u64 (value bits << 32 | piece offset).  Cluster: [3][32] u32 value bits, then [3][32] u32 piece offsets
+  unsigned long long* red_best = reinterpret_cast<unsigned long long*>(smem + kp.smem_red);
+  unsigned long long* red_found = reinterpret_cast<unsigned long long*>(smem + kp.smem_red + 768);  // [2][32] entry | info << 32
   float* red_hyp = reinterpret_cast<float*>(smem + kp.smem_red + 1280);                       // [12][32]
   float* red_gc = reinterpret_cast<float*>(smem + kp.smem_red + 1280 + 12 * 128);             // [W][32]
+  // the cluster's reductions live in rank 0's shared memory (shared::cluster addresses; rank 0 = this CTA when S == 1)
+  const uint32_t a_best = cluster_map(smem_u32(red_best), 0), a_found = cluster_map(smem_u32(red_found), 0);
+  const uint32_t a_cl = cluster_map(smem_u32(smem) + kp.smem_red_cl, 0);      // [kMaxSplit][32] f32
+  const uint32_t a_partcl = cluster_map(smem_u32(smem) + kp.epi_cl, 0);       // [kMaxSplit][kPartRows][32] f32
+  const uint32_t a_teamrows = cluster_map(smem_u32(smem) + kp.epi_team, 0);   // [T][2][32] f32
   constexpr uint32_t ESZ = CLIP ? (uint32_t)sizeof(EntryClip) : (uint32_t)sizeof(Entry);
   Ring ring;
   ring.init(smem_u32(smem) + kp.smem_ring + warp * (kStages * kp.stage_bytes),
             smem_u32(smem) + kp.smem_bar + warp * (kStages * 8), kp.stage_bytes, lane);
-  const uint32_t b1_0 = __ldg(kp.warp_b1 + warp), b1_1 = __ldg(kp.warp_b1 + warp + 1);
+  const uint32_t b1_0 = __ldg(kp.warp_b1 + vwarp), b1_1 = __ldg(kp.warp_b1 + vwarp + 1);
   ring.begin(kp.stream1 + b1_0, b1_1 - b1_0);  // phase-1 pieces start streaming in while the prologue runs
   {  // pull this CTA's slice of theta into L2 in one go: every later read of it is a hit
     const int nthr = W * 32;
     if (kp.sd == 1) {  // chain-major: 32 rows of D floats
       const int per = (kp.D + 31) / 32;
       for (int i = threadIdx.x; i < 32 * per; i += nthr) {
-        const int c = min(blockIdx.x * kChains + i / per, kp.C - 1);
+        const int c = min(group * kChains + i / per, kp.C - 1);
         asm volatile("prefetch.global.L2 [%0];" ::"l"(kp.theta + (size_t)c * (size_t)kp.sc + (size_t)(i % per) * 32));
       }
     } else {
       for (int d = threadIdx.x; d < kp.D; d += nthr)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(kp.theta + (size_t)d * (size_t)kp.sd + (size_t)blockIdx.x * kChains));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(kp.theta + (size_t)d * (size_t)kp.sd + (size_t)group * kChains));
     }
   }
 
@@ -77,8 +99,16 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
       sts64(tab + kp.tabQ1 + zr, 0.0f, 0.0f);
     }
     if (kp.has0) sts64(tab + kp.tabP0 + zr, 0.0f, 0.0f);
-    red_best[lane] = red_best[32 + lane] = red_best[64 + lane] = 0ull;
-    red_found[lane] = red_found[32 + lane] = 0xffffffffu;
+    if (crank == 0) {
+      if (S == 1) {
+        red_best[lane] = red_best[32 + lane] = red_best[64 + lane] = 0ull;
+      } else {
+        uint32_t* rb = reinterpret_cast<uint32_t*>(red_best);
+        rb[lane] = rb[32 + lane] = rb[64 + lane] = 0u;                         // values
+        rb[96 + lane] = rb[128 + lane] = rb[160 + lane] = 0xffffffffu;         // piece offsets (atomicMin)
+      }
+      red_found[lane] = red_found[32 + lane] = ~0ull;
+    }
   }
   const float r = sigmoid_clipped(ln.ld(o.raw));
   {
@@ -101,7 +131,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
 #pragma unroll
       for (int i = 0; i < 4; i++)
         if (i < ndec) x[i] = fmaf(hy.sig[i], ln.ld(o.dec[i] + t), hy.mu[i]);
-      if (!(__ldg(kp.team_flags + t) & 1) && ln.active) {  // team without matches: no list will write its slots
+      if (!(__ldg(kp.team_flags + t) & 1) && ln.active && crank == 0) {  // team without matches: no list will write its slots
         *ln.g(o.za + t) = 0.0f;
         *ln.g(o.zd + t) = 0.0f;
 #pragma unroll
@@ -124,14 +154,14 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
           sts64(tab + kp.tabQ1 + r, expf(ex[eBa1]), expf(ex[eAa1]));
         }
         if (kp.has0) sts64(tab + kp.tabP0 + r, expf(ex[eA0]), expf(ex[eB0]));
-        if (!CLIP) {  // static sum of w * y * log(lambda): linear in the exponents
+        if (!CLIP && crank == 0) {  // static sum of w * y * log(lambda): linear in the exponents
 #pragma unroll
           for (int e = 0; e < 6; e++) lp_acc = fmaf(__ldg(kp.yexp + (size_t)v * 6 + e), ex[e], lp_acc);
         }
       }
     }
   }
-  __syncthreads();
+  sync_all();
 
   // ---- phase 1 ----------------------------------------------------------------------------------
   float best[3] = {0.0f, 0.0f, 0.0f};
@@ -231,20 +261,39 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
       ring.release(k);
     }
   }
-  const uint32_t b2_0 = __ldg(kp.warp_b2 + warp), b2_1 = __ldg(kp.warp_b2 + warp + 1);
+  const uint32_t b2_0 = __ldg(kp.warp_b2 + vwarp), b2_1 = __ldg(kp.warp_b2 + vwarp + 1);
   ring.begin(kp.stream2 + b2_0, b2_1 - b2_0);  // tau pieces start streaming in during the bounds step
 
   // ---- bounds (bpl/_util.py:17-31) ------------------------------------------------------------------
+  // the maxima and the piece each came from.  One CTA: a 64-bit atomicMax on (value bits | piece offset).  A cluster:
+  // 32-bit atomics only (value first, then the owners of the maximum agree on a piece) -- the 64-bit max is a CAS loop
+  // for the local CTA and a remote atomic for the others, and the two do not exclude each other (measured lost updates).
+  if (S == 1) {
 #pragma unroll
-  for (int q = 0; q < 3; q++)
-    if (best[q] > 0.0f)
-      atomicMax(red_best + q * 32 + lane, ((unsigned long long)__float_as_uint(best[q]) << 32) | besth[q]);
-  __syncthreads();
+    for (int q = 0; q < 3; q++)
+      if (best[q] > 0.0f)
+        atomicMax(red_best + q * 32 + lane, ((unsigned long long)__float_as_uint(best[q]) << 32) | besth[q]);
+    __syncthreads();
 #pragma unroll
-  for (int q = 0; q < 3; q++) {
-    const unsigned long long b = red_best[q * 32 + lane];
-    best[q] = __uint_as_float((uint32_t)(b >> 32));
-    besth[q] = (uint32_t)b;
+    for (int q = 0; q < 3; q++) {
+      const unsigned long long bq = red_best[q * 32 + lane];
+      best[q] = __uint_as_float((uint32_t)(bq >> 32));
+      besth[q] = (uint32_t)bq;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 3; q++)
+      if (best[q] > 0.0f) dsm_atom_max_u32(a_best + (uint32_t)(q * 32 + lane) * 4u, __float_as_uint(best[q]));
+    cg::this_cluster().sync();
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      const float gq = __uint_as_float(dsm_ld_u32(a_best + (uint32_t)(q * 32 + lane) * 4u));
+      if (best[q] == gq && gq > 0.0f) dsm_atom_min_u32(a_best + (uint32_t)((3 + q) * 32 + lane) * 4u, besth[q]);
+      best[q] = gq;
+    }
+    cg::this_cluster().sync();
+#pragma unroll
+    for (int q = 0; q < 3; q++) besth[q] = dsm_ld_u32(a_best + (uint32_t)((3 + q) * 32 + lane) * 4u);
   }
   const float Lam = fmaxf(best[0], best[1]);
   const int qlam = best[0] >= best[1] ? 0 : 1;
@@ -252,22 +301,22 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
   const float UB = fminf(1.0f / best[2], 1.0f);
   const float cc = fmaf(r, UB - LB, LB);
 
-  // ---- arg-max search: warp w looks at entries w, w+W, ... of each chain's two arg-max pieces -----------
+  // ---- arg-max search: virtual warp w looks at entries w, w+VW, ... of each chain's two arg-max pieces -----------
 #pragma unroll 1
   for (int which = 0; which < 2; which++) {
-    const bool need = which == 0 || best[2] > 1.0f;  // UB = 1: no dependence on the rates
-    const uint32_t hoff = which == 0 ? (qlam == 0 ? besth[0] : besth[1]) : besth[2];
+    const bool need = (which == 0 || best[2] > 1.0f) && best[which == 0 ? qlam : 2] > 0.0f;  // UB = 1: no dependence on the rates
+    const uint32_t hoff = need ? (which == 0 ? (qlam == 0 ? besth[0] : besth[1]) : besth[2]) : b1_0;
     const float target = which == 0 ? Lam : best[2];
     const int q = which == 0 ? qlam : 2;
     const Hdr L = unpack_hdr(__ldg(reinterpret_cast<const uint4*>(kp.stream1 + hoff)));
     const uint32_t n = need ? L.n0 : 0u;
-    float2 own = lds64(tab + L.own_off);
+    float2 own = lds64(tab + (need ? L.own_off : 0u));
     if (L.kind >= kH0) { const float s = own.x; own.x = own.y; own.y = s; }
     const unsigned char* ent = kp.stream1 + hoff + 16;
     const uint32_t nmax = __reduce_max_sync(kFull, n);
     uint32_t found = 0xffffffffu, info = 0u;
 #pragma unroll 4
-    for (uint32_t i = warp; i < nmax; i += W) {
+    for (uint32_t i = vwarp; i < nmax; i += VW) {
       if (i < n) {
         const uint32_t off = __ldg(reinterpret_cast<const uint32_t*>(ent + (size_t)i * ESZ));
         const float2 ea = lds64(tab + off);
@@ -279,17 +328,17 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
         } else {
           val = q == 0 ? X : (q == 1 ? Y : (own.x * own.y) * (ea.x * ea.y));
         }
-        if (val == target && ((i << 24) | off) < found) {
+        if (val == target && found == 0xffffffffu) {
           found = (i << 24) | off;
           // own vteam | kind | "X not clipped" | "Y not clipped"
           info = L.vteam | (L.kind << 16) | ((!CLIP || X < 15.0f) ? 1u << 18 : 0u) | ((!CLIP || Y < 15.0f) ? 1u << 19 : 0u);
         }
       }
     }
-    if (found != 0xffffffffu) {
-      atomicMin(red_found + which * 32 + lane, found);
-      red_info[which * 32 + lane] = info;  // several finders only under exact ties: any of them will do
-    }
+    // one 64-bit store keeps (entry, piece info) together; several finders only under exact ties inside the piece
+    // (then any of them will do: clipped ties carry no gradient)
+    if (found != 0xffffffffu)
+      dsm_st_u64(a_found + (uint32_t)(which * 32 + lane) * 8u, (unsigned long long)found | ((unsigned long long)info << 32));
   }
 
   // ---- phase 2: tau terms (bpl/_util.py:54-91) -----------------------------------------------------
@@ -385,13 +434,20 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
     }
   }
   red_gc[warp * 32 + lane] = gc;
-  __syncthreads();  // tables are dead from here on; raw slots hold both phases
+  __syncthreads();
   gc = 0.0f;
   for (int w = 0; w < W; w++) gc += red_gc[w * 32 + lane];
+  if (S > 1) {  // the CTAs' sums meet in rank 0
+    if (warp == 0) dsm_st_f32(a_cl + (uint32_t)(crank * 32 + lane) * 4u, gc);
+    cg::this_cluster().sync();
+    gc = 0.0f;
+    for (int q = 0; q < S; q++) gc += dsm_ld_f32(a_cl + (uint32_t)(q * 32 + lane) * 4u);
+  }
+  // tables are dead from here on; raw slots hold both phases
   {  // the 1-1 matches: tau = 1 - c for all of them
     const float t11 = fmaxf(1.0f - cc, 0.0f);
     gc -= kp.w11 / t11;
-    if (warp == 0 && kp.w11 != 0.0f) lp_acc = fmaf(kp.w11, logf(t11), lp_acc);
+    if (vwarp == 0 && kp.w11 != 0.0f) lp_acc = fmaf(kp.w11, logf(t11), lp_acc);
   }
 
   // ---- arg-max fix-up: every warp works out the two matches of its chain and folds
@@ -401,12 +457,13 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
   fx.confs = 0u;
 #pragma unroll
   for (int which = 0; which < 2; which++) {
-    const uint32_t packed = red_found[which * 32 + lane];
+    const unsigned long long fi = dsm_ld_u64(a_found + (uint32_t)(which * 32 + lane) * 8u);
+    const uint32_t packed = (uint32_t)fi;
     fx.teams[which] = 0xffffffffu;
     fx.vts[which] = 0u;
     fx.vx[which] = fx.vy[which] = 0.0f;
     if (packed != 0xffffffffu) {  // else: UB = 1 (or nothing matched: cannot happen, same arithmetic as phase 1)
-      const uint32_t info = red_info[which * 32 + lane];
+      const uint32_t info = (uint32_t)(fi >> 32);
       const uint32_t f_off = packed & 0xffffffu;
       const bool h1 = ((info >> 16) & 3u) == kH1;
       const uint32_t own_v = info & 0xffffu;
@@ -445,8 +502,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
     hy.mu_d = red_hyp[0 * 32 + lane]; hy.sig_a = red_hyp[1 * 32 + lane]; hy.sig_d = red_hyp[2 * 32 + lane];
 #pragma unroll
     for (int i = 0; i < 4; i++) { hy.mu[i] = red_hyp[(3 + i) * 32 + lane]; hy.sig[i] = red_hyp[(7 + i) * 32 + lane]; }
-    float* team_rows = reinterpret_cast<float*>(smem + kp.epi_team);
-    for (int t = warp; t < kp.T; t += W) {
+
+    for (int t = vwarp; t < kp.T; t += VW) {
       const float za = ln.ld(o.za + t), zd = ln.ld(o.zd + t);
       const float4 ys = __ldg(reinterpret_cast<const float4*>(kp.yteam + (size_t)t * 8));
       const float2 ys2 = __ldg(reinterpret_cast<const float2*>(kp.yteam + (size_t)t * 8 + 4));
@@ -497,14 +554,14 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
         }
       }
       if (kp.K > 0) {  // rows for the covariate-coefficient pass
-        team_rows[(size_t)t * 64 + lane] = ra;
-        team_rows[(size_t)t * 64 + 32 + lane] = rd;
+        dsm_st_f32(a_teamrows + (uint32_t)(t * 64 + lane) * 4u, ra);  // (rank 0's rows)
+        dsm_st_f32(a_teamrows + (uint32_t)(t * 64 + 32 + lane) * 4u, rd);
       }
     }
     if (dc) a_mu[0] += hacc;
   }
   // confederation strengths: N(0,1) prior + sum over the virtual teams of the confederation
-  for (int k = warp; k < kp.Cf; k += W) {
+  for (int k = vwarp; k < kp.Cf; k += VW) {
     const float cf = ln.ld(o.conf + k);
     float s = __ldg(kp.yconf + k) - cf;
     lp_acc -= 0.5f * cf * cf;
@@ -527,10 +584,23 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
     p[12 * 32] = a_rho;
   }
   __syncthreads();
+  if (S > 1) {  // per-CTA sums of the 13 rows go to rank 0; the other CTAs are done
+    for (int row = warp; row < kAccRows; row += W) {
+      float s = 0.0f;
+      for (int w = 0; w < W; w++) s += part[((size_t)w * kPartRows + row) * 32 + lane];
+      dsm_st_f32(a_partcl + (uint32_t)((crank * kPartRows + row) * 32 + lane) * 4u, s);
+    }
+    cg::this_cluster().sync();
+    if (crank != 0) return;
+  }
   // the epilogue items are dealt round-robin to the warps: scalar hyper sites, u, corr_coef_raw, coefficients
   auto total = [&](int row) {
     float s = 0.0f;
-    for (int w = 0; w < W; w++) s += part[((size_t)w * kPartRows + row) * 32 + lane];
+    if (S > 1) {
+      for (int q = 0; q < S; q++) s += dsm_ld_f32(a_partcl + (uint32_t)((q * kPartRows + row) * 32 + lane) * 4u);
+    } else {
+      for (int w = 0; w < W; w++) s += part[((size_t)w * kPartRows + row) * 32 + lane];
+    }
     return s;
   };
   float lp = 0.0f;
@@ -591,11 +661,51 @@ static int launch_t(const KernelParams& kp, cudaStream_t stream, bool set_attr) 
     BPLX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return BPLX_OK;
   }
-  const int grid = (kp.C + kChains - 1) / kChains;
-  fn<<<grid, kp.nwarps * 32, kp.smem_total, stream>>>(kp);
+  const int groups = (kp.C + kChains - 1) / kChains;
+  if (kp.split > 1) {  // one thread-block cluster per group of chains
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(groups * kp.split));
+    cfg.blockDim = dim3((unsigned)(kp.nwarps * 32));
+    cfg.dynamicSmemBytes = kp.smem_total;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)kp.split;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    BPLX_CUDA(cudaLaunchKernelEx(&cfg, fn, kp));
+  } else {
+    fn<<<groups, kp.nwarps * 32, kp.smem_total, stream>>>(kp);
+  }
   BPLX_CUDA(cudaGetLastError());
   note_launch(1);
   return BPLX_OK;
+}
+
+template <bool CLIP>
+static int max_clusters_t(const KernelParams& kp, int split) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)split);
+  cfg.blockDim = dim3((unsigned)(kp.nwarps * 32));
+  cfg.dynamicSmemBytes = kp.smem_total;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)split;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, &logdensity_kernel<CLIP>, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+int logdensity_max_clusters(const KernelParams& kp, int split) {
+  return kp.clip ? max_clusters_t<true>(kp, split) : max_clusters_t<false>(kp, split);
 }
 
 int logdensity_set_attributes(const KernelParams& kp) {

@@ -379,10 +379,10 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err, int 
   const std::vector<double> cost2 = team_costs(raw2, 12.0, 60.0, 30.0);
   // shared memory left for the rings decides how many warps / which stage size fit
   auto smem_need = [&](int W, uint32_t stage) {
-    const uint32_t epi = (K > 0 ? (uint32_t)T * kRowBytes : 0u) + (uint32_t)W * kPartRows * 128u;
+    const uint32_t epi = (K > 0 ? (uint32_t)T * kRowBytes : 0u) + (uint32_t)(W + kMaxSplit) * kPartRows * 128u;
     const uint32_t tabb = (std::max(table_bytes, epi) + 127u) / 128u * 128u;
     return tabb + (uint32_t)W * kStages * stage + 128u + (uint32_t)W * kStages * 8u + 3u * 256u + 2u * 128u + 2u * 128u +
-           12u * 128u + (uint32_t)W * 128u;
+           12u * 128u + (uint32_t)(W + kMaxSplit) * 128u;
   };
   const uint32_t kSmemMax = 227u * 1024u;
   int W = 0;
@@ -411,8 +411,6 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err, int 
   }
   kp.nwarps = W;
   kp.stage_bytes = stage;
-  assign(cost1, W, &w1);
-  assign(cost2, W, &w2);
 
   // ---- emit the streams ---------------------------------------------------------------------------
   const uint32_t zero_row = (uint32_t)V * kRowBytes;
@@ -420,14 +418,20 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err, int 
     const unsigned char* b = static_cast<const unsigned char*>(p);
     s->insert(s->end(), b, b + n);
   };
+  // one set of streams per split: Wtot = W * split virtual warps (virtual warp = cluster rank * W + warp)
+  auto emit = [&](int Wtot, std::vector<unsigned char>* s1, std::vector<unsigned char>* s2, std::vector<uint32_t>* wb1,
+                  std::vector<uint32_t>* wb2) {
+  const int W = Wtot;  // (shadows the per-CTA warp count inside the emitter)
+  assign(cost1, W, &w1);
+  assign(cost2, W, &w2);
   P.n1 = P.n2 = P.n1_padded = P.n2_padded = P.nlists1 = P.nlists2 = 0;
-  P.warp_b1.assign(W + 1, 0);
-  P.warp_b2.assign(W + 1, 0);
+  wb1->assign(W + 1, 0);
+  wb2->assign(W + 1, 0);
   for (int phase = 1; phase <= 2; phase++) {
     const auto& raw = phase == 1 ? raw1 : raw2;
     const auto& by_warp = phase == 1 ? w1 : w2;
-    std::vector<unsigned char>& S = phase == 1 ? P.stream1 : P.stream2;
-    std::vector<uint32_t>& wb = phase == 1 ? P.warp_b1 : P.warp_b2;
+    std::vector<unsigned char>& S = phase == 1 ? *s1 : *s2;
+    std::vector<uint32_t>& wb = phase == 1 ? *wb1 : *wb2;
     const size_t esz = (phase == 1 && kp.clip) ? sizeof(EntryClip) : sizeof(Entry);
     const size_t gran = 16;  // bytes of entries a piece grows by
     const size_t min_piece = sizeof(ListHdr) + gran;
@@ -521,17 +525,24 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err, int 
     }
     if (S.empty()) S.resize(16, 0);  // never upload an empty buffer
   }
+  };
+  for (int i = kNumSplits - 1; i >= 1; i--)
+    emit(W << i, &P.more[i - 1].stream1, &P.more[i - 1].stream2, &P.more[i - 1].warp_b1, &P.more[i - 1].warp_b2);
+  emit(W, &P.stream1, &P.stream2, &P.warp_b1, &P.warp_b2);  // last: the statistics describe split 1
 
   // ---- shared-memory carve-up --------------------------------------------------------------------
   kp.epi_team = 0;
   kp.epi_part = K > 0 ? (uint32_t)T * kRowBytes : 0u;
-  const uint32_t epi = kp.epi_part + (uint32_t)W * kPartRows * 128u;
+  kp.epi_cl = kp.epi_part + (uint32_t)W * kPartRows * 128u;
+  const uint32_t epi = kp.epi_cl + (uint32_t)kMaxSplit * kPartRows * 128u;
   kp.tab_bytes = (std::max(table_bytes, epi) + 127u) / 128u * 128u;
   kp.smem_ring = kp.tab_bytes;
   kp.smem_bar = kp.smem_ring + (uint32_t)W * kStages * stage;
   kp.smem_red = (kp.smem_bar + (uint32_t)W * kStages * 8u + 127u) / 128u * 128u;
   // red area: best[3][32] u64 | found[2][32] u32 | info[2][32] u32 | hyper values [12][32] f32 | gc / lp parts [W][32] f32
-  kp.smem_total = kp.smem_red + 3u * 256u + 2u * 128u + 2u * 128u + 12u * 128u + (uint32_t)W * 128u;
+  //           | cluster gc partials [kMaxSplit][32] f32
+  kp.smem_red_cl = kp.smem_red + 3u * 256u + 2u * 128u + 2u * 128u + 12u * 128u + (uint32_t)W * 128u;
+  kp.smem_total = kp.smem_red_cl + (uint32_t)kMaxSplit * 128u;
   if (kp.smem_total > kSmemMax)
     FAIL(BPLX_E_UNSUPPORTED, "problem needs %u bytes of shared memory per CTA (max %u): too many (team, confederation) pairs (%d)",
          kp.smem_total, kSmemMax, V);

@@ -50,6 +50,8 @@ constexpr int kMaxWarpsDyn = 16;  // DYNAMIC kernel: 128 registers per thread
 constexpr int kStages = 2;        // ring depth per warp (stage size: KernelParams::stage_bytes, 512 or 1024)
 constexpr int kAccRows = 13;      // hyper accumulators: lp, mu_d, ls_a, ls_d, mu[4], ls[4], rho
 constexpr int kPartRows = 16;     // rows per warp in the final cross-warp reduction
+constexpr int kMaxSplit = 8;      // CTAs (one thread-block cluster) that can share one group of 32 chains
+constexpr int kNumSplits = 4;     // plans are built for 1, 2, 4 and 8 CTAs per chain group
 
 enum Kind : uint8_t { kH1 = 0, kA1 = 1, kH0 = 2, kA0 = 3 };
 enum Exponent : int { eAh1 = 0, eBh1 = 1, eBa1 = 2, eAa1 = 3, eA0 = 4, eB0 = 5 };
@@ -121,6 +123,8 @@ struct KernelParams {
   uint32_t min_piece1, min_piece2;  // a stage tail shorter than this holds no piece (phase 1 / phase 2)
   uint32_t smem_ring, smem_bar, smem_red, smem_total;  // carve-up (bytes)
   uint32_t epi_team, epi_part;   // epilogue reuse of the table area: team rows, per-warp partials
+  uint32_t epi_cl;               // ... and the per-CTA partials of a cluster ([kMaxSplit][kPartRows][32], on rank 0)
+  uint32_t smem_red_cl;          // [kMaxSplit][32] d/d corr_coef partials of a cluster (rank 0)
   ThetaOffsets off;
   const unsigned char* stream1;  // phase-1 streams of all warps
   const unsigned char* stream2;  // phase-2 streams
@@ -144,6 +148,7 @@ struct KernelParams {
   float const_term;  // -sum w (lgamma(yh+1) + lgamma(ya+1)) + every normalising constant of the priors
   // call arguments
   int C;
+  int split;   // CTAs per chain group for this call (cluster size; the streams below belong to this split)
   int sd, sc;  // element strides of theta/grad: index = d*sd + c*sc (api.cu checks that it fits 31 bits)
   const float* theta;
   float* lp;
@@ -154,10 +159,16 @@ struct KernelParams {
   int Cpad;
 };
 
-struct HostPlan {
-  KernelParams kp{};  // scalar fields filled; pointers null
+struct SplitStreams {  // the two phases' streams for nwarps * split virtual warps
   std::vector<unsigned char> stream1, stream2;
   std::vector<uint32_t> warp_b1, warp_b2;
+};
+
+struct HostPlan {
+  KernelParams kp{};  // scalar fields filled; pointers null
+  std::vector<unsigned char> stream1, stream2;  // split 1
+  std::vector<uint32_t> warp_b1, warp_b2;
+  SplitStreams more[kNumSplits - 1];            // splits 2, 4, 8 (empty for DYNAMIC)
   std::vector<int32_t> team_vptr, conf_vptr, conf_vlist;
   std::vector<uint8_t> team_flags;
   std::vector<uint16_t> v_team;

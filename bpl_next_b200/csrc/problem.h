@@ -11,6 +11,12 @@ struct bplx_problem {
   int device = 0;
   bplx::KernelParams kp{};  // static part filled at create; call arguments filled per launch
   std::string layout;
+  // streams per split (1, 2, 4, 8 CTAs per chain group) and how many clusters of each size the device can hold at once
+  const unsigned char* s1[bplx::kNumSplits] = {};
+  const unsigned char* s2[bplx::kNumSplits] = {};
+  const uint32_t* wb1[bplx::kNumSplits] = {};
+  const uint32_t* wb2[bplx::kNumSplits] = {};
+  int max_clusters[bplx::kNumSplits] = {0, 0, 0, 0};
   std::vector<void*> dev_allocs;
   // host-variant staging (lazily grown, guarded by mu)
   std::mutex mu;
@@ -29,6 +35,7 @@ struct bplx_problem {
 namespace bplx {
 int launch_logdensity(const KernelParams& kp, cudaStream_t stream);
 int logdensity_set_attributes(const KernelParams& kp);
+int logdensity_max_clusters(const KernelParams& kp, int split);  // co-resident clusters of `split` CTAs, 0 if unsupported
 int launch_logdensity_dynamic(const KernelParams& kp, cudaStream_t stream);
 int logdensity_dynamic_set_attributes();
 }  // namespace bplx

@@ -340,14 +340,31 @@ int eval_dynamic(const HostPlan& P, const double* theta, double* lp_out, double*
 }
 }  // namespace
 
+extern "C" int bplx_plancheck_eval2(const bplx_problem_desc* desc, int split_idx, const double* theta, double* lp_out,
+                                    double* grad, double* corr_out, char* errbuf, int errlen);
 extern "C" int bplx_plancheck_eval(const bplx_problem_desc* desc, const double* theta, double* lp_out, double* grad,
                                    double* corr_out, char* errbuf, int errlen) {
+  return bplx_plancheck_eval2(desc, 0, theta, lp_out, grad, corr_out, errbuf, errlen);
+}
+
+// split_idx i walks the streams built for 2^i CTAs per chain group (nwarps << i virtual warps)
+extern "C" int bplx_plancheck_eval2(const bplx_problem_desc* desc, int split_idx, const double* theta, double* lp_out,
+                                    double* grad, double* corr_out, char* errbuf, int errlen) {
   HostPlan P;
   std::string err;
   int rc = build_plan(*desc, &P, &err);
   if (rc != BPLX_OK) {
     if (errbuf && errlen > 0) snprintf(errbuf, errlen, "%s", err.c_str());
     return rc;
+  }
+  if (split_idx < 0 || split_idx >= kNumSplits) return -140;
+  if (split_idx > 0) {  // walk the split's streams in place of split 1
+    if (P.kp.model == BPLX_DYNAMIC) return -141;
+    P.stream1 = P.more[split_idx - 1].stream1;
+    P.stream2 = P.more[split_idx - 1].stream2;
+    P.warp_b1 = P.more[split_idx - 1].warp_b1;
+    P.warp_b2 = P.more[split_idx - 1].warp_b2;
+    P.kp.nwarps <<= split_idx;
   }
   const KernelParams& kp = P.kp;
   if (kp.model == BPLX_DYNAMIC) return eval_dynamic(P, theta, lp_out, grad, corr_out);

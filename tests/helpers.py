@@ -94,12 +94,15 @@ def plancheck_lib():
         lib.bplx_plancheck_eval.argtypes = [C.POINTER(_abi.ProblemDesc), C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_char_p, C.c_int]
         lib.bplx_plancheck_eval.restype = C.c_int
+        lib.bplx_plancheck_eval2.argtypes = [C.POINTER(_abi.ProblemDesc), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_char_p, C.c_int]
+        lib.bplx_plancheck_eval2.restype = C.c_int
         _plancheck = lib
     return _plancheck
 
 
-def plancheck_eval(arr: bdata.MatchArrays, theta: np.ndarray):
-    """Double-precision walk of the product's static plan, chain by chain."""
+def plancheck_eval(arr: bdata.MatchArrays, theta: np.ndarray, split_idx: int = 0):
+    """Double-precision walk of the product's static plan (for 2**split_idx CTAs per chain group), chain by chain."""
     lib = plancheck_lib()
     desc = arr.desc()
     theta = np.ascontiguousarray(theta, dtype=np.float64)
@@ -110,8 +113,8 @@ def plancheck_eval(arr: bdata.MatchArrays, theta: np.ndarray):
     err = C.create_string_buffer(512)
     for c in range(Cn):
         one_lp, one_cc = C.c_double(), C.c_double()
-        rc = lib.bplx_plancheck_eval(C.byref(desc), theta[c].ctypes.data, C.addressof(one_lp),
-                                     grad[c].ctypes.data, C.addressof(one_cc), err, 512)
+        rc = lib.bplx_plancheck_eval2(C.byref(desc), split_idx, theta[c].ctypes.data, C.addressof(one_lp),
+                                      grad[c].ctypes.data, C.addressof(one_cc), err, 512)
         if rc != 0:
             raise RuntimeError(f"plancheck rc={rc}: {err.value.decode()}")
         lp[c], cc[c] = one_lp.value, one_cc.value

@@ -157,3 +157,22 @@ def test_results_are_bit_reproducible():
     torch.cuda.synchronize()
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("split", [1, 2, 4, 8])
+@pytest.mark.parametrize("model,kw", [("extended", dict(weighted=True, K=3)), ("neutral_wc", dict(multi_conf=True, K=2, T=13, M=400)),
+                                      ("dixon_coles", dict())])
+def test_cluster_split(model, kw, split, monkeypatch):
+    """Few-chain mode: 1, 2, 4 or 8 CTAs (one thread-block cluster) share a group of chains; same numbers."""
+    import torch
+    from bpl_next_b200 import Problem
+
+    monkeypatch.setenv("BPLX_SPLIT", str(split))
+    arr = H.small_problem(model, seed=3, **kw)
+    p = Problem(arr)
+    for C in (45, 7):
+        theta = H.random_theta(p.D, C, seed=11, radius=1.0, dtype=np.float32)
+        lp, grad, cc = p.logdensity(torch.from_numpy(theta).cuda())
+        torch.cuda.synchronize()
+        _check(arr, theta.astype(np.float64), lp.cpu().numpy(), grad.cpu().numpy(), cc.cpu().numpy())
+    p.close()

@@ -92,3 +92,18 @@ def test_plan_edge_cases(name, arr):
     np.testing.assert_allclose(cc_p, cc_o, rtol=1e-9, atol=1e-12)
     scale = np.abs(g_o).max(axis=1, keepdims=True)
     np.testing.assert_allclose(g_p / scale, g_o / scale, rtol=0, atol=2e-7)
+
+
+@pytest.mark.parametrize("split_idx", [1, 2, 3])
+def test_split_plans_match_oracle(split_idx):
+    """The streams built for 2, 4 and 8 CTAs per chain group (few-chain cluster mode) describe the same model."""
+    for model, kw in [("extended", dict(K=2)), ("neutral_wc", dict(multi_conf=True, T=13, M=400))]:
+        arr = H.small_problem(model, seed=8, **kw)
+        d = H.to_oracle(arr)
+        D = om.num_params(model, arr.num_teams, arr.num_covariates, arr.num_conferences)
+        theta = H.random_theta(D, 3, seed=19, radius=1.0)
+        lp_o, g_o, cc_o = om.log_density_and_grad(d, theta)
+        lp_p, g_p, cc_p = H.plancheck_eval(arr, theta, split_idx)
+        np.testing.assert_allclose(lp_p, lp_o, rtol=1e-7)
+        scale = np.abs(g_o).max(axis=1, keepdims=True)
+        np.testing.assert_allclose(g_p / scale, g_o / scale, rtol=0, atol=2e-7)
