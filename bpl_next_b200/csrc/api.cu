@@ -76,7 +76,7 @@ static int enqueue(const bplx_problem* p, int C, int layout, int ld, const float
   int si = 0;
   const int groups = (C + kChains - 1) / kChains;
   for (int i = kNumSplits - 1; i >= 1; i--)
-    if (p->s1[i] && groups <= p->max_clusters[i]) {
+    if (p->s1[i] && (1 << i) <= kp.split_hint && groups <= p->max_clusters[i]) {
       si = i;
       break;
     }

@@ -411,6 +411,12 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err, int 
   }
   kp.nwarps = W;
   kp.stage_bytes = stage;
+  {  // a cluster only pays when one CTA's share of the walk is long compared with the cluster barriers (~1 us each):
+     // measured, configs[1] data (1.5 k cost units per warp) loses 50 %, configs[2] data (50 k) gains 3.4x
+    std::vector<std::vector<int>> t1, t2;
+    const double span = assign(cost1, W, &t1) + assign(cost2, W, &t2);
+    kp.split_hint = span >= 32000.0 ? 8 : span >= 16000.0 ? 4 : span >= 8000.0 ? 2 : 1;
+  }
 
   // ---- emit the streams ---------------------------------------------------------------------------
   const uint32_t zero_row = (uint32_t)V * kRowBytes;

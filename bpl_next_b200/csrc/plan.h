@@ -125,6 +125,7 @@ struct KernelParams {
   uint32_t epi_team, epi_part;   // epilogue reuse of the table area: team rows, per-warp partials
   uint32_t epi_cl;               // ... and the per-CTA partials of a cluster ([kMaxSplit][kPartRows][32], on rank 0)
   uint32_t smem_red_cl;          // [kMaxSplit][32] d/d corr_coef partials of a cluster (rank 0)
+  int split_hint;                // largest cluster size worth using (small plans are latency-bound: 1)
   ThetaOffsets off;
   const unsigned char* stream1;  // phase-1 streams of all warps
   const unsigned char* stream2;  // phase-2 streams

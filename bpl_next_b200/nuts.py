@@ -102,6 +102,13 @@ def sample(potential: Callable[[torch.Tensor, torch.Tensor, torch.Tensor], None]
     dev = theta0.device
     f32 = dict(dtype=torch.float32, device=dev)
     num_keep = (num_samples + thin - 1) // thin
+    # state: 18 + 2 * max_tree_depth vectors of [D, C]; output: num_keep of them.  Fail early and say what to change.
+    need = 4 * D * Cn * (18 + 2 * max_tree_depth + num_keep) + 8 * num_keep * Cn
+    free, _total = torch.cuda.mem_get_info(dev)
+    if need > 0.95 * free:
+        raise MemoryError(
+            f"NUTS on {Cn} chains x {D} parameters needs {need / 2**30:.1f} GiB ({num_keep} stored draws of "
+            f"{4 * D * Cn / 2**20:.0f} MiB each), {free / 2**30:.1f} GiB are free: raise `thin` or lower num_samples / the chain count")
     vecs = {n: torch.zeros((D, Cn), **f32) for n in ("p_half", "inv_mass", "zL", "rL", "gL", "zR", "rR", "gR", "zP", "gP",
                                                       "r_sum", "zQ", "gQ", "r_sum_sub", "wf_mean", "wf_m2")}
     r_ckpts = torch.zeros((max_tree_depth, D, Cn), **f32)
