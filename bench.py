@@ -264,7 +264,8 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "chains_per_gpu": C, "theta": f"U(-{args.radius},{args.radius})"},
+            "config": {"workload": desc + f", {C} chains/GPU", "chains_per_gpu": C, "matches": arr.num_matches,
+                       "teams": arr.num_teams, "params": D, "theta": f"U(-{args.radius},{args.radius})"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                              "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
