@@ -125,76 +125,78 @@ __global__ void __launch_bounds__(kGridThreads, 1) score_grid_kernel(const __gri
     cp_async_wait<1>();
     __syncthreads();
     const int ns = min(kGridStage, s_end - (s_begin + st * kGridStage));
-    // two samples per trip: their gathers / exps overlap.  The accumulators hold sum_s e^-lh lh^i e^-la la^j; the
-    // 1 / (i! j!) of the two Poisson pmfs is applied once, by the finalize kernel.
+    // Software pipeline over the samples of the stage: the rates and pmf powers of sample j+1 (gathers -> exp -> exp ->
+    // recurrence, one long dependent chain) are computed in the same basic block as the R x CC FMAs of sample j, so the
+    // scheduler hides the chain behind the FMA stream (two warps per scheduler cannot hide it by themselves).
+    // The accumulators hold sum_s e^-lh lh^i e^-la la^j; 1 / (i! j!) is applied once, by the finalize kernel.
+    auto vectors = [&](int j, bool live, float (&ph)[R], float (&pa)[CC], float (&tt)[4]) {
+      const float* A = cur + L.att + j * gp.T;
+      const float* Dd = cur + L.def + j * gp.T;
+      float eh = A[h] - Dd[a], ea = A[a] - Dd[h];
+      if (gp.model == BPLX_DIXON_COLES) {
+        eh += cur[L.ha + j];
+      } else if (gp.model == BPLX_EXTENDED) {
+        eh += cur[L.ha + j * gp.T + h];
+      } else {
+        if (gp.model == BPLX_NEUTRAL_WC) {
+          const float* cs = cur + L.conf + j * gp.Cf;
+          const float dcf = cs[hc] - cs[ac];
+          eh += dcf;
+          ea -= dcf;
+        }
+        eh += n * cur[L.ha + j * gp.T + h] - n * cur[L.ad + j * gp.T + a];
+        ea += n * cur[L.aa + j * gp.T + a] - n * cur[L.hd + j * gp.T + h];
+      }
+      const float lh = __expf(eh), la = __expf(ea);
+      const float c = cur[L.corr + j];
+      float p = live ? __expf(-lh) : 0.0f;  // a sample past the end of the stage gets weight 0
+      if (!SINGLE)
+        for (int k = 1; k <= r0; k++) p *= lh;
+      ph[0] = p;
+#pragma unroll
+      for (int i = 1; i < R; i++) {
+        p *= lh;
+        ph[i] = p;
+      }
+      p = __expf(-la);
+      if (!SINGLE)
+        for (int k = 1; k <= c0; k++) p *= la;
+      pa[0] = p;
+#pragma unroll
+      for (int i = 1; i < CC; i++) {
+        p *= la;
+        pa[i] = p;
+      }
+      // tau on the four low-score cells, clipped at 0 (bpl/_util.py:62-68)
+      tt[0] = tt[1] = tt[2] = tt[3] = 1.0f;
+      if (corner) {
+        tt[0] = fmaxf(1.0f - (c * lh) * la, 0.0f);
+        tt[1] = fmaxf(fmaf(c, lh, 1.0f), 0.0f);  // home 0, away 1
+        tt[2] = fmaxf(fmaf(c, la, 1.0f), 0.0f);  // home 1, away 0
+        tt[3] = fmaxf(1.0f - c, 0.0f);
+      }
+    };
+    float ph[R], pa[CC], tt[4];
+    vectors(0, true, ph, pa, tt);
 #pragma unroll 1
-    for (int j0 = 0; j0 < ns; j0 += 2) {
-      float ph[2][R], pa[2][CC], t00[2], t01[2], t10[2], t11[2];
+    for (int j = 0; j < ns; j++) {
+      float ph_n[R], pa_n[CC], tt_n[4];
+      vectors(min(j + 1, ns - 1), j + 1 < ns, ph_n, pa_n, tt_n);
 #pragma unroll
-      for (int u = 0; u < 2; u++) {
-        const int j = min(j0 + u, ns - 1);
-        const float* A = cur + L.att + j * gp.T;
-        const float* Dd = cur + L.def + j * gp.T;
-        float eh = A[h] - Dd[a], ea = A[a] - Dd[h];
-        if (gp.model == BPLX_DIXON_COLES) {
-          eh += cur[L.ha + j];
-        } else if (gp.model == BPLX_EXTENDED) {
-          eh += cur[L.ha + j * gp.T + h];
-        } else {
-          if (gp.model == BPLX_NEUTRAL_WC) {
-            const float* cs = cur + L.conf + j * gp.Cf;
-            const float dcf = cs[hc] - cs[ac];
-            eh += dcf;
-            ea -= dcf;
-          }
-          eh += n * cur[L.ha + j * gp.T + h] - n * cur[L.ad + j * gp.T + a];
-          ea += n * cur[L.aa + j * gp.T + a] - n * cur[L.hd + j * gp.T + h];
-        }
-        const float lh = __expf(eh), la = __expf(ea);
-        const float c = cur[L.corr + j];
-        // e^-lambda lambda^k by recurrence (k! is applied at the end); a duplicated last sample gets weight 0
-        float p = (j0 + u < ns) ? __expf(-lh) : 0.0f;
-        if (!SINGLE)
-          for (int k = 1; k <= r0; k++) p *= lh;
-        ph[u][0] = p;
+      for (int i = 0; i < R; i++) {
 #pragma unroll
-        for (int i = 1; i < R; i++) {
-          p *= lh;
-          ph[u][i] = p;
-        }
-        p = __expf(-la);
-        if (!SINGLE)
-          for (int k = 1; k <= c0; k++) p *= la;
-        pa[u][0] = p;
-#pragma unroll
-        for (int i = 1; i < CC; i++) {
-          p *= la;
-          pa[u][i] = p;
-        }
-        // tau on the four low-score cells, clipped at 0 (bpl/_util.py:62-68)
-        t00[u] = t01[u] = t10[u] = t11[u] = 1.0f;
-        if (corner) {
-          t00[u] = fmaxf(1.0f - (c * lh) * la, 0.0f);
-          t10[u] = fmaxf(fmaf(c, la, 1.0f), 0.0f);  // home 1, away 0
-          t01[u] = fmaxf(fmaf(c, lh, 1.0f), 0.0f);  // home 0, away 1
-          t11[u] = fmaxf(1.0f - c, 0.0f);
+        for (int jj = 0; jj < CC; jj++) {
+          float w = ph[i];
+          if (i < 2 && jj < 2) w *= tt[i * 2 + jj];
+          acc[i][jj] = fmaf(w, pa[jj], acc[i][jj]);
         }
       }
 #pragma unroll
-      for (int u = 0; u < 2; u++) {
+      for (int i = 0; i < R; i++) ph[i] = ph_n[i];
 #pragma unroll
-        for (int i = 0; i < R; i++) {
+      for (int i = 0; i < CC; i++) pa[i] = pa_n[i];
 #pragma unroll
-          for (int jj = 0; jj < CC; jj++) {
-            float w = ph[u][i];
-            if (i == 0 && jj == 0) w *= t00[u];
-            if (i == 0 && jj == 1) w *= t01[u];
-            if (i == 1 && jj == 0) w *= t10[u];
-            if (i == 1 && jj == 1) w *= t11[u];
-            acc[i][jj] = fmaf(w, pa[u][jj], acc[i][jj]);
-          }
-        }
-      }
+      for (int i = 0; i < 4; i++) tt[i] = tt_n[i];
     }
     __syncthreads();
   }
