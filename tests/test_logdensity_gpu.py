@@ -176,3 +176,23 @@ def test_cluster_split(model, kw, split, monkeypatch):
         torch.cuda.synchronize()
         _check(arr, theta.astype(np.float64), lp.cpu().numpy(), grad.cpu().numpy(), cc.cpu().numpy())
     p.close()
+
+
+@pytest.mark.parametrize("seed", range(0, 40, 3))
+def test_random_problems(seed):
+    """The randomised problems of tests/test_plan_random.py through the CUDA kernels (33 chains, both layouts)."""
+    import torch
+    from bpl_next_b200 import Problem
+    from tests.test_plan_random import _random_problem
+
+    model, kw = _random_problem(seed)
+    arr = H.small_problem(model, seed=100 + seed, **kw)
+    p = Problem(arr)
+    theta = H.random_theta(p.D, 33, seed=seed, radius=0.8, dtype=np.float32)
+    for minor in (False, True):
+        t = torch.from_numpy(theta).cuda()
+        lp, grad, cc = p.logdensity(t.t().contiguous() if minor else t, chain_minor=minor)
+        torch.cuda.synchronize()
+        g = grad.t().contiguous() if minor else grad
+        _check(arr, theta.astype(np.float64), lp.cpu().numpy(), g.cpu().numpy(), cc.cpu().numpy())
+    p.close()
