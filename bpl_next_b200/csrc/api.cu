@@ -24,14 +24,19 @@ void set_error(const char* fmt, ...) {
 }
 void note_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
+constexpr size_t kUploadSlack = (size_t)kMaxSplit * kMaxWarps * sizeof(EntryClip) + 64;
 template <typename T>
 static int upload(bplx_problem* p, const std::vector<T>& h, const T** out) {
   *out = nullptr;
   if (h.empty()) return BPLX_OK;
   void* d = nullptr;
-  BPLX_CUDA(cudaMalloc(&d, h.size() * sizeof(T)));
+  // kUploadSlack zero bytes follow every array: the arg-max search reads its first candidate entry of a piece before it
+  // knows how many entries the piece has (logdensity.cu)
+  const size_t bytes = h.size() * sizeof(T);
+  BPLX_CUDA(cudaMalloc(&d, bytes + kUploadSlack));
   p->dev_allocs.push_back(d);
-  BPLX_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  BPLX_CUDA(cudaMemcpy(d, h.data(), bytes, cudaMemcpyHostToDevice));
+  BPLX_CUDA(cudaMemset(static_cast<unsigned char*>(d) + bytes, 0, kUploadSlack));
   *out = static_cast<const T*>(d);
   return BPLX_OK;
 }
@@ -90,7 +95,7 @@ static int enqueue(const bplx_problem* p, int C, int layout, int ld, const float
   kp.stream2 = p->s2[si];
   kp.warp_b1 = p->wb1[si];
   kp.warp_b2 = p->wb2[si];
-  return kp.model == BPLX_DYNAMIC ? launch_logdensity_dynamic(kp, stream) : launch_logdensity(kp, stream);
+  return kp.model == BPLX_DYNAMIC ? launch_logdensity_dynamic(kp, stream) : launch_logdensity(kp, p->wb[si], stream);
 }
 
 }  // namespace bplx
@@ -135,6 +140,13 @@ int bplx_problem_create(const bplx_problem_desc* desc, bplx_problem** out) {
     UP(more[i - 1].warp_b1, p->wb1[i]);
     UP(more[i - 1].warp_b2, p->wb2[i]);
   }
+  auto keep_bounds = [&](int i, const std::vector<uint32_t>& b1, const std::vector<uint32_t>& b2) {
+    const size_t cap = sizeof(p->wb[i].b1) / sizeof(uint32_t);
+    for (size_t k = 0; k < b1.size() && k < cap; k++) p->wb[i].b1[k] = b1[k];
+    for (size_t k = 0; k < b2.size() && k < cap; k++) p->wb[i].b2[k] = b2[k];
+  };
+  keep_bounds(0, hp.warp_b1, hp.warp_b2);
+  for (int i = 1; i < kNumSplits; i++) keep_bounds(i, hp.more[i - 1].warp_b1, hp.more[i - 1].warp_b2);
   kp.stream1 = p->s1[0];
   kp.stream2 = p->s2[0];
   kp.warp_b1 = p->wb1[0];
@@ -240,6 +252,16 @@ int bplx_logdensity_fwdbwd_host(bplx_problem* p, int C, const float* theta, floa
   // (only worth it when a chunk still fills the GPU: below ~16k chains K1 is latency-bound and chunking serialises it;
   //  measured on configs[1], 4,096 chains: 104 us in one piece, 138 us in four)
   const int nchunk = C >= 32768 ? 4 : (C >= 16384 ? 2 : 1);
+  if (nchunk == 1) {  // one piece: everything in order on one stream, no events (each costs microseconds at this scale)
+    BPLX_CUDA(cudaMemcpyAsync(p->d_theta, theta, (size_t)C * D * sizeof(float), cudaMemcpyHostToDevice, s));
+    int rc = enqueue(p, C, BPLX_CHAIN_MAJOR, (int)D, p->d_theta, d_lp, d_grad, d_cc, p->d_ws, p->d_ws_bytes, s);
+    if (rc != BPLX_OK) return rc;
+    BPLX_CUDA(cudaMemcpyAsync(grad, d_grad, (size_t)C * D * sizeof(float), cudaMemcpyDeviceToHost, s));
+    BPLX_CUDA(cudaMemcpyAsync(lp, d_lp, (size_t)C * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (corr_coef) BPLX_CUDA(cudaMemcpyAsync(corr_coef, d_cc, (size_t)C * sizeof(float), cudaMemcpyDeviceToHost, s));
+    BPLX_CUDA(cudaStreamSynchronize(s));
+    return BPLX_OK;
+  }
   const int per = ((C + nchunk - 1) / nchunk + 31) / 32 * 32;
   for (int k = 0, c0 = 0; c0 < C; k++, c0 += per) {
     const int n = C - c0 < per ? C - c0 : per;

@@ -55,6 +55,35 @@ __device__ __forceinline__ uint4 lds128u(uint32_t addr) {
   return v;
 }
 
+// packed FP32 pairs (sm_100: FFMA2 / FMUL2 / FADD2 -- two IEEE fp32 operations per issue slot; a pair whose halves are
+// the same register is taken as a broadcast scalar operand, a negated one folds into the instruction)
+__device__ __forceinline__ unsigned long long pk2(float2 a) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+  return r;
+}
+__device__ __forceinline__ float2 upk2(unsigned long long v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)), "l"(pk2(c)));
+  return upk2(d);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)));
+  return upk2(d);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)));
+  return upk2(d);
+}
+__device__ __forceinline__ float2 bc2(float x) { return make_float2(x, x); }
+
 // distributed shared memory (thread-block clusters): 32-bit shared::cluster addresses ----------------------
 // (generic-pointer atomics on a mapped address compile to a LOCAL shared-memory CAS loop -- address the remote CTA
 //  explicitly.  A launch without a cluster attribute is an implicit cluster of one: rank 0 is the CTA itself.)

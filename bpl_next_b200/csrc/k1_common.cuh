@@ -47,19 +47,29 @@ __device__ __forceinline__ void red_add(float* p, float v) {
 }
 __device__ __forceinline__ float ld_cg(const float* p) { return __ldcg(p); }  // L2 only: the line is red.add'ed
 
-__device__ __forceinline__ Hyp load_hyp(const KernelParams& kp, const Lane& ln) {
+// (two steps, so that a kernel can issue the loads early and do the exponentials when it needs the values)
+__device__ __forceinline__ Hyp load_hyp_raw(const KernelParams& kp, const Lane& ln) {
   const ThetaOffsets& o = kp.off;
   Hyp hy;
   hy.mu_d = ln.ld(o.mean_defence);
-  hy.sig_a = expf(ln.ld(o.log_std_attack));
-  hy.sig_d = expf(ln.ld(o.log_std_defence));
+  hy.sig_a = ln.ld(o.log_std_attack);
+  hy.sig_d = ln.ld(o.log_std_defence);
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     hy.mu[i] = o.mean[i] >= 0 ? ln.ld(o.mean[i]) : 0.0f;
-    hy.sig[i] = o.log_std[i] >= 0 ? expf(ln.ld(o.log_std[i])) : 0.0f;
+    hy.sig[i] = o.log_std[i] >= 0 ? ln.ld(o.log_std[i]) : 0.0f;
   }
   return hy;
 }
+__device__ __forceinline__ Hyp finish_hyp(const KernelParams& kp, Hyp hy) {
+  const ThetaOffsets& o = kp.off;
+  hy.sig_a = expf(hy.sig_a);
+  hy.sig_d = expf(hy.sig_d);
+#pragma unroll
+  for (int i = 0; i < 4; i++) hy.sig[i] = o.log_std[i] >= 0 ? expf(hy.sig[i]) : 0.0f;
+  return hy;
+}
+__device__ __forceinline__ Hyp load_hyp(const KernelParams& kp, const Lane& ln) { return finish_hyp(kp, load_hyp_raw(kp, ln)); }
 
 struct Hdr {
   uint32_t own_off, vteam, kind, flags, n0, n1, n2, team;

@@ -32,11 +32,161 @@
 
 namespace cg = cooperative_groups;
 
+#ifdef BPLX_TIMELINE
+// debug build only: per-warp globaltimer stamps at the region boundaries of CTA 0 (read back with bplx_timeline_read)
+__device__ unsigned long long g_timeline[32 * 24];
+#define BPLX_STAMP(i)                                                                    \
+  do {                                                                                   \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) {                                    \
+      unsigned long long t_;                                                             \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                             \
+      g_timeline[(threadIdx.x >> 5) * 24 + (i)] = t_;                                    \
+    }                                                                                    \
+  } while (0)
+// the stamp is taken once `dep` (a float) has been computed
+#define BPLX_STAMP_DEP(i, dep)                                                           \
+  do {                                                                                   \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) {                                    \
+      unsigned long long t_;                                                             \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_) : "f"(dep));                  \
+      g_timeline[(threadIdx.x >> 5) * 24 + (i)] = t_;                                    \
+    }                                                                                    \
+  } while (0)
+#else
+#define BPLX_STAMP(i)
+#define BPLX_STAMP_DEP(i, dep)
+#endif
+
 namespace bplx {
 
+// One phase-1 piece of a model that clips its rates at 15 (DIXON_COLES, EXTENDED; bpl/dixon_coles.py:66-75): entries
+// (opponent row, w, w y_x, w y_y).  *lp  sum w (y log rate - rate) of a home list;  m1..m3  maxima of the two rates and
+// their product;  *gx, *gy  d/d (log X, log Y) of the list's own team.
+// FAST: the prologue's bound says no rate of these 32 chains reaches the clip -- the same arithmetic with
+// min(x, 15) = x and every guard true, bit for bit.
+template <bool FAST, bool HOME>
+__device__ __forceinline__ void rate_piece_clip(uint32_t& a, const uint32_t e_end, const float2 own, const uint32_t tab,
+                                                float& lp, float& m1, float& m2, float& m3, float& gx, float& gy) {
+  float2 lg = make_float2(0.0f, 0.0f), lw = lg, g = lg;
+#pragma unroll 4
+  for (; a < e_end; a += 16) {
+    const uint4 q = lds128u(a);
+    const float2 ea = lds64(tab + q.x);
+    const float w = __uint_as_float(q.y);
+    const float2 wy = make_float2(__uint_as_float(q.z), __uint_as_float(q.w));
+    const float2 XY = mul2(own, ea);
+    const float2 d = fma2(bc2(-w), XY, wy);  // w (y - rate): the gradient term of an unclipped rate
+    if (FAST) {
+      g = add2(g, d);
+    } else {
+      if (XY.x < 15.0f) g.x += d.x;
+      if (XY.y < 15.0f) g.y += d.y;
+    }
+    if (HOME) {
+      const float2 c = FAST ? XY : make_float2(fminf(XY.x, 15.0f), fminf(XY.y, 15.0f));
+      lg = fma2(wy, make_float2(lg2_approx(c.x), lg2_approx(c.y)), lg);
+      lw = fma2(bc2(w), c, lw);
+      m1 = fmaxf(m1, c.x);
+      m2 = fmaxf(m2, c.y);
+      m3 = fmaxf(m3, c.x * c.y);
+    }
+  }
+  gx = g.x;
+  gy = g.y;
+  if (HOME) lp = fmaf(lg.x + lg.y, kLn2, -(lw.x + lw.y));
+}
+
+// order-preserving float <-> unsigned key (for an integer atomicMax over floats of either sign)
+__device__ __forceinline__ uint32_t float_key(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k) {
+  return __uint_as_float(k ^ ((k & 0x80000000u) ? 0x80000000u : 0xffffffffu));
+}
+
+// The tau terms of one phase-2 piece (bpl/_util.py:54-91): entries with tau = 1 - c X Y, then 1 + c X, then 1 + c Y.
+//   *lt  sum w log2 tau;  *du  d/d corr_coef;  *gx, *gy  d/d (log X, log Y) of the list's own team
+// kTauPlain: model without rate clipping.  kTauClipped: rates clipped at 15 (DIXON_COLES, EXTENDED).  kTauUnclipped:
+// same model, but the chain maxima say no rate of these 32 chains is at the clip -- the clipped arithmetic with
+// min(x, 15) = x and every guard true, bit for bit, minus the instructions.
+enum { kTauPlain = 0, kTauUnclipped = 1, kTauClipped = 2 };
+template <int MODE>
+__device__ __forceinline__ void tau_piece(uint32_t& a, const Hdr& L, const float2 own, const bool home, const float cc,
+                                          const uint32_t tab, float& lt_out, float& du_out, float& gx_out, float& gy_out) {
+  // every 16 bytes hold two entries (opponent row offset, w): their arithmetic runs as packed pairs (.x = first entry)
+  const float2 one = make_float2(1.0f, 1.0f);
+  float2 lt = make_float2(0.0f, 0.0f), uxy = lt, sxy_x = lt, sxy_y = lt;
+  {
+    const float Pxy = own.x * own.y;
+    const uint32_t e_end = a + L.n0 * (uint32_t)sizeof(Entry);
+#pragma unroll 2
+    for (; a < e_end; a += 16) {
+      const uint4 q = lds128u(a);
+      const float2 ea = lds64(tab + q.x), eb = lds64(tab + q.z);
+      const float2 w = make_float2(__uint_as_float(q.y), __uint_as_float(q.w));
+      float2 t, ra, rb;
+      if (MODE == kTauPlain) {
+        t = mul2(bc2(Pxy), make_float2(ea.x * ea.y, eb.x * eb.y));
+      } else {
+        ra = mul2(own, ea);
+        rb = mul2(own, eb);
+        if (MODE == kTauClipped) t = make_float2(fminf(ra.x, 15.0f) * fminf(ra.y, 15.0f), fminf(rb.x, 15.0f) * fminf(rb.y, 15.0f));
+        else t = make_float2(ra.x * ra.y, rb.x * rb.y);
+      }
+      float2 tau = fma2(bc2(-cc), t, one);
+      tau.x = fmaxf(tau.x, 0.0f);
+      tau.y = fmaxf(tau.y, 0.0f);
+      const float2 val = mul2(mul2(w, t), make_float2(rcp_approx(tau.x), rcp_approx(tau.y)));
+      uxy = add2(uxy, val);
+      if (MODE == kTauClipped) {
+        if (ra.x < 15.0f) sxy_x.x += val.x;
+        if (rb.x < 15.0f) sxy_x.y += val.y;
+        if (ra.y < 15.0f) sxy_y.x += val.x;
+        if (rb.y < 15.0f) sxy_y.y += val.y;
+      }
+      if (home) lt = fma2(w, make_float2(lg2_approx(tau.x), lg2_approx(tau.y)), lt);
+    }
+  }
+  float u1[2] = {0.0f, 0.0f}, s1[2] = {0.0f, 0.0f};
+#pragma unroll
+  for (int c = 0; c < 2; c++) {
+    const float oc = c == 0 ? own.x : own.y;
+    const uint32_t e_end = a + (c == 0 ? L.n1 : L.n2) * (uint32_t)sizeof(Entry);
+    float2 u = make_float2(0.0f, 0.0f), sm = u;
+#pragma unroll 2
+    for (; a < e_end; a += 16) {
+      const uint4 q = lds128u(a);
+      const float2 Rr = mul2(bc2(oc), make_float2(lds32(tab + q.x), lds32(tab + q.z)));  // `off` already selects .x or .y
+      const float2 w = make_float2(__uint_as_float(q.y), __uint_as_float(q.w));
+      const float2 R = MODE == kTauClipped ? make_float2(fminf(Rr.x, 15.0f), fminf(Rr.y, 15.0f)) : Rr;
+      float2 tau = fma2(bc2(cc), R, one);
+      tau.x = fmaxf(tau.x, 0.0f);
+      tau.y = fmaxf(tau.y, 0.0f);
+      const float2 val = mul2(mul2(w, R), make_float2(rcp_approx(tau.x), rcp_approx(tau.y)));
+      u = add2(u, val);
+      if (MODE == kTauClipped) {
+        if (Rr.x < 15.0f) sm.x += val.x;
+        if (Rr.y < 15.0f) sm.y += val.y;
+      }
+      if (home) lt = fma2(w, make_float2(lg2_approx(tau.x), lg2_approx(tau.y)), lt);
+    }
+    u1[c] = u.x + u.y;
+    s1[c] = MODE == kTauClipped ? sm.x + sm.y : u1[c];
+  }
+  const float uxy_s = uxy.x + uxy.y;
+  const float sx = MODE == kTauClipped ? sxy_x.x + sxy_x.y : uxy_s, sy = MODE == kTauClipped ? sxy_y.x + sxy_y.y : uxy_s;
+  lt_out = lt.x + lt.y;
+  du_out = u1[0] + u1[1] - uxy_s;
+  gx_out = cc * (s1[0] - sx);
+  gy_out = cc * (s1[1] - sy);
+}
+
 template <bool CLIP>
-__global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __grid_constant__ KernelParams kp) {
+__global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __grid_constant__ KernelParams kp,
+                                                                        const __grid_constant__ WarpBounds wb) {
   extern __shared__ __align__(1024) unsigned char smem[];
+  BPLX_STAMP(19);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = kp.nwarps;
   const ThetaOffsets& o = kp.off;
   const int S = kp.split;  // CTAs of the cluster that shares this group of chains (1: no cluster)
@@ -56,7 +206,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
   ln.sd = kp.sd;
   ln.active = chain_raw < kp.C;
   const uint32_t tab = smem_u32(smem) + lane * 8;  // + row byte offset
-  // one CTA: [3][32] u64 (value bits << 32 | piece offset).  Cluster: [3][32] u32 value bits, then [3][32] u32 piece offsets
+  // [3][32] u32 value bits, then [3][32] u32 piece offsets
   unsigned long long* red_best = reinterpret_cast<unsigned long long*>(smem + kp.smem_red);
   unsigned long long* red_found = reinterpret_cast<unsigned long long*>(smem + kp.smem_red + 768);  // [2][32] entry | info << 32
   float* red_hyp = reinterpret_cast<float*>(smem + kp.smem_red + 1280);                       // [12][32]
@@ -70,8 +220,37 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
   Ring ring;
   ring.init(smem_u32(smem) + kp.smem_ring + warp * (kStages * kp.stage_bytes),
             smem_u32(smem) + kp.smem_bar + warp * (kStages * 8), kp.stage_bytes, lane);
-  const uint32_t b1_0 = __ldg(kp.warp_b1 + vwarp), b1_1 = __ldg(kp.warp_b1 + vwarp + 1);
+  const uint32_t b1_0 = wb.b1[vwarp], b1_1 = wb.b1[vwarp + 1];
   ring.begin(kp.stream1 + b1_0, b1_1 - b1_0);  // phase-1 pieces start streaming in while the prologue runs
+  // Everything the prologue needs from global memory is requested here, in one go, right after the ring has been
+  // started (the ring's set-up ends in a fence, which would wait for loads already in flight): one round trip for all
+  // of it.  (What the first pass over a team needs is then fetched one team ahead.)
+  const int ndec = kp.ndec;
+  const bool dc = ndec == 0;
+  const float raw_in = ln.ld(o.raw);  // (its sigmoid -- a division, hence branches -- waits until the prologue's end)
+  const float u_in = (warp == 0 && !dc) ? ln.ld(o.u) : 0.0f;
+  struct TeamIn { float za, zd, dz[4], xs[4]; int fl, v0, v1; };
+  auto load_team = [&](int t) {
+    TeamIn in;
+    in.za = ln.ld(o.za + t);
+    in.zd = ln.ld(o.zd + t);
+#pragma unroll
+    for (int i = 0; i < 4; i++) in.dz[i] = i < ndec ? ln.ld(o.dec[i] + t) : 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; j++) in.xs[j] = j < kp.K ? __ldg(kp.Xs + (size_t)t * kp.K + j) : 0.0f;
+    in.fl = __ldg(kp.team_flags + t);
+    in.v0 = __ldg(kp.team_vptr + t);
+    in.v1 = __ldg(kp.team_vptr + t + 1);
+    return in;
+  };
+  TeamIn nx = load_team(min(warp, kp.T - 1));
+  float ba[4], bd[4];  // the first four covariate coefficients (more: the loop below)
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    ba[j] = j < kp.K ? ln.ld(o.beta_a + j) : 0.0f;
+    bd[j] = j < kp.K ? ln.ld(o.beta_d + j) : 0.0f;
+  }
+  const Hyp hy_in = load_hyp_raw(kp, ln);
   {  // pull this CTA's slice of theta into L2 in one go: every later read of it is a hit
     const int nthr = W * 32;
     if (kp.sd == 1) {  // chain-major: 32 rows of D floats
@@ -86,12 +265,10 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
     }
   }
 
-  const int ndec = kp.ndec;
-  const bool dc = ndec == 0;
   float lp_acc = 0.0f;  // this thread's share of the log-density
   float hacc = 0.0f;    // DIXON_COLES: d/d home_advantage
 
-  // ---- prologue -------------------------------------------------------------------------------
+  uint32_t* red_clip = reinterpret_cast<uint32_t*>(smem + kp.smem_red_cl);  // [2][32] keys, this CTA's own (CLIP models)
   if (warp == 0) {
     const uint32_t zr = (uint32_t)kp.V * kRowBytes;  // zero rows used by padding entries
     if (kp.has1) {
@@ -99,47 +276,55 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
       sts64(tab + kp.tabQ1 + zr, 0.0f, 0.0f);
     }
     if (kp.has0) sts64(tab + kp.tabP0 + zr, 0.0f, 0.0f);
+    if (CLIP) red_clip[lane] = red_clip[32 + lane] = 0u;
     if (crank == 0) {
-      if (S == 1) {
-        red_best[lane] = red_best[32 + lane] = red_best[64 + lane] = 0ull;
-      } else {
-        uint32_t* rb = reinterpret_cast<uint32_t*>(red_best);
-        rb[lane] = rb[32 + lane] = rb[64 + lane] = 0u;                         // values
-        rb[96 + lane] = rb[128 + lane] = rb[160 + lane] = 0xffffffffu;         // piece offsets (atomicMin)
-      }
+      uint32_t* rb = reinterpret_cast<uint32_t*>(red_best);
+      rb[lane] = rb[32 + lane] = rb[64 + lane] = 0u;                  // values
+      rb[96 + lane] = rb[128 + lane] = rb[160 + lane] = 0xffffffffu;  // piece offsets (atomicMin)
       red_found[lane] = red_found[32 + lane] = ~0ull;
     }
   }
-  const float r = sigmoid_clipped(ln.ld(o.raw));
+  if (CLIP) __syncthreads();  // the prologue's atomics on red_clip follow (all warps are still in step: cheap)
+
+  BPLX_STAMP(0);
+  // ---- prologue -------------------------------------------------------------------------------
+  BPLX_STAMP_DEP(12, raw_in);
   {
-    const Hyp hy = load_hyp(kp, ln);
+    const Hyp hy = finish_hyp(kp, hy_in);
+    BPLX_STAMP_DEP(13, hy.sig_a + hy.sig_d + hy.sig[0] + hy.sig[1] + hy.sig[2] + hy.sig[3] + nx.za + nx.zd);
     if (warp == 0) {  // the team pass reads them back from shared memory
       red_hyp[0 * 32 + lane] = hy.mu_d; red_hyp[1 * 32 + lane] = hy.sig_a; red_hyp[2 * 32 + lane] = hy.sig_d;
 #pragma unroll
       for (int i = 0; i < 4; i++) { red_hyp[(3 + i) * 32 + lane] = hy.mu[i]; red_hyp[(7 + i) * 32 + lane] = hy.sig[i]; }
-      red_hyp[11 * 32 + lane] = dc ? 0.5f : sigmoid_clipped(ln.ld(o.u));
     }
+    float exA = -FLT_MAX, exB = -FLT_MAX;  // largest exponent of either factor over this warp's virtual teams
     for (int t = warp; t < kp.T; t += W) {
+      const TeamIn in = nx;
+      if (t + W < kp.T) nx = load_team(t + W);
       float am = 0.0f, dm = hy.mu_d;
-      for (int k = 0; k < kp.K; k++) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) {  // (absent covariates: x = 0, the sums do not change)
+        am = fmaf(in.xs[j], ba[j], am);
+        dm = fmaf(in.xs[j], bd[j], dm);
+      }
+      for (int k = 4; k < kp.K; k++) {
         const float x = __ldg(kp.Xs + (size_t)t * kp.K + k);
         am = fmaf(x, ln.ld(o.beta_a + k), am);
         dm = fmaf(x, ln.ld(o.beta_d + k), dm);
       }
-      const float att = fmaf(ln.ld(o.za + t), hy.sig_a, am), def = fmaf(ln.ld(o.zd + t), hy.sig_d, dm);
+      const float att = fmaf(in.za, hy.sig_a, am), def = fmaf(in.zd, hy.sig_d, dm);
       float x[4] = {dc ? hy.mu[0] : 0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
       for (int i = 0; i < 4; i++)
-        if (i < ndec) x[i] = fmaf(hy.sig[i], ln.ld(o.dec[i] + t), hy.mu[i]);
-      if (!(__ldg(kp.team_flags + t) & 1) && ln.active && crank == 0) {  // team without matches: no list will write its slots
+        if (i < ndec) x[i] = fmaf(hy.sig[i], in.dz[i], hy.mu[i]);
+      if (!(in.fl & 1) && ln.active && crank == 0) {  // team without matches: no list will write its slots
         *ln.g(o.za + t) = 0.0f;
         *ln.g(o.zd + t) = 0.0f;
 #pragma unroll
         for (int i = 0; i < 4; i++)
           if (i < ndec) *ln.g(o.dec[i] + t) = 0.0f;
       }
-      const int v0 = __ldg(kp.team_vptr + t), v1 = __ldg(kp.team_vptr + t + 1);
-      for (int v = v0; v < v1; v++) {
+      for (int v = in.v0; v < in.v1; v++) {
         const float cf = kp.Cf > 0 ? ln.ld(o.conf + __ldg(kp.v_conf + v)) : 0.0f;
         float ex[6];
         ex[eAh1] = att + x[0] + cf;
@@ -154,15 +339,31 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
           sts64(tab + kp.tabQ1 + r, expf(ex[eBa1]), expf(ex[eAa1]));
         }
         if (kp.has0) sts64(tab + kp.tabP0 + r, expf(ex[eA0]), expf(ex[eB0]));
+        if (CLIP) {
+          exA = fmaxf(exA, fmaxf(ex[eAh1], fmaxf(ex[eAa1], ex[eA0])));
+          exB = fmaxf(exB, fmaxf(ex[eBh1], fmaxf(ex[eBa1], ex[eB0])));
+        }
         if (!CLIP && crank == 0) {  // static sum of w * y * log(lambda): linear in the exponents
 #pragma unroll
           for (int e = 0; e < 6; e++) lp_acc = fmaf(__ldg(kp.yexp + (size_t)v * 6 + e), ex[e], lp_acc);
         }
       }
     }
+    if (warp == 0) red_hyp[11 * 32 + lane] = dc ? 0.5f : sigmoid_clipped(u_in);
+    if (CLIP && warp < kp.T) {
+      atomicMax(red_clip + lane, float_key(exA));
+      atomicMax(red_clip + 32 + lane, float_key(exB));
+    }
   }
+  const float r = sigmoid_clipped(raw_in);
+  BPLX_STAMP(1);
   sync_all();
 
+  BPLX_STAMP(2);
+  // every rate is exp(A-side exponent of one virtual team + B-side exponent of another): with the two maxima below
+  // log 15 (less a margin for the rounding of exp and the product) no rate of the chain can be at the clip
+  bool fast1 = false;
+  if (CLIP) fast1 = __all_sync(kFull, key_float(red_clip[lane]) + key_float(red_clip[32 + lane]) < 2.707f);
   // ---- phase 1 ----------------------------------------------------------------------------------
   float best[3] = {0.0f, 0.0f, 0.0f};
   uint32_t besth[3] = {0u, 0u, 0u};  // byte offset (in stream1) of the header of the piece that holds the maximum
@@ -172,6 +373,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
     for (uint32_t k = 0; k < nst; k++) {
       uint32_t bytes;
       const uint32_t a0 = ring.acquire(k, &bytes);
+      if (k == 0) BPLX_STAMP(16);
       uint32_t a = a0;
       const uint32_t aend = a0 + bytes;
       while (a + kp.min_piece1 <= aend) {
@@ -188,16 +390,15 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
         const bool home = (L.kind & 1) == 0;
         float gx, gy;
         if (!CLIP) {
-          float ax0 = 0.0f, ay0 = 0.0f, ax1 = 0.0f, ay1 = 0.0f;
+          float2 acc0 = make_float2(0.0f, 0.0f), acc1 = acc0;  // sum w * (X-side row, Y-side row), even / odd entries
           if (home) {
             float m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
 #pragma unroll 4
             for (; a < e_end; a += 16) {
               const uint4 q = lds128u(a);  // two entries
               const float2 ea = lds64(tab + q.x), eb = lds64(tab + q.z);
-              const float wa = __uint_as_float(q.y), wb = __uint_as_float(q.w);
-              ax0 = fmaf(wa, ea.x, ax0); ay0 = fmaf(wa, ea.y, ay0);
-              ax1 = fmaf(wb, eb.x, ax1); ay1 = fmaf(wb, eb.y, ay1);
+              acc0 = fma2(bc2(__uint_as_float(q.y)), ea, acc0);
+              acc1 = fma2(bc2(__uint_as_float(q.w)), eb, acc1);
               m1 = fmaxf(m1, fmaxf(ea.x, eb.x));
               m2 = fmaxf(m2, fmaxf(ea.y, eb.y));
               m3 = fmaxf(m3, fmaxf(ea.x * ea.y, eb.x * eb.y));
@@ -211,38 +412,25 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
             for (; a < e_end; a += 16) {
               const uint4 q = lds128u(a);
               const float2 ea = lds64(tab + q.x), eb = lds64(tab + q.z);
-              const float wa = __uint_as_float(q.y), wb = __uint_as_float(q.w);
-              ax0 = fmaf(wa, ea.x, ax0); ay0 = fmaf(wa, ea.y, ay0);
-              ax1 = fmaf(wb, eb.x, ax1); ay1 = fmaf(wb, eb.y, ay1);
+              acc0 = fma2(bc2(__uint_as_float(q.y)), ea, acc0);
+              acc1 = fma2(bc2(__uint_as_float(q.w)), eb, acc1);
             }
           }
-          const float SX = own.x * (ax0 + ax1), SY = own.y * (ay0 + ay1);
+          const float SX = own.x * (acc0.x + acc1.x), SY = own.y * (acc0.y + acc1.y);
           lp_acc -= 0.5f * (SX + SY);  // every match is in two lists
           gx = -SX;
           gy = -SY;
         } else {
-          gx = gy = 0.0f;
-          float lp2 = 0.0f, lpw = 0.0f, m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
-#pragma unroll 2
-          for (; a < e_end; a += 16) {
-            const uint4 q = lds128u(a);  // one entry: off, w, w*y_x, w*y_y
-            const float2 ea = lds64(tab + q.x);
-            const float w = __uint_as_float(q.y), wyx = __uint_as_float(q.z), wyy = __uint_as_float(q.w);
-            const float X = own.x * ea.x, Y = own.y * ea.y;
-            const float Xc = fminf(X, 15.0f), Yc = fminf(Y, 15.0f);
-            if (home) {  // warp-uniform
-              lp2 = fmaf(wyx, lg2_approx(Xc), lp2);
-              lp2 = fmaf(wyy, lg2_approx(Yc), lp2);
-              lpw = fmaf(w, Xc + Yc, lpw);
-              m1 = fmaxf(m1, Xc);
-              m2 = fmaxf(m2, Yc);
-              m3 = fmaxf(m3, Xc * Yc);
-            }
-            gx += X < 15.0f ? fmaf(-w, X, wyx) : 0.0f;
-            gy += Y < 15.0f ? fmaf(-w, Y, wyy) : 0.0f;
+          float lp = 0.0f, m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
+          if (fast1) {
+            if (home) rate_piece_clip<true, true>(a, e_end, own, tab, lp, m1, m2, m3, gx, gy);
+            else rate_piece_clip<true, false>(a, e_end, own, tab, lp, m1, m2, m3, gx, gy);
+          } else {
+            if (home) rate_piece_clip<false, true>(a, e_end, own, tab, lp, m1, m2, m3, gx, gy);
+            else rate_piece_clip<false, false>(a, e_end, own, tab, lp, m1, m2, m3, gx, gy);
           }
           if (home) {
-            lp_acc += fmaf(lp2, kLn2, -lpw);
+            lp_acc += lp;
             if (m1 > best[0]) { best[0] = m1; besth[0] = hoff; }
             if (m2 > best[1]) { best[1] = m2; besth[1] = hoff; }
             if (m3 > best[2]) { best[2] = m3; besth[2] = hoff; }
@@ -257,68 +445,77 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
           }
         }
         if (L.flags & kTeamLast) put_raw<false>(kp, ln, (int)L.team, g, hacc);
+        if (k == 0 && a - a0 <= kp.stage_bytes / 2) BPLX_STAMP(17);
       }
       ring.release(k);
     }
   }
-  const uint32_t b2_0 = __ldg(kp.warp_b2 + vwarp), b2_1 = __ldg(kp.warp_b2 + vwarp + 1);
+  const uint32_t b2_0 = wb.b2[vwarp], b2_1 = wb.b2[vwarp + 1];
   ring.begin(kp.stream2 + b2_0, b2_1 - b2_0);  // tau pieces start streaming in during the bounds step
 
+  BPLX_STAMP(3);
   // ---- bounds (bpl/_util.py:17-31) ------------------------------------------------------------------
-  // the maxima and the piece each came from.  One CTA: a 64-bit atomicMax on (value bits | piece offset).  A cluster:
-  // 32-bit atomics only (value first, then the owners of the maximum agree on a piece) -- the 64-bit max is a CAS loop
-  // for the local CTA and a remote atomic for the others, and the two do not exclude each other (measured lost updates).
-  if (S == 1) {
+  // the maxima and the piece each came from, with 32-bit atomics in two steps: the value first, then the owners of the
+  // maximum agree on the lowest piece offset.  (A 64-bit max on value | offset is a CAS loop in shared memory -- about
+  // 1 us with 20 warps on the same 32 words -- and in a cluster the local CAS loop and the remote atomic do not
+  // exclude each other: measured lost updates.)
 #pragma unroll
-    for (int q = 0; q < 3; q++)
-      if (best[q] > 0.0f)
-        atomicMax(red_best + q * 32 + lane, ((unsigned long long)__float_as_uint(best[q]) << 32) | besth[q]);
-    __syncthreads();
+  for (int q = 0; q < 3; q++)
+    if (best[q] > 0.0f) dsm_atom_max_u32(a_best + (uint32_t)(q * 32 + lane) * 4u, __float_as_uint(best[q]));
+  sync_all();
+  BPLX_STAMP(14);
 #pragma unroll
-    for (int q = 0; q < 3; q++) {
-      const unsigned long long bq = red_best[q * 32 + lane];
-      best[q] = __uint_as_float((uint32_t)(bq >> 32));
-      besth[q] = (uint32_t)bq;
-    }
-  } else {
-#pragma unroll
-    for (int q = 0; q < 3; q++)
-      if (best[q] > 0.0f) dsm_atom_max_u32(a_best + (uint32_t)(q * 32 + lane) * 4u, __float_as_uint(best[q]));
-    cg::this_cluster().sync();
-#pragma unroll
-    for (int q = 0; q < 3; q++) {
-      const float gq = __uint_as_float(dsm_ld_u32(a_best + (uint32_t)(q * 32 + lane) * 4u));
-      if (best[q] == gq && gq > 0.0f) dsm_atom_min_u32(a_best + (uint32_t)((3 + q) * 32 + lane) * 4u, besth[q]);
-      best[q] = gq;
-    }
-    cg::this_cluster().sync();
-#pragma unroll
-    for (int q = 0; q < 3; q++) besth[q] = dsm_ld_u32(a_best + (uint32_t)((3 + q) * 32 + lane) * 4u);
+  for (int q = 0; q < 3; q++) {
+    const float gq = __uint_as_float(dsm_ld_u32(a_best + (uint32_t)(q * 32 + lane) * 4u));
+    if (best[q] == gq && gq > 0.0f) dsm_atom_min_u32(a_best + (uint32_t)((3 + q) * 32 + lane) * 4u, besth[q]);
+    best[q] = gq;
   }
+  sync_all();
+  BPLX_STAMP(15);
+#pragma unroll
+  for (int q = 0; q < 3; q++) besth[q] = dsm_ld_u32(a_best + (uint32_t)((3 + q) * 32 + lane) * 4u);
+  // no rate of these 32 chains at the clip: phase 2 takes the short form of the clipped arithmetic
+  const bool noclip = CLIP && __all_sync(kFull, best[0] < 15.0f && best[1] < 15.0f);
   const float Lam = fmaxf(best[0], best[1]);
   const int qlam = best[0] >= best[1] ? 0 : 1;
+  // arg-max search, loads first: the headers of each chain's two arg-max pieces and this warp's first candidate entry
+  // of each (its address needs only the piece offset; past the end of a short piece it reads a neighbour or the zero
+  // slack behind the stream, and is ignored) -- one round trip to L2 for all four
+  bool s_need[2];
+  uint32_t s_hoff[2], s_off0[2];
+  uint4 s_hdr[2];
+#pragma unroll
+  for (int which = 0; which < 2; which++) {
+    s_need[which] = (which == 0 || best[2] > 1.0f) && best[which == 0 ? qlam : 2] > 0.0f;  // UB = 1: no dependence on the rates
+    s_hoff[which] = s_need[which] ? (which == 0 ? (qlam == 0 ? besth[0] : besth[1]) : besth[2]) : b1_0;
+    const unsigned char* base = kp.stream1 + s_hoff[which];
+    s_off0[which] = __ldg(reinterpret_cast<const uint32_t*>(base + 16 + (size_t)vwarp * ESZ));
+    s_hdr[which] = __ldg(reinterpret_cast<const uint4*>(base));
+  }
   const float LB = -1.0f / Lam;
   const float UB = fminf(1.0f / best[2], 1.0f);
   const float cc = fmaf(r, UB - LB, LB);
 
+  BPLX_STAMP(4);
   // ---- arg-max search: virtual warp w looks at entries w, w+VW, ... of each chain's two arg-max pieces -----------
-#pragma unroll 1
+#pragma unroll
   for (int which = 0; which < 2; which++) {
-    const bool need = (which == 0 || best[2] > 1.0f) && best[which == 0 ? qlam : 2] > 0.0f;  // UB = 1: no dependence on the rates
-    const uint32_t hoff = need ? (which == 0 ? (qlam == 0 ? besth[0] : besth[1]) : besth[2]) : b1_0;
+    const bool need = s_need[which];
     const float target = which == 0 ? Lam : best[2];
     const int q = which == 0 ? qlam : 2;
-    const Hdr L = unpack_hdr(__ldg(reinterpret_cast<const uint4*>(kp.stream1 + hoff)));
+    const unsigned char* ent = kp.stream1 + s_hoff[which] + 16;
+    uint32_t off_next = s_off0[which];
+    const Hdr L = unpack_hdr(s_hdr[which]);
     const uint32_t n = need ? L.n0 : 0u;
     float2 own = lds64(tab + (need ? L.own_off : 0u));
     if (L.kind >= kH0) { const float s = own.x; own.x = own.y; own.y = s; }
-    const unsigned char* ent = kp.stream1 + hoff + 16;
     const uint32_t nmax = __reduce_max_sync(kFull, n);
     uint32_t found = 0xffffffffu, info = 0u;
-#pragma unroll 4
+#pragma unroll 1
     for (uint32_t i = vwarp; i < nmax; i += VW) {
+      const uint32_t off = off_next;
+      if (i + VW < nmax) off_next = __ldg(reinterpret_cast<const uint32_t*>(ent + (size_t)(i + VW) * ESZ));
       if (i < n) {
-        const uint32_t off = __ldg(reinterpret_cast<const uint32_t*>(ent + (size_t)i * ESZ));
         const float2 ea = lds64(tab + off);
         const float X = own.x * ea.x, Y = own.y * ea.y;
         float val;
@@ -341,6 +538,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
       dsm_st_u64(a_found + (uint32_t)(which * 32 + lane) * 8u, (unsigned long long)found | ((unsigned long long)info << 32));
   }
 
+  BPLX_STAMP(5);
   // ---- phase 2: tau terms (bpl/_util.py:54-91) -----------------------------------------------------
   float gc = 0.0f;
   {
@@ -349,6 +547,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
     for (uint32_t k = 0; k < nst; k++) {
       uint32_t bytes;
       const uint32_t a0 = ring.acquire(k, &bytes);
+      if (k == 0) BPLX_STAMP(18);
       uint32_t a = a0;
       const uint32_t aend = a0 + bytes;
       while (a + kp.min_piece2 <= aend) {
@@ -361,65 +560,14 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
         float2 own = lds64(tab + L.own_off);
         if (L.kind >= kH0) { const float s = own.x; own.x = own.y; own.y = s; }
         const bool home = (L.kind & 1) == 0;
-        float lt = 0.0f, uxy = 0.0f, sxy_x = 0.0f, sxy_y = 0.0f;
-        {  // tau = 1 - c X Y
-          const float Pxy = own.x * own.y;
-          const uint32_t e_end = a + L.n0 * (uint32_t)sizeof(Entry);
-#pragma unroll 1
-          for (; a < e_end; a += 16) {
-            const uint4 q = lds128u(a);  // two entries (opponent row offset, w)
-#pragma unroll
-            for (int j = 0; j < 2; j++) {
-              const float2 ea = lds64(tab + (j ? q.z : q.x));
-              const float w = __uint_as_float(j ? q.w : q.y);
-              if (CLIP) {
-                const float Xr = own.x * ea.x, Yr = own.y * ea.y;
-                const float t = fminf(Xr, 15.0f) * fminf(Yr, 15.0f);
-                const float tau = fmaxf(fmaf(-cc, t, 1.0f), 0.0f);
-                const float val = (w * t) * rcp_approx(tau);
-                uxy += val;
-                sxy_x += Xr < 15.0f ? val : 0.0f;
-                sxy_y += Yr < 15.0f ? val : 0.0f;
-                if (home) lt = fmaf(w, lg2_approx(tau), lt);
-              } else {
-                const float t = Pxy * (ea.x * ea.y);
-                const float tau = fmaxf(fmaf(-cc, t, 1.0f), 0.0f);
-                uxy = fmaf(w * t, rcp_approx(tau), uxy);
-                if (home) lt = fmaf(w, lg2_approx(tau), lt);
-              }
-            }
-          }
-        }
-        float u1[2] = {0.0f, 0.0f}, s1[2] = {0.0f, 0.0f};  // tau = 1 + c X, then tau = 1 + c Y
-#pragma unroll
-        for (int c = 0; c < 2; c++) {
-          const float oc = c == 0 ? own.x : own.y;
-          const uint32_t e_end = a + (c == 0 ? L.n1 : L.n2) * (uint32_t)sizeof(Entry);
-          float u = 0.0f, sm = 0.0f;
-#pragma unroll 1
-          for (; a < e_end; a += 16) {
-            const uint4 q = lds128u(a);
-#pragma unroll
-            for (int j = 0; j < 2; j++) {
-              const float Rr = oc * lds32(tab + (j ? q.z : q.x));  // `off` already selects .x or .y
-              const float w = __uint_as_float(j ? q.w : q.y);
-              const float R = CLIP ? fminf(Rr, 15.0f) : Rr;
-              const float tau = fmaxf(fmaf(cc, R, 1.0f), 0.0f);
-              const float val = (w * R) * rcp_approx(tau);
-              u += val;
-              if (CLIP) sm += Rr < 15.0f ? val : 0.0f;
-              if (home) lt = fmaf(w, lg2_approx(tau), lt);
-            }
-          }
-          u1[c] = u;
-          s1[c] = CLIP ? sm : u;
-        }
-        if (!CLIP) sxy_x = sxy_y = uxy;
+        float lt, du, gx, gy;
+        if (!CLIP) tau_piece<kTauPlain>(a, L, own, home, cc, tab, lt, du, gx, gy);
+        else if (noclip) tau_piece<kTauUnclipped>(a, L, own, home, cc, tab, lt, du, gx, gy);
+        else tau_piece<kTauClipped>(a, L, own, home, cc, tab, lt, du, gx, gy);
         if (home) {
           lp_acc = fmaf(lt, kLn2, lp_acc);
-          gc += u1[0] + u1[1] - uxy;
+          gc += du;
         }
-        const float gx = cc * (s1[0] - sxy_x), gy = cc * (s1[1] - sxy_y);
         add_own(g, L.kind, gx, gy);
         if (kp.Cf > 0) {
           cacc += L.kind == kH1 ? gx - gy : gy - gx;
@@ -433,6 +581,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
       ring.release(k);
     }
   }
+  BPLX_STAMP(6);
   red_gc[warp * 32 + lane] = gc;
   __syncthreads();
   gc = 0.0f;
@@ -450,6 +599,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
     if (vwarp == 0 && kp.w11 != 0.0f) lp_acc = fmaf(kp.w11, logf(t11), lp_acc);
   }
 
+  BPLX_STAMP(7);
   // ---- arg-max fix-up: every warp works out the two matches of its chain and folds
   //      them into the team pass below ---------------------------------------------------------------------
   Fixup fx;
@@ -459,8 +609,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
   for (int which = 0; which < 2; which++) {
     const unsigned long long fi = dsm_ld_u64(a_found + (uint32_t)(which * 32 + lane) * 8u);
     const uint32_t packed = (uint32_t)fi;
-    fx.teams[which] = 0xffffffffu;
-    fx.vts[which] = 0u;
+    fx.teams[which] = 0xffffffffu;  // (unused here: the team pass matches virtual-team ranges, no v_team look-up)
+    fx.vts[which] = 0xffffffffu;    // none
     fx.vx[which] = fx.vy[which] = 0.0f;
     if (packed != 0xffffffffu) {  // else: UB = 1 (or nothing matched: cannot happen, same arithmetic as phase 1)
       const uint32_t info = (uint32_t)(fi >> 32);
@@ -480,12 +630,12 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
       }
       fx.h1 |= (h1 ? 1u : 0u) << which;
       fx.vts[which] = own_v | (opp_v << 16);
-      fx.teams[which] = (uint32_t)__ldg(kp.v_team + own_v) | ((uint32_t)__ldg(kp.v_team + opp_v) << 16);
       if (kp.Cf > 0)
         fx.confs |= ((uint32_t)__ldg(kp.v_conf + own_v) | ((uint32_t)__ldg(kp.v_conf + opp_v) << 8)) << (16 * which);
     }
   }
 
+  BPLX_STAMP(8);
   // ---- team pass: raw slots -> parameter gradients, priors, hyper-parameter sums ---------------------------
   const bool has_rho = !dc;
   float u = 0.5f, rho = 0.0f, inv_s2 = 1.0f;
@@ -505,6 +655,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
 
     for (int t = vwarp; t < kp.T; t += VW) {
       const float za = ln.ld(o.za + t), zd = ln.ld(o.zd + t);
+      const uint32_t v0 = (uint32_t)__ldg(kp.team_vptr + t), nv = (uint32_t)__ldg(kp.team_vptr + t + 1) - v0;
       const float4 ys = __ldg(reinterpret_cast<const float4*>(kp.yteam + (size_t)t * 8));
       const float2 ys2 = __ldg(reinterpret_cast<const float2*>(kp.yteam + (size_t)t * 8 + 4));
       float ra = ld_cg(ln.g(o.za + t)) + ys.x;
@@ -520,8 +671,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
       }
 #pragma unroll
       for (int which = 0; which < 2; which++) {
-        if ((fx.teams[which] & 0xffffu) == (uint32_t)t) fold_fixup(fx, which, 0, ra, rd, rx);
-        if ((fx.teams[which] >> 16) == (uint32_t)t) fold_fixup(fx, which, 1, ra, rd, rx);
+        // the arg-max match's own / opponent virtual team is one of this team's
+        if ((fx.vts[which] & 0xffffu) - v0 < nv) fold_fixup(fx, which, 0, ra, rd, rx);
+        if ((fx.vts[which] >> 16) - v0 < nv) fold_fixup(fx, which, 1, ra, rd, rx);
       }
       float p_za, p_zd;
       if (has_rho) {  // za ~ N(0,1), zd ~ N(rho za, sqrt(1-rho^2))  (extended_dixon_coles.py:165-174)
@@ -569,11 +721,12 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
     for (int j = j0; j < j1; j++) s += ld_cg(ln.sc + (size_t)__ldg(kp.conf_vlist + j) * kp.Cpad);
 #pragma unroll
     for (int ws = 0; ws < 4; ws++)
-      if (fx.teams[ws >> 1] != 0xffffffffu && ((fx.confs >> (8 * ((ws >> 1) * 2 + (ws & 1)))) & 0xffu) == (uint32_t)k)
+      if (fx.vts[ws >> 1] != 0xffffffffu && ((fx.confs >> (8 * ((ws >> 1) * 2 + (ws & 1)))) & 0xffu) == (uint32_t)k)
         s += fixup_conf(fx, ws >> 1, ws & 1);
     if (ln.active) *ln.g(o.conf + k) = s;
   }
 
+  BPLX_STAMP(9);
   // ---- cross-warp reduction of the hyper accumulators (table area is reused) ----------------------------
   float* part = reinterpret_cast<float*>(smem + kp.epi_part);
   {
@@ -593,6 +746,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
     cg::this_cluster().sync();
     if (crank != 0) return;
   }
+  BPLX_STAMP(10);
   // the epilogue items are dealt round-robin to the warps: scalar hyper sites, u, corr_coef_raw, coefficients
   auto total = [&](int row) {
     float s = 0.0f;
@@ -644,6 +798,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
       if (ln.active) *ln.g(d) = s;
     }
   }
+  BPLX_STAMP(11);
   red_gc[warp * 32 + lane] = lp;  // every warp read its gc sum before the previous barrier: the rows are free
   __syncthreads();
   if (warp == 0 && ln.active) {
@@ -655,7 +810,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
 
 // ---- host launcher --------------------------------------------------------------------------------------
 template <bool CLIP>
-static int launch_t(const KernelParams& kp, cudaStream_t stream, bool set_attr) {
+static int launch_t(const KernelParams& kp, const WarpBounds& wb, cudaStream_t stream, bool set_attr) {
   auto* fn = &logdensity_kernel<CLIP>;
   if (set_attr) {
     BPLX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -675,9 +830,9 @@ static int launch_t(const KernelParams& kp, cudaStream_t stream, bool set_attr) 
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    BPLX_CUDA(cudaLaunchKernelEx(&cfg, fn, kp));
+    BPLX_CUDA(cudaLaunchKernelEx(&cfg, fn, kp, wb));
   } else {
-    fn<<<groups, kp.nwarps * 32, kp.smem_total, stream>>>(kp);
+    fn<<<groups, kp.nwarps * 32, kp.smem_total, stream>>>(kp, wb);
   }
   BPLX_CUDA(cudaGetLastError());
   note_launch(1);
@@ -708,11 +863,18 @@ int logdensity_max_clusters(const KernelParams& kp, int split) {
   return kp.clip ? max_clusters_t<true>(kp, split) : max_clusters_t<false>(kp, split);
 }
 
-int logdensity_set_attributes(const KernelParams& kp) {
-  return kp.clip ? launch_t<true>(kp, nullptr, true) : launch_t<false>(kp, nullptr, true);
+#ifdef BPLX_TIMELINE
+extern "C" int bplx_timeline_read(unsigned long long* out) {
+  return cudaMemcpyFromSymbol(out, g_timeline, sizeof(g_timeline)) == cudaSuccess ? 0 : -1;
 }
-int launch_logdensity(const KernelParams& kp, cudaStream_t stream) {
-  return kp.clip ? launch_t<true>(kp, stream, false) : launch_t<false>(kp, stream, false);
+#endif
+
+int logdensity_set_attributes(const KernelParams& kp) {
+  static const WarpBounds none{};
+  return kp.clip ? launch_t<true>(kp, none, nullptr, true) : launch_t<false>(kp, none, nullptr, true);
+}
+int launch_logdensity(const KernelParams& kp, const WarpBounds& wb, cudaStream_t stream) {
+  return kp.clip ? launch_t<true>(kp, wb, stream, false) : launch_t<false>(kp, wb, stream, false);
 }
 
 }  // namespace bplx

@@ -109,6 +109,12 @@ struct HyperDesc {
 };
 
 // everything the kernel needs; device pointers are filled by api.cu after upload
+// byte ranges of the virtual warps' phase-1 / phase-2 streams for the split in use, as a kernel parameter (constant bank):
+// a warp needs them to start its TMA ring, and a global load there is a round trip to L2 on the critical path
+struct WarpBounds {
+  uint32_t b1[kMaxSplit * kMaxWarps + 1], b2[kMaxSplit * kMaxWarps + 1];
+};
+
 struct KernelParams {
   int model, T, K, Cf, V;
   int G;           // DYNAMIC: gameweeks (else 0)

@@ -16,6 +16,7 @@ struct bplx_problem {
   const unsigned char* s2[bplx::kNumSplits] = {};
   const uint32_t* wb1[bplx::kNumSplits] = {};
   const uint32_t* wb2[bplx::kNumSplits] = {};
+  bplx::WarpBounds wb[bplx::kNumSplits] = {};  // host copies of wb1 / wb2 (static models): passed by value at launch
   int max_clusters[bplx::kNumSplits] = {0, 0, 0, 0};
   std::vector<void*> dev_allocs;
   // host-variant staging (lazily grown, guarded by mu)
@@ -33,7 +34,7 @@ struct bplx_problem {
 };
 
 namespace bplx {
-int launch_logdensity(const KernelParams& kp, cudaStream_t stream);
+int launch_logdensity(const KernelParams& kp, const WarpBounds& wb, cudaStream_t stream);
 int logdensity_set_attributes(const KernelParams& kp);
 int logdensity_max_clusters(const KernelParams& kp, int split);  // co-resident clusters of `split` CTAs, 0 if unsupported
 int launch_logdensity_dynamic(const KernelParams& kp, cudaStream_t stream);

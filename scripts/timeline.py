@@ -1,0 +1,32 @@
+"""Per-warp region timeline of K1 on CTA 0 (debug library built with -DBPLX_TIMELINE, see logdensity.cu).
+usage: python scripts/timeline.py [cfg2|cfg3|cfg1] [radius]"""
+import ctypes, os, sys, numpy as np, torch
+sys.path.insert(0, '.')
+from bpl_next_b200 import _abi
+_abi.LIB_PATH = os.path.join(os.path.dirname(_abi.LIB_PATH), "libbplx_timeline.so")
+import bench
+from bpl_next_b200 import Problem
+wl = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
+radius = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0  # theta ~ U(-radius, radius)
+arr, C, desc = bench.workload(wl)
+p = Problem(arr)
+lib = _abi.lib()
+sets = [(torch.rand((p.D, C), device="cuda") * 2 - 1) * radius for _ in range(60)]  # rotate: theta misses L2 like in the bench
+names = ["start", "prologue done", "after barrier P", "phase 1 done", "after bounds barrier", "search done", "phase 2 done",
+         "after barrier B+gc", "fix-up done", "team pass done", "after partial barrier", "epilogue done",
+         "(prologue) first theta load back", "(prologue) hyper + first team loads back", "(bounds) after max barrier", "(bounds) after offset barrier", "(phase 1) first stage acquired", "(phase 1) first piece done", "(phase 2) first stage acquired", "kernel entry"]
+acc = None
+for it in range(len(sets)):
+    p.logdensity(sets[it], chain_minor=True)
+    torch.cuda.synchronize()
+    buf = (ctypes.c_ulonglong * (32 * 24))()
+    lib.bplx_timeline_read.argtypes = [ctypes.c_void_p]
+    assert lib.bplx_timeline_read(buf) == 0
+    t = np.array(buf, dtype=np.uint64).reshape(32, 24)[: p.stats()["warps"], :20].astype(np.float64)
+    t -= t[:, 19].min()
+    if it >= 10:
+        acc = t if acc is None else acc + t
+acc /= (len(sets) - 10)
+print(desc, "warps", acc.shape[0], "radius", radius)
+for i, n in enumerate(names):
+    print(f"{n:24s} min {acc[:, i].min() / 1e3:7.2f} us   max {acc[:, i].max() / 1e3:7.2f} us")
