@@ -123,6 +123,17 @@ __device__ __forceinline__ void put_raw(const KernelParams& kp, const Lane& ln, 
   }
 }
 
+// the same sums of one side's tau lists, stored to that side's shared-memory slots (slot i of a chain at q[i * 32])
+__device__ __forceinline__ void put_side(const KernelParams& kp, float* q, const float (&g)[6], float& hacc) {
+  q[0] = g[eAh1] + g[eAa1] + g[eA0];
+  q[32] = -(g[eBh1] + g[eBa1] + g[eB0]);
+  const float rx[4] = {g[eAh1], g[eAa1], -g[eBh1], -g[eBa1]};
+  if (kp.ndec == 0) hacc += rx[0];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+    if (i < kp.ndec) q[(2 + i) * 32] = rx[i];
+}
+
 // Per-warp TMA ring over a contiguous global byte stream (the warp's list pieces of one phase).
 // One elected lane issues cp.async.bulk copies of one stage into the warp's private ring and every
 // lane waits on the stage's mbarrier before reading it; the same warp produces and consumes, so a

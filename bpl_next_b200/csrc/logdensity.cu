@@ -137,13 +137,15 @@ __device__ __forceinline__ void tau_piece(uint32_t& a, const Hdr& L, const float
       float2 tau = fma2(bc2(-cc), t, one);
       tau.x = fmaxf(tau.x, 0.0f);
       tau.y = fmaxf(tau.y, 0.0f);
-      const float2 val = mul2(mul2(w, t), make_float2(rcp_approx(tau.x), rcp_approx(tau.y)));
-      uxy = add2(uxy, val);
+      // sums of (w t) / tau as explicit fused multiply-adds, packed or scalar: the same rounding in every form (left
+      // as mul + add, ptxas contracts the packed pair into an FFMA2 in one form and not in another)
+      const float2 wt = mul2(w, t), rc = make_float2(rcp_approx(tau.x), rcp_approx(tau.y));
+      uxy = fma2(wt, rc, uxy);
       if (MODE == kTauClipped) {
-        if (ra.x < 15.0f) sxy_x.x += val.x;
-        if (rb.x < 15.0f) sxy_x.y += val.y;
-        if (ra.y < 15.0f) sxy_y.x += val.x;
-        if (rb.y < 15.0f) sxy_y.y += val.y;
+        if (ra.x < 15.0f) sxy_x.x = fmaf(wt.x, rc.x, sxy_x.x);
+        if (rb.x < 15.0f) sxy_x.y = fmaf(wt.y, rc.y, sxy_x.y);
+        if (ra.y < 15.0f) sxy_y.x = fmaf(wt.x, rc.x, sxy_y.x);
+        if (rb.y < 15.0f) sxy_y.y = fmaf(wt.y, rc.y, sxy_y.y);
       }
       if (home) lt = fma2(w, make_float2(lg2_approx(tau.x), lg2_approx(tau.y)), lt);
     }
@@ -163,11 +165,11 @@ __device__ __forceinline__ void tau_piece(uint32_t& a, const Hdr& L, const float
       float2 tau = fma2(bc2(cc), R, one);
       tau.x = fmaxf(tau.x, 0.0f);
       tau.y = fmaxf(tau.y, 0.0f);
-      const float2 val = mul2(mul2(w, R), make_float2(rcp_approx(tau.x), rcp_approx(tau.y)));
-      u = add2(u, val);
+      const float2 wr = mul2(w, R), rc = make_float2(rcp_approx(tau.x), rcp_approx(tau.y));
+      u = fma2(wr, rc, u);
       if (MODE == kTauClipped) {
-        if (Rr.x < 15.0f) sm.x += val.x;
-        if (Rr.y < 15.0f) sm.y += val.y;
+        if (Rr.x < 15.0f) sm.x = fmaf(wr.x, rc.x, sm.x);
+        if (Rr.y < 15.0f) sm.y = fmaf(wr.y, rc.y, sm.y);
       }
       if (home) lt = fma2(w, make_float2(lg2_approx(tau.x), lg2_approx(tau.y)), lt);
     }
@@ -268,6 +270,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
   float lp_acc = 0.0f;  // this thread's share of the log-density
   float hacc = 0.0f;    // DIXON_COLES: d/d home_advantage
 
+  // phase-2 slot sums per (side, team) when the plan deals a team's two sides to different warps (plan.cc)
+  const bool p2s = kp.smem_p2 != 0 && S == 1;
+  float* p2_tab = reinterpret_cast<float*>(smem + kp.smem_p2);
   uint32_t* red_clip = reinterpret_cast<uint32_t*>(smem + kp.smem_red_cl);  // [2][32] keys, this CTA's own (CLIP models)
   if (warp == 0) {
     const uint32_t zr = (uint32_t)kp.V * kRowBytes;  // zero rows used by padding entries
@@ -301,6 +306,13 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
     for (int t = warp; t < kp.T; t += W) {
       const TeamIn in = nx;
       if (t + W < kp.T) nx = load_team(t + W);
+      if (p2s) {  // phase-2 slot tables of this team: a side without tau lists is never written
+#pragma unroll
+        for (int side = 0; side < 2; side++)
+#pragma unroll
+          for (int i = 0; i < 6; i++)
+            if (i < 2 + ndec) p2_tab[((side * kp.T + t) * (2 + ndec) + i) * 32 + lane] = 0.0f;
+      }
       float am = 0.0f, dm = hy.mu_d;
 #pragma unroll
       for (int j = 0; j < 4; j++) {  // (absent covariates: x = 0, the sums do not change)
@@ -363,7 +375,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
   // every rate is exp(A-side exponent of one virtual team + B-side exponent of another): with the two maxima below
   // log 15 (less a margin for the rounding of exp and the product) no rate of the chain can be at the clip
   bool fast1 = false;
-  if (CLIP) fast1 = __all_sync(kFull, key_float(red_clip[lane]) + key_float(red_clip[32 + lane]) < 2.707f);
+  if (CLIP) fast1 = __all_sync(kFull, key_float(red_clip[lane]) + key_float(red_clip[32 + lane]) < 2.707f) && !(kp.force_clip_forms & 1);
   // ---- phase 1 ----------------------------------------------------------------------------------
   float best[3] = {0.0f, 0.0f, 0.0f};
   uint32_t besth[3] = {0u, 0u, 0u};  // byte offset (in stream1) of the header of the piece that holds the maximum
@@ -475,7 +487,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
 #pragma unroll
   for (int q = 0; q < 3; q++) besth[q] = dsm_ld_u32(a_best + (uint32_t)((3 + q) * 32 + lane) * 4u);
   // no rate of these 32 chains at the clip: phase 2 takes the short form of the clipped arithmetic
-  const bool noclip = CLIP && __all_sync(kFull, best[0] < 15.0f && best[1] < 15.0f);
+  const bool noclip = CLIP && __all_sync(kFull, best[0] < 15.0f && best[1] < 15.0f) && !(kp.force_clip_forms & 2);
   const float Lam = fmaxf(best[0], best[1]);
   const int qlam = best[0] >= best[1] ? 0 : 1;
   // arg-max search, loads first: the headers of each chain's two arg-max pieces and this warp's first candidate entry
@@ -576,7 +588,10 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
             cacc = 0.0f;
           }
         }
-        if (L.flags & kTeamLast) put_raw<true>(kp, ln, (int)L.team, g, hacc);
+        if (L.flags & kTeamLast) {
+          if (p2s) put_side(kp, p2_tab + (((L.kind & 1) * kp.T + L.team) * (2 + ndec)) * 32 + lane, g, hacc);
+          else put_raw<true>(kp, ln, (int)L.team, g, hacc);
+        }
       }
       ring.release(k);
     }
@@ -667,6 +682,17 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
         if (i < ndec) {
           dec[i] = ln.ld(o.dec[i] + t);
           rx[i] += ld_cg(ln.g(o.dec[i] + t));
+        }
+      }
+      if (p2s) {  // home-side sums, then away-side sums
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+          const float* q = p2_tab + ((side * kp.T + t) * (2 + ndec)) * 32 + lane;
+          ra += q[0];
+          rd += q[32];
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+            if (i < ndec) rx[i] += q[(2 + i) * 32];
         }
       }
 #pragma unroll

@@ -411,11 +411,55 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err, int 
   }
   kp.nwarps = W;
   kp.stage_bytes = stage;
+  kp.force_clip_forms = 0;
+  if (const char* e = getenv("BPLX_CLIP_FORMS")) kp.force_clip_forms = atoi(e);
   {  // a cluster only pays when one CTA's share of the walk is long compared with the cluster barriers (~1 us each):
      // measured, configs[1] data (1.5 k cost units per warp) loses 50 %, configs[2] data (50 k) gains 3.4x
     std::vector<std::vector<int>> t1, t2;
     const double span = assign(cost1, W, &t1) + assign(cost2, W, &t2);
     kp.split_hint = span >= 32000.0 ? 8 : span >= 16000.0 ? 4 : span >= 8000.0 ? 2 : 1;
+  }
+
+  // ---- few teams: phase 2 by (team, side) ------------------------------------------------------------
+  // With about as many teams as warps the longest tau list decides phase 2 (configs[1]: 13..74 entries per team on 20
+  // warps).  The split-1 plan may then deal a team's home-side (H1, H0) and away-side (A1, A0) lists to different
+  // warps; each side's slot sums go to its own shared-memory table (plain stores) and the team pass adds the two in a
+  // fixed order, so the result stays deterministic.  Not with confederations (their per-virtual-team sums are
+  // red.add'ed by the list owner), not in a cluster (the tables would be remote).
+  std::vector<std::vector<int>> w2_items;  // per warp: team * 4 + side mask (1 home side, 2 away side, 3 both)
+  kp.smem_p2 = 0;
+  {
+    std::vector<std::pair<int, double>> units;
+    for (int t = 0; t < T; t++)
+      for (int side = 0; side < 2; side++) {
+        double c = 0.0;
+        for (int v = P.team_vptr[t]; v < P.team_vptr[t + 1]; v++)
+          for (int k = side; k < 4; k += 2) {
+            const size_t n = raw2[(size_t)v * 4 + k].size();
+            if (n) c += 60.0 * (1.0 + (double)n / 100.0) + 12.0 * (double)n;
+          }
+        if (c > 0.0) units.push_back({t * 4 + (1 << side), c + 30.0});
+      }
+    std::stable_sort(units.begin(), units.end(), [](const auto& a, const auto& b) { return a.second > b.second; });
+    std::vector<double> load(W, 0.0);
+    std::vector<std::vector<int>> items(W);
+    for (const auto& u : units) {
+      int best = 0;
+      for (int w = 1; w < W; w++)
+        if (load[w] < load[best]) best = w;
+      load[best] += u.second;
+      items[best].push_back(u.first);
+    }
+    for (auto& v : items) std::sort(v.begin(), v.end());
+    std::vector<std::vector<int>> t2;
+    const double span_team = assign(cost2, W, &t2);
+    const double span_unit = units.empty() ? 0.0 : *std::max_element(load.begin(), load.end());
+    const uint32_t p2_bytes = 2u * (uint32_t)T * (uint32_t)(2 + kp.ndec) * 128u;
+    const bool off = getenv("BPLX_NO_P2SPLIT") != nullptr;
+    if (!off && Cf <= 0 && span_unit < 0.85 * span_team && smem_need(W, stage) + p2_bytes <= kSmemMax) {
+      w2_items = items;
+      kp.smem_p2 = 1;  // (the offset is set in the carve-up below)
+    }
   }
 
   // ---- emit the streams ---------------------------------------------------------------------------
@@ -427,15 +471,22 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err, int 
   // one set of streams per split: Wtot = W * split virtual warps (virtual warp = cluster rank * W + warp)
   auto emit = [&](int Wtot, std::vector<unsigned char>* s1, std::vector<unsigned char>* s2, std::vector<uint32_t>* wb1,
                   std::vector<uint32_t>* wb2) {
+  const bool by_side = kp.smem_p2 != 0 && Wtot == kp.nwarps;  // phase 2 of the split-1 plan dealt by (team, side)
   const int W = Wtot;  // (shadows the per-CTA warp count inside the emitter)
   assign(cost1, W, &w1);
   assign(cost2, W, &w2);
+  std::vector<std::vector<int>> it1(W), it2(W);
+  for (int w = 0; w < W; w++) {
+    for (int t : w1[w]) it1[w].push_back(t * 4 + 3);
+    for (int t : w2[w]) it2[w].push_back(t * 4 + 3);
+  }
+  if (by_side) it2 = w2_items;
   P.n1 = P.n2 = P.n1_padded = P.n2_padded = P.nlists1 = P.nlists2 = 0;
   wb1->assign(W + 1, 0);
   wb2->assign(W + 1, 0);
   for (int phase = 1; phase <= 2; phase++) {
     const auto& raw = phase == 1 ? raw1 : raw2;
-    const auto& by_warp = phase == 1 ? w1 : w2;
+    const auto& by_warp = phase == 1 ? it1 : it2;
     std::vector<unsigned char>& S = phase == 1 ? *s1 : *s2;
     std::vector<uint32_t>& wb = phase == 1 ? *wb1 : *wb2;
     const size_t esz = (phase == 1 && kp.clip) ? sizeof(EntryClip) : sizeof(Entry);
@@ -445,13 +496,14 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err, int 
     S.clear();
     for (int w = 0; w < W; w++) {
       const size_t wstart = S.size();
-      for (int t : by_warp[w]) {
+      for (int item : by_warp[w]) {
+        const int t = item >> 2, sides = item & 3;
         size_t team_first_hdr = (size_t)-1, last_hdr = 0;
         for (int v = P.team_vptr[t]; v < P.team_vptr[t + 1]; v++) {
           size_t vteam_last_hdr = (size_t)-1;
           for (int k = 0; k < 4; k++) {
             const auto& r = raw[(size_t)v * 4 + k];
-            if (r.empty()) continue;
+            if (r.empty() || !((sides >> (k & 1)) & 1)) continue;
             (phase == 1 ? P.n1 : P.n2) += (long long)r.size();
             // the padded entry sequence of the list, with the tau class of every entry
             std::vector<unsigned char> body;
@@ -549,6 +601,10 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err, int 
   //           | cluster gc partials [kMaxSplit][32] f32
   kp.smem_red_cl = kp.smem_red + 3u * 256u + 2u * 128u + 2u * 128u + 12u * 128u + (uint32_t)W * 128u;
   kp.smem_total = kp.smem_red_cl + (uint32_t)kMaxSplit * 128u;
+  if (kp.smem_p2) {
+    kp.smem_p2 = kp.smem_total;
+    kp.smem_total += 2u * (uint32_t)T * (uint32_t)(2 + kp.ndec) * 128u;
+  }
   if (kp.smem_total > kSmemMax)
     FAIL(BPLX_E_UNSUPPORTED, "problem needs %u bytes of shared memory per CTA (max %u): too many (team, confederation) pairs (%d)",
          kp.smem_total, kSmemMax, V);

@@ -131,7 +131,11 @@ struct KernelParams {
   uint32_t epi_team, epi_part;   // epilogue reuse of the table area: team rows, per-warp partials
   uint32_t epi_cl;               // ... and the per-CTA partials of a cluster ([kMaxSplit][kPartRows][32], on rank 0)
   uint32_t smem_red_cl;          // [kMaxSplit][32] d/d corr_coef partials of a cluster (rank 0)
+  uint32_t smem_p2;              // 0, or [2 sides][T][2 + ndec][32] f32: phase-2 slot sums when the split-1 plan deals a
+                                 // team's home-side and away-side tau lists to different warps (small T, one CTA)
   int split_hint;                // largest cluster size worth using (small plans are latency-bound: 1)
+  int force_clip_forms;          // testing (env BPLX_CLIP_FORMS at create): bit 0 / bit 1 = phase 1 / phase 2 always take the
+                                 // clipping form of the arithmetic, even when no rate of the chains is near the clip
   ThetaOffsets off;
   const unsigned char* stream1;  // phase-1 streams of all warps
   const unsigned char* stream2;  // phase-2 streams

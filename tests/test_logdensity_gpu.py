@@ -196,3 +196,38 @@ def test_random_problems(seed):
         g = grad.t().contiguous() if minor else grad
         _check(arr, theta.astype(np.float64), lp.cpu().numpy(), g.cpu().numpy(), cc.cpu().numpy())
     p.close()
+
+
+@pytest.mark.parametrize("model,kw", [("dixon_coles", dict()), ("extended", dict(weighted=True, K=3))])
+def test_clip_free_forms(model, kw, monkeypatch):
+    """Models that clip their rates at 15 take a shorter form of the same arithmetic when no rate of a group of 32
+    chains can reach the clip (prologue bound for phase 1, the reduced maxima for phase 2).  Near the mode (radius
+    0.15: every rate far below 15) the short form must agree with the oracle, and it must give the same BITS as the
+    clipping form: the same chains next to one far-out chain (which switches the whole group to the clipping form)."""
+    import torch
+    from bpl_next_b200 import Problem
+
+    arr = H.small_problem(model, seed=3, **kw)
+    p = Problem(arr)
+    C = 64
+    near = H.random_theta(p.D, C, seed=5, radius=0.15, dtype=np.float32)
+    lp, grad, cc = [x.cpu().numpy() for x in p.logdensity(torch.from_numpy(near).cuda())]
+    _check(arr, near.astype(np.float64), lp, grad, cc)
+    mixed = near.copy()
+    far = H.random_theta(p.D, 2, seed=9, radius=2.0, dtype=np.float32)
+    mixed[7], mixed[40] = far[0], far[1]  # one far-out chain in each group of 32
+    lp2, grad2, cc2 = [x.cpu().numpy() for x in p.logdensity(torch.from_numpy(mixed).cuda())]
+    keep = np.ones(C, bool)
+    keep[[7, 40]] = False
+    assert np.array_equal(lp[keep], lp2[keep])
+    assert np.array_equal(grad[keep], grad2[keep])
+    assert np.array_equal(cc[keep], cc2[keep])
+    _check(arr, mixed.astype(np.float64), lp2, grad2, cc2)
+    p.close()
+    # the same through the testing switch: phase 1 / phase 2 / both forced to the clipping form on the near batch
+    for forms in ("1", "2", "3"):
+        monkeypatch.setenv("BPLX_CLIP_FORMS", forms)
+        q = Problem(arr)
+        lp3, grad3, cc3 = [x.cpu().numpy() for x in q.logdensity(torch.from_numpy(near).cuda())]
+        q.close()
+        assert np.array_equal(lp, lp3) and np.array_equal(grad, grad3) and np.array_equal(cc, cc3), forms
