@@ -281,6 +281,17 @@ def extras(args, pk):
     from oracle import datasets
 
     out = []
+    # configs[1] again with theta near the mode, U(-0.2, 0.2): what a sampler past its first warm-up steps sends.  No rate
+    # of any chain is near the clip at 15, so K1 takes the clip-free forms of the same arithmetic.
+    arr, C, desc = workload("cfg2")
+    p = Problem(arr)
+    ms, reps, nb, set_bytes, finite = time_logdensity(p, C, 50, 5, 0.2, args.seed + 9, use_graph=True, target_s=0.5)
+    evals = C * arr.num_matches * 50 / (ms * 1e-3)
+    out.append({"workload": desc + f", {C} chains on 1 GPU, theta U(-0.2,0.2) (typical-set inputs: clip-free forms)",
+                "metric": METRIC, "value": evals, "unit": UNIT, "ms_per_call": ms / 50, "finite": finite,
+                "fp32_frac": FLOPS_PER_EVAL[arr.model] * evals / 1e12 / pk["fp32_tflops"]})
+    p.close()
+    del p
     # configs[2]: NeutralWC, 32,768 chains on one GPU (inputs 2 x 175 MB > L2)
     arr, C, desc = workload("cfg3")
     p = Problem(arr)
