@@ -27,6 +27,8 @@
 // shared memory of cluster rank 0 through distributed shared memory.
 #include <cooperative_groups.h>
 
+#include <math.h>
+
 #include "k1_common.cuh"
 #include "problem.h"
 
@@ -118,22 +120,18 @@ __device__ __forceinline__ void tau_piece(uint32_t& a, const Hdr& L, const float
   const float2 one = make_float2(1.0f, 1.0f);
   float2 lt = make_float2(0.0f, 0.0f), uxy = lt, sxy_x = lt, sxy_y = lt;
   {
-    const float Pxy = own.x * own.y;
     const uint32_t e_end = a + L.n0 * (uint32_t)sizeof(Entry);
 #pragma unroll 2
     for (; a < e_end; a += 16) {
       const uint4 q = lds128u(a);
       const float2 ea = lds64(tab + q.x), eb = lds64(tab + q.z);
       const float2 w = make_float2(__uint_as_float(q.y), __uint_as_float(q.w));
-      float2 t, ra, rb;
-      if (MODE == kTauPlain) {
-        t = mul2(bc2(Pxy), make_float2(ea.x * ea.y, eb.x * eb.y));
-      } else {
-        ra = mul2(own, ea);
-        rb = mul2(own, eb);
-        if (MODE == kTauClipped) t = make_float2(fminf(ra.x, 15.0f) * fminf(ra.y, 15.0f), fminf(rb.x, 15.0f) * fminf(rb.y, 15.0f));
-        else t = make_float2(ra.x * ra.y, rb.x * rb.y);
-      }
+      // the two rates first, then their product, as the reference groups it: (own.x own.y) (ea.x ea.y) overflows far
+      // from the typical set where the rates themselves do not
+      const float2 ra = mul2(own, ea), rb = mul2(own, eb);
+      float2 t;
+      if (MODE == kTauClipped) t = make_float2(fminf(ra.x, 15.0f) * fminf(ra.y, 15.0f), fminf(rb.x, 15.0f) * fminf(rb.y, 15.0f));
+      else t = make_float2(ra.x * ra.y, rb.x * rb.y);
       float2 tau = fma2(bc2(-cc), t, one);
       tau.x = fmaxf(tau.x, 0.0f);
       tau.y = fmaxf(tau.y, 0.0f);
@@ -210,7 +208,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
   const uint32_t tab = smem_u32(smem) + lane * 8;  // + row byte offset
   // [3][32] u32 value bits, then [3][32] u32 piece offsets
   unsigned long long* red_best = reinterpret_cast<unsigned long long*>(smem + kp.smem_red);
-  unsigned long long* red_found = reinterpret_cast<unsigned long long*>(smem + kp.smem_red + 768);  // [2][32] entry | info << 32
+  unsigned long long* red_found = reinterpret_cast<unsigned long long*>(smem + kp.smem_red + 768);  // [2][32] u32 entry words (atomicMin), then [2][32] u32 piece info
   float* red_hyp = reinterpret_cast<float*>(smem + kp.smem_red + 1280);                       // [12][32]
   float* red_gc = reinterpret_cast<float*>(smem + kp.smem_red + 1280 + 12 * 128);             // [W][32]
   // the cluster's reductions live in rank 0's shared memory (shared::cluster addresses; rank 0 = this CTA when S == 1)
@@ -538,16 +536,18 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
           val = q == 0 ? X : (q == 1 ? Y : (own.x * own.y) * (ea.x * ea.y));
         }
         if (val == target && found == 0xffffffffu) {
-          found = (i << 24) | off;
-          // own vteam | kind | "X not clipped" | "Y not clipped"
-          info = L.vteam | (L.kind << 16) | ((!CLIP || X < 15.0f) ? 1u << 18 : 0u) | ((!CLIP || Y < 15.0f) ? 1u << 19 : 0u);
+          // entry index | "X not clipped" | "Y not clipped" | opponent row offset (< 4 MB)
+          found = (i << 24) | ((!CLIP || X < 15.0f) ? 1u << 23 : 0u) | ((!CLIP || Y < 15.0f) ? 1u << 22 : 0u) | off;
+          info = L.vteam | (L.kind << 16);  // own vteam | kind: the same for every finder of this chain
         }
       }
     }
-    // one 64-bit store keeps (entry, piece info) together; several finders only under exact ties inside the piece
-    // (then any of them will do: clipped ties carry no gradient)
-    if (found != 0xffffffffu)
-      dsm_st_u64(a_found + (uint32_t)(which * 32 + lane) * 8u, (unsigned long long)found | ((unsigned long long)info << 32));
+    // several warps find an entry only under exact ties inside the piece (clipped rates, or rates that overflowed to
+    // inf far from the typical set): the lowest entry index wins -- atomicMin, so the choice does not depend on timing
+    if (found != 0xffffffffu) {
+      dsm_atom_min_u32(a_found + (uint32_t)(which * 32 + lane) * 4u, found);
+      dsm_st_u32(a_found + (uint32_t)(64 + which * 32 + lane) * 4u, info);
+    }
   }
 
   BPLX_STAMP(5);
@@ -622,18 +622,17 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
   fx.confs = 0u;
 #pragma unroll
   for (int which = 0; which < 2; which++) {
-    const unsigned long long fi = dsm_ld_u64(a_found + (uint32_t)(which * 32 + lane) * 8u);
-    const uint32_t packed = (uint32_t)fi;
+    const uint32_t packed = dsm_ld_u32(a_found + (uint32_t)(which * 32 + lane) * 4u);
     fx.teams[which] = 0xffffffffu;  // (unused here: the team pass matches virtual-team ranges, no v_team look-up)
     fx.vts[which] = 0xffffffffu;    // none
     fx.vx[which] = fx.vy[which] = 0.0f;
     if (packed != 0xffffffffu) {  // else: UB = 1 (or nothing matched: cannot happen, same arithmetic as phase 1)
-      const uint32_t info = (uint32_t)(fi >> 32);
-      const uint32_t f_off = packed & 0xffffffu;
+      const uint32_t info = dsm_ld_u32(a_found + (uint32_t)(64 + which * 32 + lane) * 4u);
+      const uint32_t f_off = packed & 0x3fffffu;
       const bool h1 = ((info >> 16) & 3u) == kH1;
       const uint32_t own_v = info & 0xffffu;
       const uint32_t opp_v = (f_off - (h1 ? kp.tabQ1 : kp.tabP0)) / kRowBytes;
-      const bool xfree = (info >> 18) & 1u, yfree = (info >> 19) & 1u;
+      const bool xfree = (packed >> 23) & 1u, yfree = (packed >> 22) & 1u;
       if (which == 0) {
         const float wgt = gc * (1.0f - r) / Lam;  // dc/dLB * dLB/d eta
         fx.vx[0] = (qlam == 0 && xfree) ? wgt : 0.0f;
@@ -830,7 +829,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
   if (warp == 0 && ln.active) {
     lp = kp.const_term;
     for (int w = 0; w < W; w++) lp += red_gc[w * 32 + lane];
-    kp.lp[chain] = lp;
+    // a log-density is never +inf: that is an intermediate that overflowed float32 far from the typical set (a sampler
+    // would accept such a point as the best ever seen); NaN is what the callers reject
+    kp.lp[chain] = lp == INFINITY ? NAN : lp;
   }
 }
 

@@ -13,6 +13,8 @@
 //   suffix pass   (team-owned)      d/d attack[j] summed over the later gameweeks (the walk's transpose)
 //   gameweek pass (gameweek-owned)  priors, chain rule and the ten per-gameweek hyper-parameter gradients,
 //                                   which need no cross-warp reduction because one warp sees the whole gameweek.
+#include <math.h>
+
 #include "k1_common.cuh"
 #include "problem.h"
 
@@ -525,7 +527,9 @@ __global__ void __launch_bounds__(kMaxWarpsDyn * 32, 1) logdensity_dynamic_kerne
   if (warp == 0 && ln.active) {
     lp = kp.const_term;
     for (int w = 0; w < W; w++) lp += red_gc[w * 32 + lane];
-    kp.lp[chain] = lp;
+    // a log-density is never +inf: that is an intermediate that overflowed float32 far from the typical set (a sampler
+    // would accept such a point as the best ever seen); NaN is what the callers reject
+    kp.lp[chain] = lp == INFINITY ? NAN : lp;
   }
 }
 

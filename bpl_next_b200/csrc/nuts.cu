@@ -17,6 +17,8 @@
 #include <curand_kernel.h>
 #include <math_constants.h>
 
+#include <stdlib.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(32 * kNutsMaxY) nuts_step_kernel(const bplx_nu
   if (pending) {
     const float pe1 = -lp_new;
     float delta = pe1 + 0.5f * acc1[0] - st.energy_current;
-    if (!(delta == delta)) delta = CUDART_INF_F;  // NaN -> reject
+    if (!(delta == delta) || !(fabsf(lp_new) < CUDART_INF_F)) delta = CUDART_INF_F;  // NaN, or a log-density that is not finite -> reject
     const float w_leaf = -delta;
     const float acc = fminf(1.0f, expf(-delta));
     // ---- merge the leaf into the subtree (uniform transition kernel inside a subtree) -----------------------------
@@ -328,6 +330,407 @@ __global__ void __launch_bounds__(32 * kNutsMaxY) nuts_step_kernel(const bplx_nu
   }
 }
 
+// ---- register-resident variant -------------------------------------------------------------------------------------
+// The kernel above walks its stages through global memory: every stage re-reads vectors the previous one wrote, so a
+// launch is a chain of dependent round trips to L2 -- and with many chains per block the block pays for the union of
+// the stages its chains are in (measured, DixonColes D = 44: 10 us at one chain, 46 us at 1,024 chains, three times the
+// log-density kernel beside it).  For small models the slice of every state vector a thread owns fits in registers:
+// block = (CPB chains, Y = 512 / CPB slices), thread (x, y) owns d = y + j Y, j < NPT.  Everything that does not
+// depend on the chain's scalar state is requested in ONE batch at entry; what does (the other end of the trajectory,
+// the Welford accumulators, the first checkpoint level of the U-turn test) in a second batch that arrives while the
+// first stages run; the stages then work on registers and store what they change.  Same arithmetic in the same order
+// as the kernel above: with the same (32, Y) geometry the two give identical bits (tests/test_nuts_gpu.py).
+template <int CPB, int NPT>
+__global__ void __launch_bounds__(512) nuts_step_fast_kernel(const bplx_nuts_params P) {
+  __shared__ float red[2 * 512];
+  __shared__ unsigned lvl_mask;
+  const int Y = blockDim.y, y = threadIdx.y, x = threadIdx.x;
+  const int c_raw = blockIdx.x * CPB + x;
+  const bool valid = c_raw < P.C;
+  const int c = valid ? c_raw : P.C - 1;
+  const int D = P.D;
+  const size_t ld = (size_t)P.ld;
+  if (x == 0 && y == 0) lvl_mask = 0u;
+  bool has[NPT];
+  size_t off[NPT];
+#pragma unroll
+  for (int j = 0; j < NPT; j++) {
+    const int d = y + j * Y;
+    has[j] = d < D;
+    off[j] = (size_t)(has[j] ? d : 0) * ld + (size_t)c;
+  }
+  auto ldv = [&](const float* base, float (&v)[NPT], bool on) {
+#pragma unroll
+    for (int j = 0; j < NPT; j++) v[j] = (on && has[j]) ? base[off[j]] : 0.0f;
+  };
+  auto stv = [&](float* base, const float (&v)[NPT]) {
+#pragma unroll
+    for (int j = 0; j < NPT; j++)
+      if (has[j]) base[off[j]] = v[j];
+  };
+  auto reduce1 = [&](float& v) {  // sum over the slices of every chain (all threads of the block call it)
+    __syncthreads();
+    red[y * CPB + x] = v;
+    __syncthreads();
+    float s = 0.0f;
+    for (int k = 0; k < Y; k++) s += red[k * CPB + x];
+    v = s;
+  };
+  auto reduce2 = [&](float (&v)[2]) {
+    __syncthreads();
+    red[y * CPB + x] = v[0];
+    red[(Y + y) * CPB + x] = v[1];
+    __syncthreads();
+    float s0 = 0.0f, s1 = 0.0f;
+    for (int k = 0; k < Y; k++) {
+      s0 += red[k * CPB + x];
+      s1 += red[(Y + k) * CPB + x];
+    }
+    v[0] = s0;
+    v[1] = s1;
+  };
+
+  // ---- batch 1: independent of the chain's state ---------------------------------------------------------------------
+  float th[NPT], gr[NPT], ph[NPT], im[NPT], rL[NPT], rR[NPT], zP[NPT], gP[NPT], rS[NPT], zQ[NPT], gQ[NPT], rQ[NPT];
+  ldv(P.theta_eval, th, true);
+  ldv(P.grad, gr, true);
+  ldv(P.p_half, ph, true);
+  ldv(P.inv_mass, im, true);
+  ldv(P.rL, rL, true);
+  ldv(P.rR, rR, true);
+  ldv(P.zP, zP, true);
+  ldv(P.gP, gP, true);
+  ldv(P.r_sum, rS, true);
+  ldv(P.zQ, zQ, true);
+  ldv(P.gQ, gQ, true);
+  ldv(P.r_sum_sub, rQ, true);
+  NutsChain* chains = static_cast<NutsChain*>(P.chain);
+  NutsChain st = chains[c];
+  const float lp_new = P.lp[c];
+  const bool live = valid && st.stage != kNutsDone;
+  const bool pending = live && st.stage == kNutsEvalPending;
+  const bool right = st.going_right != 0;  // the direction of the leapfrog that has just been evaluated
+  // the U-turn levels this leaf has to be tested against (numpyro `_leaf_idx_to_ckpt_idxs`)
+  const unsigned leaf = (unsigned)st.sub_num;
+  int idx_min = 1, idx_max = 0;
+  if (pending) {
+    idx_max = __popc(leaf >> 1);
+    idx_min = idx_max - (__ffs(~leaf) - 1) + 1;  // minus the number of trailing one bits
+  }
+  const unsigned my_lvls = (pending && idx_max >= idx_min) ? (((2u << idx_max) - 1u) & ~((1u << idx_min) - 1u)) : 0u;
+  // ---- batch 2: the other end of the trajectory, the Welford accumulators, the first checkpoint level ----------------
+  float zO[NPT], gO[NPT], wm[NPT], w2[NPT], ck[NPT], cks[NPT];
+  ldv(right ? P.zL : P.zR, zO, live);
+  ldv(right ? P.gL : P.gR, gO, live);
+  const bool warm = live && st.t < P.num_warmup;
+  ldv(P.wf_mean, wm, warm);
+  ldv(P.wf_m2, w2, warm);
+  {
+    const int i0 = my_lvls ? 31 - __clz(my_lvls) : 0;
+    ldv(P.r_ckpts + (size_t)i0 * D * ld, ck, my_lvls != 0u);
+    ldv(P.r_sum_ckpts + (size_t)i0 * D * ld, cks, my_lvls != 0u);
+  }
+  curandStatePhilox4_32_10_t rng;
+  curand_init(P.seed, (unsigned long long)(P.chain_offset + c), st.rng_offset, &rng);
+  unsigned draws = 0;
+  auto uniform = [&]() { draws++; return curand_uniform(&rng); };
+
+  // ======== A. finish the pending leapfrog ==============================================================================
+  if (live && st.stage == kNutsInitEval) {  // gradient at the initial position has just been computed
+#pragma unroll
+    for (int j = 0; j < NPT; j++) {
+      zP[j] = th[j];
+      gP[j] = gr[j];
+    }
+    stv(P.zP, zP);
+    stv(P.gP, gP);
+    st.pe = -lp_new;
+    st.stage = kNutsNewTransition;
+  }
+  const float eps = right ? st.step_size : -st.step_size;
+  float r1[NPT];
+  float acc1 = 0.0f;
+#pragma unroll
+  for (int j = 0; j < NPT; j++) r1[j] = 0.0f;
+  if (pending) {
+#pragma unroll
+    for (int j = 0; j < NPT; j++) {
+      if (has[j]) {
+        r1[j] = fmaf(0.5f * eps, gr[j], ph[j]);
+        acc1 = fmaf(im[j] * r1[j], r1[j], acc1);
+        if (right) rR[j] = r1[j];
+        else rL[j] = r1[j];
+      }
+    }
+    stv(right ? P.rR : P.rL, r1);
+    stv(right ? P.zR : P.zL, th);
+    stv(right ? P.gR : P.gL, gr);
+  }
+  reduce1(acc1);
+  bool sub_done = false;
+  if (pending) {
+    const float pe1 = -lp_new;
+    float delta = pe1 + 0.5f * acc1 - st.energy_current;
+    if (!(delta == delta) || !(fabsf(lp_new) < CUDART_INF_F)) delta = CUDART_INF_F;  // NaN, or a log-density that is not finite -> reject
+    const float w_leaf = -delta;
+    const float acc = fminf(1.0f, expf(-delta));
+    bool take;
+    if (st.sub_num == 0) {
+      take = true;
+      st.sub_weight = w_leaf;
+    } else {
+      const float pr = 1.0f / (1.0f + expf(-(w_leaf - st.sub_weight)));
+      take = uniform() < pr;
+      st.sub_weight = log_add_exp(st.sub_weight, w_leaf);
+    }
+    const bool ckpt = (leaf & 1u) == 0u;
+#pragma unroll
+    for (int j = 0; j < NPT; j++) {
+      rQ[j] = st.sub_num == 0 ? r1[j] : rQ[j] + r1[j];
+      if (take) {
+        zQ[j] = th[j];
+        gQ[j] = gr[j];
+      }
+    }
+    stv(P.r_sum_sub, rQ);
+    if (take) {
+      stv(P.zQ, zQ);
+      stv(P.gQ, gQ);
+    }
+    if (ckpt) {
+      stv(P.r_ckpts + (size_t)idx_max * D * ld, r1);
+      stv(P.r_sum_ckpts + (size_t)idx_max * D * ld, rQ);
+    }
+    if (take) st.sub_pe = pe1;
+    st.sub_div = delta > P.max_delta_energy;
+    st.sub_sum_accept += acc;
+  }
+  // ======== B. iterative U-turn test against the checkpoints: only the levels some chain of the block needs ============
+  if (my_lvls && y == 0) atomicOr(&lvl_mask, my_lvls);
+  __syncthreads();
+  bool turning = false;
+  {
+    unsigned m = lvl_mask;
+    // (the level prefetched in batch 2 is this chain's highest; the block's may be higher)
+    int have = my_lvls ? 31 - __clz(my_lvls) : -1;
+    while (m) {
+      const int i = 31 - __clz(m);
+      m &= ~(1u << i);
+      const bool need = pending && ((my_lvls >> i) & 1u) && !turning;
+      if (need && have != i) {
+        ldv(P.r_ckpts + (size_t)i * D * ld, ck, true);
+        ldv(P.r_sum_ckpts + (size_t)i * D * ld, cks, true);
+        have = i;
+      }
+      float dots[2] = {0.0f, 0.0f};
+      if (need) {
+#pragma unroll
+        for (int j = 0; j < NPT; j++) {
+          if (has[j]) {
+            const float a = ck[j], b = right ? rR[j] : rL[j], mm = im[j];
+            const float sm = (rQ[j] - cks[j] + a) - 0.5f * (a + b);  // momentum sum of the subtree that starts at checkpoint i
+            dots[0] = fmaf(mm * a, sm, dots[0]);
+            dots[1] = fmaf(mm * b, sm, dots[1]);
+          }
+        }
+      }
+      // the next level this chain needs is requested before the reduction's barriers
+      const unsigned below = my_lvls & ((1u << i) - 1u);
+      if (need && below) {
+        const int inext = 31 - __clz(below);
+        ldv(P.r_ckpts + (size_t)inext * D * ld, ck, true);
+        ldv(P.r_sum_ckpts + (size_t)inext * D * ld, cks, true);
+        have = inext;
+      }
+      reduce2(dots);
+      if (need) turning = dots[0] <= 0.0f || dots[1] <= 0.0f;
+    }
+  }
+  // ======== C. subtree complete: merge into the trajectory ===============================================================
+  bool move = false;
+  if (pending) {
+    st.sub_turning = turning;
+    st.sub_num += 1;
+    st.stage = kNutsInTree;
+    sub_done = st.sub_num == (1 << st.depth) || st.sub_turning || st.sub_div;
+    if (sub_done) {
+      float pr = fminf(1.0f, expf(st.sub_weight - st.weight));
+      if (st.sub_turning || st.sub_div) pr = 0.0f;
+      move = uniform() < pr;
+    }
+  }
+  {
+    float dots[2] = {0.0f, 0.0f};
+    if (sub_done) {
+#pragma unroll
+      for (int j = 0; j < NPT; j++) {
+        if (has[j]) {
+          const float rs = rS[j] + rQ[j];
+          rS[j] = rs;
+          if (move) {
+            zP[j] = zQ[j];
+            gP[j] = gQ[j];
+          }
+          const float a = rL[j], b = rR[j], mm = im[j];
+          const float sm = rs - 0.5f * (a + b);
+          dots[0] = fmaf(mm * a, sm, dots[0]);
+          dots[1] = fmaf(mm * b, sm, dots[1]);
+        }
+      }
+      stv(P.r_sum, rS);
+      if (move) {
+        stv(P.zP, zP);
+        stv(P.gP, gP);
+      }
+    }
+    if (__syncthreads_or(sub_done)) reduce2(dots);
+    if (sub_done) {
+      if (move) st.pe = st.sub_pe;
+      st.turning = st.sub_turning || dots[0] <= 0.0f || dots[1] <= 0.0f;
+      st.depth += 1;
+      st.weight = log_add_exp(st.weight, st.sub_weight);
+      st.diverging = st.sub_div;
+      st.sum_accept += st.sub_sum_accept;
+      st.num_prop += st.sub_num;
+      st.sub_active = 0;
+    }
+  }
+  // ======== D. transition complete: adaptation during warm-up, collection afterwards ===============================
+  if (sub_done && (st.depth >= P.max_tree_depth || st.turning || st.diverging)) {
+    const float accept = st.sum_accept / (float)st.num_prop;
+    st.num_leapfrog_total += st.num_prop;
+    if (st.diverging && st.t >= P.num_warmup) st.num_divergent += 1;
+    if (st.t < P.num_warmup) {
+      const float g = P.target_accept - accept;
+      st.da_t += 1;
+      const float t = (float)st.da_t;
+      st.da_g_avg = (1.0f - 1.0f / (t + 10.0f)) * st.da_g_avg + g / (t + 10.0f);
+      st.da_x = st.da_mu - sqrtf(t) / 0.05f * st.da_g_avg;
+      const float wt = powf(t, -0.75f);
+      st.da_x_avg = (1.0f - wt) * st.da_x_avg + wt * st.da_x;
+      st.step_size = fmaxf(expf(st.t == P.num_warmup - 1 ? st.da_x_avg : st.da_x), 1.1754944e-38f);
+      const bplx_window win = P.windows[st.window];
+      const bool middle = st.window > 0 && st.window < P.num_windows - 1;
+      const bool at_end = st.t == win.end;
+      if (middle) {
+        st.wf_n += 1;
+        const float n = (float)st.wf_n, inv_n = 1.0f / n;
+#pragma unroll
+        for (int j = 0; j < NPT; j++) {
+          const float xx = zP[j], pre = xx - wm[j];
+          const float mnew = fmaf(pre, inv_n, wm[j]);
+          const float m2new = fmaf(pre, xx - mnew, w2[j]);
+          if (at_end) {
+            if (has[j]) im[j] = (n / (n + 5.0f)) * (m2new / (n - 1.0f)) + 1e-3f * (5.0f / (n + 5.0f));
+            wm[j] = 0.0f;
+            w2[j] = 0.0f;
+          } else {
+            wm[j] = mnew;
+            w2[j] = m2new;
+          }
+        }
+        stv(P.wf_mean, wm);
+        stv(P.wf_m2, w2);
+        if (at_end) {
+          stv(P.inv_mass, im);
+          st.wf_n = 0;
+          st.da_mu = logf(10.0f * st.step_size);
+          st.da_x = st.da_x_avg = st.da_g_avg = 0.0f;
+          st.da_t = 0;
+        }
+      }
+      if (at_end) st.window += 1;
+    } else {
+      const int k = st.t - P.num_warmup;
+      if (k % P.thin == 0 && k / P.thin < P.num_keep) {
+        const int slot = k / P.thin;
+        stv(P.samples + (size_t)slot * D * ld, zP);
+        if (y == 0) {
+          P.sample_lp[(size_t)slot * ld + c] = -st.pe;
+          P.sample_accept[(size_t)slot * ld + c] = accept;
+        }
+      }
+    }
+    st.t += 1;
+    st.stage = st.t >= P.num_warmup + P.num_samples ? kNutsDone : kNutsNewTransition;
+  }
+  // ======== E. momentum refresh: r ~ N(0, M), M = 1 / inv_mass ==========================================================
+  const bool fresh = live && st.stage == kNutsNewTransition;
+  {
+    float ke = 0.0f;
+    if (fresh) {
+      const unsigned long long base = st.rng_offset + 64ull;
+#pragma unroll
+      for (int j = 0; j < NPT; j++) {
+        if (has[j]) {
+          const int d = y + j * Y;
+          curandStatePhilox4_32_10_t rn;
+          curand_init(P.seed, (unsigned long long)(P.chain_offset + c), base + 4ull * (unsigned long long)(d >> 1), &rn);
+          const float2 n2 = curand_normal2(&rn);
+          const float mm = im[j];
+          const float r = ((d & 1) ? n2.y : n2.x) * rsqrtf(mm);
+          ke = fmaf(mm * r, r, ke);
+          rL[j] = r;
+          rR[j] = r;
+          rS[j] = r;
+        }
+      }
+      stv(P.rL, rL);
+      stv(P.rR, rR);
+      stv(P.r_sum, rS);
+      stv(P.zL, zP);
+      stv(P.zR, zP);
+      stv(P.gL, gP);
+      stv(P.gR, gP);
+    }
+    if (__syncthreads_or(fresh)) reduce1(ke);
+    if (fresh) {
+      draws += 64u + 2u * (unsigned)D + 8u;
+      st.energy_current = st.pe + 0.5f * ke;
+      st.depth = 0;
+      st.weight = 0.0f;
+      st.turning = st.diverging = 0;
+      st.sum_accept = 0.0f;
+      st.num_prop = 0;
+      st.sub_active = 0;
+      st.stage = kNutsInTree;
+    }
+  }
+  // ======== F. start the next leapfrog from the outer leaf ================================================================
+  if (live && st.stage == kNutsInTree) {
+    if (!st.sub_active) {
+      st.going_right = uniform() < 0.5f ? 1 : 0;
+      st.sub_active = 1;
+      st.sub_num = 0;
+      st.sub_weight = 0.0f;
+      st.sub_sum_accept = 0.0f;
+      st.sub_turning = st.sub_div = 0;
+    }
+    const bool nr = st.going_right != 0;
+    const float e2 = nr ? st.step_size : -st.step_size;
+    // the outer leaf on that side: after a refresh both ends are the current position; the end that has just been
+    // extended is the leaf evaluated in this launch; the other end came with batch 2
+    const bool same = nr == right;
+#pragma unroll
+    for (int j = 0; j < NPT; j++) {
+      const float zF = fresh ? zP[j] : (same ? th[j] : zO[j]);
+      const float gF = fresh ? gP[j] : (same ? gr[j] : gO[j]);
+      const float rF = nr ? rR[j] : rL[j];
+      const float rh = fmaf(0.5f * e2, gF, rF);
+      ph[j] = rh;
+      th[j] = fmaf(e2 * im[j], rh, zF);
+    }
+    stv(P.p_half, ph);
+    stv(P.theta_eval, th);
+    st.stage = kNutsEvalPending;
+  }
+  if (live && y == 0) {
+    st.rng_offset += (draws + 7u) & ~3u;
+    chains[c] = st;
+    if (st.stage != kNutsDone) atomicAdd(P.active_count, 1);
+  }
+}
+
 __global__ void nuts_init_kernel(const bplx_nuts_params P) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= P.C) return;
@@ -382,7 +785,16 @@ int bplx_nuts_step(const bplx_nuts_params* p, void* stream) {
                "nuts: max_tree_depth must be in [1, 12] and thin >= 1");
   int Y = (p->D + 3) / 4;  // about four parameters per thread, at most kNutsMaxY slices per chain
   Y = Y < 1 ? 1 : (Y > kNutsMaxY ? kNutsMaxY : Y);
-  nuts_step_kernel<<<(p->C + 31) / 32, dim3(32, Y), 0, static_cast<cudaStream_t>(stream)>>>(*p);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool generic = getenv("BPLX_NUTS_GENERIC") != nullptr;  // testing: the stage-by-stage kernel for every size
+  if (!generic && p->D <= 4 * kNutsMaxY)  // same geometry as the generic kernel: identical bits
+    nuts_step_fast_kernel<32, 4><<<(p->C + 31) / 32, dim3(32, Y), 0, s>>>(*p);
+  else if (!generic && p->D <= 128)
+    nuts_step_fast_kernel<16, 4><<<(p->C + 15) / 16, dim3(16, 32), 0, s>>>(*p);
+  else if (!generic && p->D <= 256)
+    nuts_step_fast_kernel<8, 4><<<(p->C + 7) / 8, dim3(8, 64), 0, s>>>(*p);
+  else
+    nuts_step_kernel<<<(p->C + 31) / 32, dim3(32, Y), 0, s>>>(*p);
   BPLX_CUDA(cudaGetLastError());
   note_launch(1);
   return BPLX_OK;

@@ -78,3 +78,64 @@ def test_dixon_coles_posterior_is_stationary_across_seeds():
     # home advantage posterior mean: log(782/645) ~ 0.19 is the data's home/away goal ratio (prior N(0.1, 0.2))
     ha = means[0][0][0].item()
     assert 0.1 < ha < 0.3, ha
+
+
+@pytest.mark.parametrize("D,C", [(6, 70), (44, 96), (64, 33)])
+def test_register_resident_step_matches_stage_by_stage_kernel(D, C, monkeypatch):
+    """Small models run the NUTS bookkeeping out of registers (nuts_step_fast_kernel); with the same block geometry it
+    does the same arithmetic in the same order as the stage-by-stage kernel, so whole runs must agree bit for bit:
+    draws, acceptance statistics, leapfrog counts, adapted step sizes and mass matrices."""
+    import torch
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    sd = torch.exp(torch.rand((D, 1), generator=g, device="cuda") * 3 - 1.5)
+    mu = torch.rand((D, 1), generator=g, device="cuda") * 2 - 1
+
+    def potential(theta, lp, grad):
+        z = (theta - mu) / sd
+        lp.copy_(-0.5 * (z * z).sum(0))
+        grad.copy_(-z / sd)
+
+    theta0 = torch.rand((D, C), generator=g, device="cuda") * 4 - 2
+    runs = []
+    for generic in (False, True):
+        if generic:
+            monkeypatch.setenv("BPLX_NUTS_GENERIC", "1")
+        else:
+            monkeypatch.delenv("BPLX_NUTS_GENERIC", raising=False)
+        runs.append(bn.sample(potential, theta0.clone(), num_warmup=120, num_samples=40, seed=7, use_graph=False))
+    a, b = runs
+    assert a.launches == b.launches
+    assert torch.equal(a.samples, b.samples)
+    assert torch.equal(a.lp, b.lp) and torch.equal(a.accept, b.accept)
+    assert torch.equal(a.inv_mass, b.inv_mass)
+    assert np.array_equal(a.step_size, b.step_size) and np.array_equal(a.num_leapfrog, b.num_leapfrog)
+
+
+@pytest.mark.parametrize("D", [100, 200])
+def test_register_resident_step_wide_geometries(D):
+    """64 < D <= 256 uses 16 or 8 chains per block (32 / 64 slices per chain): no bit-twin to compare with, so the
+    moments of a Gaussian target are checked."""
+    import torch
+    from bpl_next_b200 import diagnostics as dg
+
+    C = 200
+    g = torch.Generator(device="cuda").manual_seed(5)
+    sd = torch.exp(torch.rand((D, 1), generator=g, device="cuda") * 2 - 1)
+    mu = torch.rand((D, 1), generator=g, device="cuda") * 2 - 1
+
+    def potential(theta, lp, grad):
+        z = (theta - mu) / sd
+        lp.copy_(-0.5 * (z * z).sum(0))
+        grad.copy_(-z / sd)
+
+    theta0 = torch.rand((D, C), generator=g, device="cuda") * 4 - 2
+    run = bn.sample(potential, theta0, num_warmup=300, num_samples=100, seed=2)
+    x = run.samples.double()
+    mean = x.mean(dim=(0, 2))
+    std = x.permute(1, 0, 2).reshape(D, -1).std(dim=1)
+    ess = dg.effective_sample_size(run.samples)
+    mcse = sd[:, 0].double() / ess.double().sqrt()
+    assert float(((mean - mu[:, 0].double()).abs() / mcse).max()) < 5.5
+    assert float((std / sd[:, 0].double() - 1).abs().max()) < 0.06
+    assert run.num_divergent.sum() == 0
