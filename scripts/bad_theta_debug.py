@@ -1,4 +1,4 @@
-"""K1 on one far-out position (scripts/bad_theta_dc.npy, found by scripts/nuts_determinism.py): is the output the same
+"""K1 on one far-out position (tests/golden/far_out_theta_dixon_coles.npy, found by scripts/nuts_determinism.py): is the output the same
 on every call?"""
 import sys, numpy as np, torch
 sys.path.insert(0, '.')
@@ -7,7 +7,7 @@ from oracle import datasets, models as om
 from tests import helpers as H
 arr = H.from_training_data("dixon_coles", datasets.dummy_data())
 p = Problem(arr)
-th = np.load("scripts/bad_theta_dc.npy").astype(np.float32)
+th = np.load("tests/golden/far_out_theta_dixon_coles.npy").astype(np.float32)
 print("layout", p.layout)
 good = H.random_theta(p.D, 64, seed=1, radius=1.0, dtype=np.float32)
 good[5] = th

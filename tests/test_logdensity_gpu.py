@@ -231,3 +231,31 @@ def test_clip_free_forms(model, kw, monkeypatch):
         lp3, grad3, cc3 = [x.cpu().numpy() for x in q.logdensity(torch.from_numpy(near).cuda())]
         q.close()
         assert np.array_equal(lp, lp3) and np.array_equal(grad, grad3) and np.array_equal(cc, cc3), forms
+
+
+def test_far_out_position_is_reproducible_and_rejectable():
+    """A position the sampler visited in its first warm-up leapfrogs (|theta| up to 1,600: rates overflow float32 to inf
+    and tie at the maximum).  The call must give the same bits every time -- the arg-max entry is chosen by atomicMin, not
+    by the last finder -- and must not report a log-density of +inf (a sampler would accept it as the best point ever)."""
+    import os
+    import torch
+    from bpl_next_b200 import Problem
+
+    arr = H.from_training_data("dixon_coles", datasets.dummy_data())
+    p = Problem(arr)
+    far = np.load(os.path.join(os.path.dirname(__file__), "golden", "far_out_theta_dixon_coles.npy")).astype(np.float32)
+    theta = H.random_theta(p.D, 64, seed=1, radius=1.0, dtype=np.float32)
+    theta[5] = far
+    theta[40] = far
+    t = torch.from_numpy(theta).cuda()
+    ref = [x.clone() for x in p.logdensity(t)]
+    assert not torch.isposinf(ref[0]).any()
+    for _ in range(20):
+        out = p.logdensity(t)
+        torch.cuda.synchronize()
+        for a, b in zip(ref, out):
+            assert torch.equal(torch.nan_to_num(a, nan=12345.0), torch.nan_to_num(b, nan=12345.0))
+    keep = np.ones(64, bool)
+    keep[[5, 40]] = False
+    _check(arr, theta[keep].astype(np.float64), ref[0].cpu().numpy()[keep], ref[1].cpu().numpy()[keep], ref[2].cpu().numpy()[keep])
+    p.close()

@@ -139,3 +139,27 @@ def test_register_resident_step_wide_geometries(D):
     assert float(((mean - mu[:, 0].double()).abs() / mcse).max()) < 5.5
     assert float((std / sd[:, 0].double() - 1).abs().max()) < 0.06
     assert run.num_divergent.sum() == 0
+
+
+def test_runs_are_reproducible_with_the_dixon_coles_kernel():
+    """Same data, seed and chain count -> the same draws, bit for bit (no timing-dependent arithmetic anywhere between
+    the log-density kernel and the NUTS step; regression test for the arg-max tie race far from the typical set)."""
+    import torch
+    from bpl_next_b200 import Problem
+    from oracle import datasets
+    from tests import helpers as H
+
+    arr = H.from_training_data("dixon_coles", datasets.dummy_data())
+    p = Problem(arr)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    theta0 = torch.rand((p.D, 96), generator=g, device="cuda") * 4 - 2
+
+    def potential(theta, lp, grad):
+        p.logdensity(theta, chain_minor=True, lp=lp, grad=grad)
+
+    a = bn.sample(potential, theta0.clone(), num_warmup=60, num_samples=20, seed=1)
+    b = bn.sample(potential, theta0.clone(), num_warmup=60, num_samples=20, seed=1, use_graph=False)
+    assert a.launches == b.launches
+    assert torch.equal(a.samples, b.samples) and torch.equal(a.lp, b.lp)
+    assert np.array_equal(a.num_leapfrog, b.num_leapfrog)
+    p.close()
