@@ -300,7 +300,12 @@ def extras(args, pk):
     evals = C * arr.num_matches * 3 / (ms * 1e-3)
     out.append({"workload": desc + f", {C} chains on 1 GPU", "metric": METRIC, "value": evals, "unit": UNIT,
                 "ms_per_call": ms / 3, "finite": finite, "plan": p.stats(),
-                "fp32_frac": FLOPS_PER_EVAL["neutral_wc"] * evals / 1e12 / pk["fp32_tflops"]})
+                "fp32_frac": FLOPS_PER_EVAL["neutral_wc"] * evals / 1e12 / pk["fp32_tflops"],
+                # one float2 table row per chain and list entry: the algorithmic shared-memory bytes against the LDS.64
+                # peak measured in this run (ncu counts 1.3x more wavefronts than that: the broadcast entry reads, bank
+                # conflicts -- profiles/r01_k1_final_cfg3.md)
+                "smem_frac": 8.0 * C * (p.stats()["entries1_padded"] + p.stats()["entries2_padded"]) / (ms / 3 * 1e-3) / 1e12
+                             / pk["smem_tbs"]})
     # the few-chain ("streaming") regime on the same data: one CTA walks the whole static plan
     st = p.stats()
     plan_bytes = 8 * (st["entries1_padded"] + st["entries2_padded"]) + 16 * 2600
