@@ -49,7 +49,7 @@ static size_t workspace_bytes(const KernelParams& kp, int C) {
 }
 
 static int enqueue(const bplx_problem* p, int C, int layout, int ld, const float* theta, float* lp, float* grad,
-                   float* corr_coef, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                   float* corr_coef, void* ws, size_t ws_bytes, cudaStream_t stream, bool pdl = false) {
   BPLX_REQUIRE(p != nullptr, BPLX_E_INVALID, "problem is NULL");
   BPLX_REQUIRE(C > 0, BPLX_E_INVALID, "num_chains must be positive (got %d)", C);
   BPLX_REQUIRE(theta && lp && grad, BPLX_E_INVALID, "theta, lp and grad must not be NULL");
@@ -95,7 +95,7 @@ static int enqueue(const bplx_problem* p, int C, int layout, int ld, const float
   kp.stream2 = p->s2[si];
   kp.warp_b1 = p->wb1[si];
   kp.warp_b2 = p->wb2[si];
-  return kp.model == BPLX_DYNAMIC ? launch_logdensity_dynamic(kp, stream) : launch_logdensity(kp, p->wb[si], stream);
+  return kp.model == BPLX_DYNAMIC ? launch_logdensity_dynamic(kp, stream) : launch_logdensity(kp, p->wb[si], stream, pdl);
 }
 
 }  // namespace bplx
@@ -214,7 +214,7 @@ size_t bplx_logdensity_workspace_bytes(const bplx_problem* p, int num_chains) {
 int bplx_logdensity_fwdbwd(const bplx_problem* p, int num_chains, int layout, int ld, const float* theta, float* lp,
                            float* grad, float* corr_coef, void* workspace, size_t workspace_bytes, void* stream) {
   return enqueue(p, num_chains, layout, ld, theta, lp, grad, corr_coef, workspace, workspace_bytes,
-                 static_cast<cudaStream_t>(stream));
+                 static_cast<cudaStream_t>(stream), /*pdl=*/true);
 }
 
 int bplx_logdensity_fwdbwd_host(bplx_problem* p, int C, const float* theta, float* lp, float* grad, float* corr_coef) {

@@ -1,5 +1,6 @@
 // common.cuh -- error plumbing and sm_100a PTX helpers shared by the bplx kernels.
 #pragma once
+#include <stdlib.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -30,6 +31,12 @@ void note_launch(int n = 1);  // kernels enqueued by this library (bplx_launch_c
       return (code);                  \
     }                                 \
   } while (0)
+
+// programmatic dependent launch on the K1 / NUTS-step launches (BPLX_NO_PDL=1 turns it off: plain stream order)
+inline bool pdl_enabled() {
+  static const bool on = getenv("BPLX_NO_PDL") == nullptr;
+  return on;
+}
 
 // ---- device helpers -----------------------------------------------------------------------
 #ifdef __CUDACC__
@@ -83,6 +90,20 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
   return upk2(d);
 }
 __device__ __forceinline__ float2 bc2(float x) { return make_float2(x, x); }
+
+// programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor in the stream is still running; everything it does before pdl_wait() must touch nothing the
+// predecessor writes or reads-then-overwrites.  pdl_wait() returns when the predecessor has completed and its writes
+// are visible; pdl_launch_dependents() lets the next kernel in the stream begin its own preamble.  Both are no-ops
+// for ordinary launches.  Pointers to data the predecessor produces are passed through after_wait() so that no load
+// from them (not even a read-only-path load the compiler considers movable) can be scheduled above the wait.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename T>
+__device__ __forceinline__ T* after_wait(T* p) {
+  asm volatile("" : "+l"(p));
+  return p;
+}
 
 // distributed shared memory (thread-block clusters): 32-bit shared::cluster addresses ----------------------
 // (generic-pointer atomics on a mapped address compile to a LOCAL shared-memory CAS loop -- address the remote CTA

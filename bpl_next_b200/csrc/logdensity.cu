@@ -222,6 +222,13 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
             smem_u32(smem) + kp.smem_bar + warp * (kStages * 8), kp.stage_bytes, lane);
   const uint32_t b1_0 = wb.b1[vwarp], b1_1 = wb.b1[vwarp + 1];
   ring.begin(kp.stream1 + b1_0, b1_1 - b1_0);  // phase-1 pieces start streaming in while the prologue runs
+  // Up to here the kernel has read only its parameters and the static plan: under programmatic dependent launch this
+  // preamble (and the TMA of the first list stages) overlaps the tail of the kernel that produces theta.
+  pdl_wait();
+  pdl_launch_dependents();
+  ln.th = after_wait(ln.th);
+  ln.gr = after_wait(ln.gr);
+  ln.sc = after_wait(ln.sc);
   // Everything the prologue needs from global memory is requested here, in one go, right after the ring has been
   // started (the ring's set-up ends in a fence, which would wait for loads already in flight): one round trip for all
   // of it.  (What the first pass over a team needs is then fetched one team ahead.)
@@ -837,30 +844,35 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
 
 // ---- host launcher --------------------------------------------------------------------------------------
 template <bool CLIP>
-static int launch_t(const KernelParams& kp, const WarpBounds& wb, cudaStream_t stream, bool set_attr) {
+static int launch_t(const KernelParams& kp, const WarpBounds& wb, cudaStream_t stream, bool set_attr, bool pdl) {
   auto* fn = &logdensity_kernel<CLIP>;
   if (set_attr) {
     BPLX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return BPLX_OK;
   }
   const int groups = (kp.C + kChains - 1) / kChains;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(groups * kp.split));
+  cfg.blockDim = dim3((unsigned)(kp.nwarps * 32));
+  cfg.dynamicSmemBytes = kp.smem_total;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  int na = 0;
   if (kp.split > 1) {  // one thread-block cluster per group of chains
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(groups * kp.split));
-    cfg.blockDim = dim3((unsigned)(kp.nwarps * 32));
-    cfg.dynamicSmemBytes = kp.smem_total;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = (unsigned)kp.split;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    BPLX_CUDA(cudaLaunchKernelEx(&cfg, fn, kp, wb));
-  } else {
-    fn<<<groups, kp.nwarps * 32, kp.smem_total, stream>>>(kp, wb);
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = (unsigned)kp.split;
+    at[na].val.clusterDim.y = 1;
+    at[na].val.clusterDim.z = 1;
+    na++;
   }
+  if (pdl && pdl_enabled()) {  // the kernel's preamble may overlap the tail of its predecessor in the stream (pdl_wait() inside)
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    na++;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = (unsigned)na;
+  BPLX_CUDA(cudaLaunchKernelEx(&cfg, fn, kp, wb));
   BPLX_CUDA(cudaGetLastError());
   note_launch(1);
   return BPLX_OK;
@@ -898,10 +910,10 @@ extern "C" int bplx_timeline_read(unsigned long long* out) {
 
 int logdensity_set_attributes(const KernelParams& kp) {
   static const WarpBounds none{};
-  return kp.clip ? launch_t<true>(kp, none, nullptr, true) : launch_t<false>(kp, none, nullptr, true);
+  return kp.clip ? launch_t<true>(kp, none, nullptr, true, false) : launch_t<false>(kp, none, nullptr, true, false);
 }
-int launch_logdensity(const KernelParams& kp, const WarpBounds& wb, cudaStream_t stream) {
-  return kp.clip ? launch_t<true>(kp, wb, stream, false) : launch_t<false>(kp, wb, stream, false);
+int launch_logdensity(const KernelParams& kp, const WarpBounds& wb, cudaStream_t stream, bool pdl) {
+  return kp.clip ? launch_t<true>(kp, wb, stream, false, pdl) : launch_t<false>(kp, wb, stream, false, pdl);
 }
 
 }  // namespace bplx

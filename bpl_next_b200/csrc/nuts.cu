@@ -64,6 +64,8 @@ __device__ __forceinline__ void reduce_y(float (&v)[N], float* red) {
 // is replicated in the Y threads of a chain (same inputs, same random numbers -> same decisions); only y == 0 writes it.
 __global__ void __launch_bounds__(32 * kNutsMaxY) nuts_step_kernel(const bplx_nuts_params P) {
   __shared__ float red[2 * kNutsMaxY * 32];
+  pdl_wait();  // (launched with programmatic stream serialization: nothing here may run ahead of the log-density kernel)
+  pdl_launch_dependents();
   const int Y = blockDim.y, y = threadIdx.y;
   const int c_raw = blockIdx.x * 32 + threadIdx.x;
   const bool valid = c_raw < P.C;
@@ -391,9 +393,10 @@ __global__ void __launch_bounds__(512) nuts_step_fast_kernel(const bplx_nuts_par
   };
 
   // ---- batch 1: independent of the chain's state ---------------------------------------------------------------------
+  // (under programmatic dependent launch this batch, the chain state and batch 2 overlap the tail of the log-density
+  //  kernel: it writes none of them; its outputs -- lp, grad -- are read after pdl_wait() below)
   float th[NPT], gr[NPT], ph[NPT], im[NPT], rL[NPT], rR[NPT], zP[NPT], gP[NPT], rS[NPT], zQ[NPT], gQ[NPT], rQ[NPT];
   ldv(P.theta_eval, th, true);
-  ldv(P.grad, gr, true);
   ldv(P.p_half, ph, true);
   ldv(P.inv_mass, im, true);
   ldv(P.rL, rL, true);
@@ -406,7 +409,6 @@ __global__ void __launch_bounds__(512) nuts_step_fast_kernel(const bplx_nuts_par
   ldv(P.r_sum_sub, rQ, true);
   NutsChain* chains = static_cast<NutsChain*>(P.chain);
   NutsChain st = chains[c];
-  const float lp_new = P.lp[c];
   const bool live = valid && st.stage != kNutsDone;
   const bool pending = live && st.stage == kNutsEvalPending;
   const bool right = st.going_right != 0;  // the direction of the leapfrog that has just been evaluated
@@ -434,6 +436,11 @@ __global__ void __launch_bounds__(512) nuts_step_fast_kernel(const bplx_nuts_par
   curand_init(P.seed, (unsigned long long)(P.chain_offset + c), st.rng_offset, &rng);
   unsigned draws = 0;
   auto uniform = [&]() { draws++; return curand_uniform(&rng); };
+  // ---- the log-density kernel's outputs ---------------------------------------------------------------------------------
+  pdl_wait();
+  pdl_launch_dependents();
+  ldv(after_wait(P.grad), gr, true);
+  const float lp_new = after_wait(P.lp)[c];
 
   // ======== A. finish the pending leapfrog ==============================================================================
   if (live && st.stage == kNutsInitEval) {  // gradient at the initial position has just been computed
@@ -787,14 +794,26 @@ int bplx_nuts_step(const bplx_nuts_params* p, void* stream) {
   Y = Y < 1 ? 1 : (Y > kNutsMaxY ? kNutsMaxY : Y);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool generic = getenv("BPLX_NUTS_GENERIC") != nullptr;  // testing: the stage-by-stage kernel for every size
+  cudaLaunchConfig_t cfg{};
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // the step's state loads overlap the log-density kernel's tail
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1u : 0u;
+  auto launch = [&](auto* fn, int cpb, dim3 block) {
+    cfg.gridDim = dim3((unsigned)((p->C + cpb - 1) / cpb));
+    cfg.blockDim = block;
+    return cudaLaunchKernelEx(&cfg, fn, *p);
+  };
   if (!generic && p->D <= 4 * kNutsMaxY)  // same geometry as the generic kernel: identical bits
-    nuts_step_fast_kernel<32, 4><<<(p->C + 31) / 32, dim3(32, Y), 0, s>>>(*p);
+    BPLX_CUDA(launch(&nuts_step_fast_kernel<32, 4>, 32, dim3(32, Y)));
   else if (!generic && p->D <= 128)
-    nuts_step_fast_kernel<16, 4><<<(p->C + 15) / 16, dim3(16, 32), 0, s>>>(*p);
+    BPLX_CUDA(launch(&nuts_step_fast_kernel<16, 4>, 16, dim3(16, 32)));
   else if (!generic && p->D <= 256)
-    nuts_step_fast_kernel<8, 4><<<(p->C + 7) / 8, dim3(8, 64), 0, s>>>(*p);
+    BPLX_CUDA(launch(&nuts_step_fast_kernel<8, 4>, 8, dim3(8, 64)));
   else
-    nuts_step_kernel<<<(p->C + 31) / 32, dim3(32, Y), 0, s>>>(*p);
+    BPLX_CUDA(launch(&nuts_step_kernel, 32, dim3(32, Y)));
   BPLX_CUDA(cudaGetLastError());
   note_launch(1);
   return BPLX_OK;

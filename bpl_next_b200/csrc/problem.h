@@ -34,7 +34,9 @@ struct bplx_problem {
 };
 
 namespace bplx {
-int launch_logdensity(const KernelParams& kp, const WarpBounds& wb, cudaStream_t stream);
+// pdl: launch with programmatic stream serialization (device-pointer entry point: the predecessor in the stream is
+// usually the kernel that produced theta; not after the host variant's copies)
+int launch_logdensity(const KernelParams& kp, const WarpBounds& wb, cudaStream_t stream, bool pdl);
 int logdensity_set_attributes(const KernelParams& kp);
 int logdensity_max_clusters(const KernelParams& kp, int split);  // co-resident clusters of `split` CTAs, 0 if unsupported
 int launch_logdensity_dynamic(const KernelParams& kp, cudaStream_t stream);
