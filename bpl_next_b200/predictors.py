@@ -11,6 +11,9 @@ from __future__ import annotations
 
 from typing import Any, Dict, Iterable, Optional, Union
 
+import warnings
+from datetime import datetime
+
 import numpy as np
 import torch
 
@@ -168,6 +171,73 @@ class _BplxPredictor:
     def _extras_from_args(self, args, kw):
         return kw
 
+    # ---- simulation from the grid (bpl/base.py:150-246, bpl/_util.py:96-112) -----------------------------------
+    @staticmethod
+    def _choice(probs: np.ndarray, num_samples: int, random_state) -> np.ndarray:
+        """``[F, K]`` probabilities -> ``[F, num_samples]`` category indices, one independent stream per fixture (the
+        reference draws with ``jax.random.choice`` under ``vmap``; like it, the row is normalised by its own sum)."""
+        if random_state is None:
+            random_state = int(datetime.now().timestamp() * 100)
+        rng = np.random.default_rng(int(random_state))
+        cdf = np.cumsum(probs.astype(np.float64), axis=1)
+        u = rng.random((probs.shape[0], int(num_samples))) * cdf[:, -1:]
+        idx = (u[:, :, None] >= cdf[:, None, :]).sum(axis=2)
+        return np.minimum(idx, probs.shape[1] - 1)
+
+    def _sample_score(self, home_team, away_team, num_samples, random_state, max_goals, **kw):
+        grid, hg, ag = _BplxPredictor.predict_score_grid_proba(self, home_team, away_team, max_goals=max_goals, **kw)
+        idx = self._choice(grid.reshape(grid.shape[0], -1), num_samples, random_state)
+        return {"home_score": hg.ravel()[idx], "away_score": ag.ravel()[idx]}
+
+    def _sample_outcome(self, home_team, away_team, num_samples, random_state, max_goals, knockout=False, **kw):
+        h, a = self._parse_fixture_args(home_team, away_team)
+        pr = _BplxPredictor.predict_outcome_proba(self, h, a, max_goals=max_goals, knockout=knockout, **kw)
+        keys = ("home_win", "away_win") if knockout else ("home_win", "draw", "away_win")
+        idx = self._choice(np.stack([pr[k] for k in keys], axis=1), num_samples, random_state)
+        names = np.append(np.asarray(self.teams), "Draw")
+        draw = len(self.teams)
+        hrep, arep = np.repeat(h[:, None], num_samples, axis=1).astype(np.int64), np.repeat(a[:, None], num_samples, axis=1).astype(np.int64)
+        away_code = 1 if knockout else 2
+        winner = np.where(idx == 0, hrep, np.where(idx == away_code, arep, draw))
+        return names[winner]
+
+    def sample_score(self, home_team, away_team, num_samples: int = 1, random_state: Optional[int] = None,
+                     max_goals: int = MAX_GOALS):
+        """``{"home_score", "away_score"}``, each ``[fixtures, num_samples]`` (``bpl/base.py:150-195``)."""
+        return self._sample_score(home_team, away_team, num_samples, random_state, max_goals)
+
+    def sample_outcome(self, home_team, away_team, num_samples: int = 1, random_state: Optional[int] = None,
+                       max_goals: int = MAX_GOALS):
+        """``[fixtures, num_samples]`` names of the winning team, or ``"Draw"`` (``bpl/base.py:197-246``)."""
+        return self._sample_outcome(home_team, away_team, num_samples, random_state, max_goals)
+
+    # ---- a team the model has not seen (extended_dixon_coles.py:401-462 and the neutral siblings) ---------------
+    def _new_team_pair(self, team_name, team_covariates):
+        """Draws of (attack, defence) for a new team from the fitted hierarchical prior, one per posterior sample."""
+        if team_name in self.teams:
+            raise ValueError(f"Team {team_name} already known to model.")
+        if self.attack_coefficients is not None:
+            if team_covariates is None:
+                warnings.warn(f"You haven't provided features for {team_name}. Assuming team_covariates are the average of "
+                              "known teams. For better forecasts, provide team_covariates.")
+                x = np.zeros(self.attack_coefficients.shape[1], np.float32)
+            else:
+                x = (0.5 * (np.asarray(team_covariates, np.float32) - self._meta["team_covariates_mean"])
+                     / self._meta["team_covariates_std"]).ravel()
+            mean_attack = self.attack_coefficients @ x
+            mean_defence = self.mean_defence + self.defence_coefficients @ x
+        else:
+            mean_attack, mean_defence = 0.0, self.mean_defence
+        a_tilde = np.random.normal(loc=0.0, scale=1.0, size=len(self.std_attack))
+        b_tilde = np.random.normal(loc=self.rho * a_tilde, scale=np.sqrt(1.0 - self.rho ** 2.0))
+        return mean_attack + a_tilde * self.std_attack, mean_defence + b_tilde * self.std_defence
+
+    def _append_team(self, team_name, columns: Dict[str, np.ndarray]):
+        self.teams = np.append(self.teams, team_name)
+        self._teams_dict[team_name] = len(self._teams_dict)
+        for name, col in columns.items():
+            setattr(self, name, np.concatenate((getattr(self, name), np.asarray(col, np.float32)[:, None]), axis=1))
+
 
 class DixonColesMatchPredictor(_BplxPredictor):
     """``bpl/dixon_coles.py:26-163``."""
@@ -188,7 +258,7 @@ class DixonColesMatchPredictor(_BplxPredictor):
 
 
 class ExtendedDixonColesMatchPredictor(_BplxPredictor):
-    """``bpl/extended_dixon_coles.py:28-399`` (``add_new_team`` is out of scope)."""
+    """``bpl/extended_dixon_coles.py:28-462``."""
     model = "extended"
 
     def fit(self, training_data, random_state: int = 42, num_warmup: int = 500, num_samples: int = 1000,
@@ -212,6 +282,13 @@ class ExtendedDixonColesMatchPredictor(_BplxPredictor):
     def _samples(self):
         return {"attack": self.attack, "defence": self.defence, "home_advantage": self.home_advantage,
                 "corr_coef": self.corr_coef}
+
+    def add_new_team(self, team_name: str, team_covariates: Optional[np.ndarray] = None) -> None:
+        """Parameters for a team not seen in training, drawn from the fitted priors (``extended_dixon_coles.py:401-462``;
+        like the reference this uses numpy's global random state)."""
+        attack, defence = self._new_team_pair(team_name, team_covariates)
+        home_advantage = np.random.normal(loc=self.mean_home_advantage, scale=self.std_home_advantage)
+        self._append_team(team_name, {"attack": attack, "defence": defence, "home_advantage": home_advantage})
 
 
 class NeutralDixonColesMatchPredictor(_BplxPredictor):
@@ -265,6 +342,24 @@ class NeutralDixonColesMatchPredictor(_BplxPredictor):
     def predict_score_n_proba(self, n, team, opponent, home: bool = True, neutral_venue: int = 0, max_goals: int = MAX_GOALS):
         return self._n_proba(n, team, opponent, home, max_goals, True, neutral_venue=neutral_venue)
 
+    def sample_score(self, home_team, away_team, neutral_venue, num_samples: int = 1, random_state: Optional[int] = None,
+                     max_goals: int = MAX_GOALS):
+        return self._sample_score(home_team, away_team, num_samples, random_state, max_goals, neutral_venue=neutral_venue)
+
+    def sample_outcome(self, home_team, away_team, neutral_venue, knockout: bool = False, num_samples: int = 1,
+                       random_state: Optional[int] = None, max_goals: int = MAX_GOALS):
+        return self._sample_outcome(home_team, away_team, num_samples, random_state, max_goals, knockout=knockout,
+                                    neutral_venue=neutral_venue)
+
+    def add_new_team(self, team_name: str, team_covariates: Optional[np.ndarray] = None) -> None:
+        """``neutral_dixon_coles.py:490-560`` / ``neutral_dixon_coles_WC.py:476-546``: the pair from the correlated prior,
+        the four venue effects from their own normal priors."""
+        attack, defence = self._new_team_pair(team_name, team_covariates)
+        cols = {"attack": attack, "defence": defence}
+        for nm in self._effects:
+            cols[nm] = np.random.normal(loc=getattr(self, "mean_" + nm), scale=getattr(self, "std_" + nm))
+        self._append_team(team_name, cols)
+
     def predict_concede_n_proba(self, n, team, opponent, home: bool = True, neutral_venue: int = 0,
                                 max_goals: int = MAX_GOALS):
         return self._n_proba(n, team, opponent, home, max_goals, False, neutral_venue=neutral_venue)
@@ -306,6 +401,16 @@ class NeutralDixonColesMatchPredictorWC(NeutralDixonColesMatchPredictor):
                               max_goals: int = MAX_GOALS):
         return _BplxPredictor.predict_outcome_proba(self, home_team, away_team, max_goals=max_goals, knockout=knockout,
                                                     home_conf=home_conf, away_conf=away_conf, neutral_venue=neutral_venue)
+
+    def sample_score(self, home_team, away_team, home_conf, away_conf, neutral_venue, num_samples: int = 1,
+                     random_state: Optional[int] = None, max_goals: int = MAX_GOALS):
+        return self._sample_score(home_team, away_team, num_samples, random_state, max_goals, home_conf=home_conf,
+                                  away_conf=away_conf, neutral_venue=neutral_venue)
+
+    def sample_outcome(self, home_team, away_team, home_conf, away_conf, neutral_venue, knockout: bool = False,
+                       num_samples: int = 1, random_state: Optional[int] = None, max_goals: int = MAX_GOALS):
+        return self._sample_outcome(home_team, away_team, num_samples, random_state, max_goals, knockout=knockout,
+                                    home_conf=home_conf, away_conf=away_conf, neutral_venue=neutral_venue)
 
     def _conf_kw(self, team_conf, opponent_conf, home, neutral_venue):
         hc, ac = (team_conf, opponent_conf) if home else (opponent_conf, team_conf)

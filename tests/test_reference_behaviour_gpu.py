@@ -103,6 +103,51 @@ def test_neutral_models(wc):  # tests/test_neutral_dixon_coles.py, tests/test_ne
     assert out["away_win"][nv == 1].mean() > out["away_win"][nv == 0].mean()
     ko = model.predict_outcome_proba("0", "1", *one_conf, 1, knockout=True)
     assert ko["home_win"] + ko["away_win"] == pytest.approx(1.0, abs=1e-6)
+    # simulation and a new team (neutral_dixon_coles.py:490-780, neutral_dixon_coles_WC.py:476-818)
+    sc = model.sample_score("0", "1", *one_conf, 0, num_samples=3000, random_state=1)
+    o1 = model.predict_outcome_proba("0", "1", *one_conf, 0)
+    assert abs((sc["home_score"] > sc["away_score"]).mean() - o1["home_win"][0]) < 0.04
+    who = model.sample_outcome("0", "1", *one_conf, 1, knockout=True, num_samples=3000, random_state=2)
+    assert set(np.unique(who)) <= {"0", "1"} and abs((who == "0").mean() - ko["home_win"][0]) < 0.04
+    np.random.seed(1)
+    T = model.attack.shape[1]
+    model.add_new_team("newcomer")
+    assert all(getattr(model, a).shape[1] == T + 1 for a in ("attack", "defence", "home_attack", "away_attack",
+                                                              "home_defence", "away_defence"))
+    res = model.predict_outcome_proba("newcomer", "0", *one_conf, 0)
+    assert res["home_win"][0] + res["draw"][0] + res["away_win"][0] == pytest.approx(1.0, abs=tol)
+
+
+def test_simulation_from_the_grid_and_new_teams(base_models, dummy_data):
+    """``sample_score`` / ``sample_outcome`` (bpl/base.py:150-246) and ``add_new_team`` (extended_dixon_coles.py:401-462):
+    the reference has no test for them, so the simulated frequencies are checked against the predicted probabilities."""
+    dc, ext = base_models
+    for model in base_models:
+        sc = model.sample_score(["0", "2"], ["1", "3"], num_samples=4000, random_state=3)
+        assert sc["home_score"].shape == (2, 4000) and sc["away_score"].shape == (2, 4000)
+        out = model.predict_outcome_proba(["0", "2"], ["1", "3"])
+        freq_home = (sc["home_score"] > sc["away_score"]).mean(axis=1)
+        np.testing.assert_allclose(freq_home, out["home_win"], atol=0.03)
+        p00 = model.predict_score_proba(["0", "2"], ["1", "3"], 0, 0)
+        np.testing.assert_allclose(((sc["home_score"] == 0) & (sc["away_score"] == 0)).mean(axis=1), p00, atol=0.02)
+        again = model.sample_score(["0", "2"], ["1", "3"], num_samples=4000, random_state=3)
+        assert np.array_equal(sc["home_score"], again["home_score"])
+        who = model.sample_outcome(["0", "2"], ["1", "3"], num_samples=4000, random_state=5)
+        assert who.shape == (2, 4000) and set(np.unique(who[0])) <= {"0", "1", "Draw"}
+        np.testing.assert_allclose((who[0] == "0").mean(), out["home_win"][0], atol=0.03)
+        np.testing.assert_allclose((who[1] == "Draw").mean(), out["draw"][1], atol=0.03)
+    # a team the model has not seen: drawn from the fitted priors, so it plays like an average team
+    with pytest.raises(ValueError):
+        ext.add_new_team("0")
+    np.random.seed(0)
+    T = ext.attack.shape[1]
+    ext.add_new_team("newcomer")
+    assert ext.attack.shape[1] == T + 1 and ext.defence.shape[1] == T + 1 and ext.home_advantage.shape[1] == T + 1
+    assert ext.teams[-1] == "newcomer"
+    res = ext.predict_outcome_proba("newcomer", "0")
+    assert res["home_win"][0] + res["draw"][0] + res["away_win"][0] == pytest.approx(1.0, abs=1e-5)
+    avg = np.mean([ext.predict_outcome_proba(str(t), "0")["home_win"][0] for t in range(1, 6)])
+    assert abs(res["home_win"][0] - avg) < 0.25
 
 
 def test_dynamic_fit_runs_and_tracks_a_drifting_team():
