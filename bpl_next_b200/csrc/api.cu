@@ -41,6 +41,17 @@ static int upload(bplx_problem* p, const std::vector<T>& h, const T** out) {
   return BPLX_OK;
 }
 
+// the device-side alias of a page-locked (cudaHostAlloc / cudaHostRegister, mapped) host array, else `fallback`
+static float* mapped_or(float* host, float* fallback) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
+    cudaGetLastError();
+    return fallback;
+  }
+  if (a.type == cudaMemoryTypeHost && a.devicePointer != nullptr) return static_cast<float*>(a.devicePointer);
+  return fallback;
+}
+
 static size_t workspace_bytes(const KernelParams& kp, int C) {
   const size_t Cpad = ((size_t)C + 31) / 32 * 32;
   if (kp.model == BPLX_DYNAMIC) return (size_t)kp.G * kp.T * 2 * Cpad * sizeof(float);  // the walk's prefix sums
@@ -253,12 +264,17 @@ int bplx_logdensity_fwdbwd_host(bplx_problem* p, int C, const float* theta, floa
   //  measured on configs[1], 4,096 chains: 104 us in one piece, 138 us in four)
   const int nchunk = C >= 32768 ? 4 : (C >= 16384 ? 2 : 1);
   if (nchunk == 1) {  // one piece: everything in order on one stream, no events (each costs microseconds at this scale)
+    // lp and corr_coef are one coalesced 128-byte store per warp: when the caller's arrays are page-locked the kernel
+    // writes them straight into host memory (posted PCIe writes) instead of two more copies of 6.6 us each
+    float* k_lp = mapped_or(lp, d_lp);
+    float* k_cc = corr_coef ? mapped_or(corr_coef, d_cc) : d_cc;
     BPLX_CUDA(cudaMemcpyAsync(p->d_theta, theta, (size_t)C * D * sizeof(float), cudaMemcpyHostToDevice, s));
-    int rc = enqueue(p, C, BPLX_CHAIN_MAJOR, (int)D, p->d_theta, d_lp, d_grad, d_cc, p->d_ws, p->d_ws_bytes, s);
+    int rc = enqueue(p, C, BPLX_CHAIN_MAJOR, (int)D, p->d_theta, k_lp, d_grad, k_cc, p->d_ws, p->d_ws_bytes, s);
     if (rc != BPLX_OK) return rc;
     BPLX_CUDA(cudaMemcpyAsync(grad, d_grad, (size_t)C * D * sizeof(float), cudaMemcpyDeviceToHost, s));
-    BPLX_CUDA(cudaMemcpyAsync(lp, d_lp, (size_t)C * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (corr_coef) BPLX_CUDA(cudaMemcpyAsync(corr_coef, d_cc, (size_t)C * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (k_lp == d_lp) BPLX_CUDA(cudaMemcpyAsync(lp, d_lp, (size_t)C * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (corr_coef && k_cc == d_cc)
+      BPLX_CUDA(cudaMemcpyAsync(corr_coef, d_cc, (size_t)C * sizeof(float), cudaMemcpyDeviceToHost, s));
     BPLX_CUDA(cudaStreamSynchronize(s));
     return BPLX_OK;
   }

@@ -259,3 +259,25 @@ def test_far_out_position_is_reproducible_and_rejectable():
     keep[[5, 40]] = False
     _check(arr, theta[keep].astype(np.float64), ref[0].cpu().numpy()[keep], ref[1].cpu().numpy()[keep], ref[2].cpu().numpy()[keep])
     p.close()
+
+
+def test_host_path_with_page_locked_outputs():
+    """Page-locked output arrays: the kernel writes lp and corr_coef straight into host memory (no copy); same numbers as
+    with ordinary numpy arrays."""
+    import torch
+    from bpl_next_b200 import Problem
+
+    arr = H.small_problem("extended", seed=3, weighted=True, K=3)
+    p = Problem(arr)
+    C = 77
+    theta = H.random_theta(p.D, C, seed=4, radius=1.0, dtype=np.float32)
+    lp0, g0, c0 = p.logdensity_host(theta)
+    th = torch.from_numpy(theta).pin_memory()
+    lp = torch.full((C,), -7.0).pin_memory()
+    gr = torch.zeros((C, p.D)).pin_memory()
+    cc = torch.full((C,), -7.0).pin_memory()
+    for _ in range(3):
+        p.logdensity_host(th.numpy(), lp=lp.numpy(), grad=gr.numpy(), corr_coef=cc.numpy())
+    assert np.array_equal(lp.numpy(), lp0) and np.array_equal(gr.numpy(), g0) and np.array_equal(cc.numpy(), c0)
+    _check(arr, theta.astype(np.float64), lp.numpy().copy(), gr.numpy().copy(), cc.numpy().copy())
+    p.close()
