@@ -262,7 +262,11 @@ int bplx_logdensity_fwdbwd_host(bplx_problem* p, int C, const float* theta, floa
   float* d_cc = d_lp + C;
   // (only worth it when a chunk still fills the GPU: below ~16k chains K1 is latency-bound and chunking serialises it;
   //  measured on configs[1], 4,096 chains: 104 us in one piece, 138 us in four)
-  const int nchunk = C >= 32768 ? 4 : (C >= 16384 ? 2 : 1);
+  int nchunk = C >= 32768 ? 4 : (C >= 16384 ? 2 : 1);
+  if (const char* e = getenv("BPLX_HOST_CHUNKS")) {  // tuning: 1, 2 or 4 pipelined chunks
+    const int want = atoi(e);
+    if (want == 1 || want == 2 || want == 4) nchunk = want;
+  }
   if (nchunk == 1) {  // one piece: everything in order on one stream, no events (each costs microseconds at this scale)
     // lp and corr_coef are one coalesced 128-byte store per warp: when the caller's arrays are page-locked the kernel
     // writes them straight into host memory (posted PCIe writes) instead of two more copies of 6.6 us each
