@@ -33,10 +33,7 @@ void note_launch(int n = 1);  // kernels enqueued by this library (bplx_launch_c
   } while (0)
 
 // programmatic dependent launch on the K1 / NUTS-step launches (BPLX_NO_PDL=1 turns it off: plain stream order)
-inline bool pdl_enabled() {
-  static const bool on = getenv("BPLX_NO_PDL") == nullptr;
-  return on;
-}
+inline bool pdl_enabled() { return getenv("BPLX_NO_PDL") == nullptr; }  // (read per launch: tests switch it)
 
 // ---- device helpers -----------------------------------------------------------------------
 #ifdef __CUDACC__

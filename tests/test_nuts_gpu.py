@@ -163,3 +163,34 @@ def test_runs_are_reproducible_with_the_dixon_coles_kernel():
     assert torch.equal(a.samples, b.samples) and torch.equal(a.lp, b.lp)
     assert np.array_equal(a.num_leapfrog, b.num_leapfrog)
     p.close()
+
+
+def test_dependent_launch_does_not_change_results(monkeypatch):
+    """K1 and the NUTS step start their preambles before the previous kernel of the stream has finished (programmatic
+    dependent launch).  Anything read too early would show up as a different run: with and without it, eager and as a
+    CUDA graph, the draws must be identical."""
+    import torch
+    from bpl_next_b200 import Problem
+    from oracle import datasets
+    from tests import helpers as H
+
+    arr = H.from_training_data("extended", datasets.dummy_data())
+    p = Problem(arr)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    theta0 = torch.rand((p.D, 160), generator=g, device="cuda") * 4 - 2
+
+    def potential(theta, lp, grad):
+        p.logdensity(theta, chain_minor=True, lp=lp, grad=grad)
+
+    runs = []
+    for no_pdl in (False, True):
+        if no_pdl:
+            monkeypatch.setenv("BPLX_NO_PDL", "1")
+        else:
+            monkeypatch.delenv("BPLX_NO_PDL", raising=False)
+        for graph in (True, False):
+            runs.append(bn.sample(potential, theta0.clone(), num_warmup=50, num_samples=15, seed=3, use_graph=graph))
+    for r in runs[1:]:
+        assert r.launches == runs[0].launches
+        assert torch.equal(r.samples, runs[0].samples) and torch.equal(r.lp, runs[0].lp)
+    p.close()
