@@ -64,6 +64,27 @@ def neutral_dummy_data():
             "time_diff": time_diff, "game_weights": game_weights}
 
 
+def with_covariates(td, K=3, seed=5):
+    """A reference-format data set plus `team_covariates` (dict team -> K features of different scales and offsets)."""
+    td = dict(td)
+    teams = sorted(set(td["home_team"]) | set(td["away_team"]))
+    rng = np.random.default_rng(seed)
+    td["team_covariates"] = {t: rng.normal(size=K) * (1.0 + np.arange(K)) + np.arange(K) for t in teams}
+    return td
+
+
+def ref_shim_cases():
+    """name -> (model, data set, fit kwargs): the cases of scripts/make_ref_shim_golden.py / tests/test_golden.py."""
+    return {
+        "dixon_coles": ("dixon_coles", dummy_data(), {}),
+        "extended": ("extended", dummy_data(), {}),
+        "extended_weighted_cov": ("extended", with_covariates(timed_dummy_data()), dict(epsilon=0.3, rescale_weights=True)),
+        "neutral": ("neutral", neutral_dummy_data(), {}),
+        "neutral_weighted": ("neutral", neutral_dummy_data(), dict(epsilon=0.2, rescale_weights=True)),
+        "neutral_wc": ("neutral_wc", neutral_dummy_data(), dict(epsilon=0.2)),
+    }
+
+
 def _names(n):
     w = len(str(n - 1))
     return [f"T{str(i).zfill(w)}" for i in range(n)]

@@ -1,6 +1,7 @@
 """Restatement of the five bpl-next ``_model`` log-densities in unconstrained space.
 
-TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``; parity unpinned).
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``: pinned to the reference's source run under stand-ins for jax /
+numpyro, ``oracle/ref_shim.py``; numpyro's own arithmetic is restated, not pinned).
 
 Written with torch so that the same lines give (a) float64 values + autograd gradients for parity
 (``jax.grad`` of numpyro's ``potential_energy`` is what the reference runs) and (b) a float32,

@@ -1,6 +1,6 @@
 """Restatement of the posterior-predictive path: expected goals, score proba, grid, outcome.
 
-TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``; parity unpinned).
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``: pinned to the reference's predict source run under stand-ins for jax / numpyro).
 
 Literal numpy restatement (float64 by default; ``dtype=np.float32`` reproduces the reference's
 working precision) of

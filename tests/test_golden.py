@@ -13,7 +13,10 @@ from oracle import models as om, predict as op
 from tests import helpers as H
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-DENSITY = sorted(f for f in glob.glob(os.path.join(GOLD, "*.npz")) if not os.path.basename(f).startswith("grid_"))
+DENSITY = sorted(f for f in glob.glob(os.path.join(GOLD, "*.npz"))
+                 if not os.path.basename(f).startswith(("grid_", "ref_shim_", "refgrid_")))
+REF_SOURCE = sorted(glob.glob(os.path.join(GOLD, "ref_shim_*.npz")))
+REF_GRIDS = sorted(glob.glob(os.path.join(GOLD, "refgrid_*.npz")))
 GRIDS = sorted(glob.glob(os.path.join(GOLD, "grid_*.npz")))
 
 
@@ -57,6 +60,53 @@ def test_k1_matches_golden(path):
     np.testing.assert_allclose(cc, z["corr_coef"], rtol=1e-4, atol=1e-6)
 
 
+# ---- vectors from the reference's own source ------------------------------------------------------------------------
+# tests/golden/ref_shim_*.npz were written by scripts/make_ref_shim_golden.py in the build container: the reference's
+# real fit() (its own data preparation) and _model, executed under stand-ins for the jax / numpyro names they use
+# (oracle/ref_shim.py), traced at six positions of radius 0.3 ... 2.  Log-density and gradient in numpyro's site layout.
+def _ref_case(path):
+    from oracle import datasets
+
+    name = os.path.basename(path)[len("ref_shim_"):-len(".npz")]
+    model, td, kw = datasets.ref_shim_cases()[name]
+    arr, _ = bdata.prepare(model, td, epsilon=kw.get("epsilon"), rescale_weights=kw.get("rescale_weights", False))
+    return arr, np.load(path)
+
+
+def test_reference_source_vectors_present():
+    assert len(REF_SOURCE) == 6
+
+
+@pytest.mark.parametrize("path", REF_SOURCE, ids=os.path.basename)
+def test_oracle_matches_reference_source(path):
+    """The oracle restatement (and the double-precision plan walker) against the reference's model + data-prep code.
+    Unweighted models agree to rounding; with weights / covariates the product's host prep keeps them in float32."""
+    arr, z = _ref_case(path)
+    theta = z["theta"]
+    lp, g, _ = om.log_density_and_grad(H.to_oracle(arr), theta)
+    np.testing.assert_allclose(lp, z["lp"], rtol=2e-7)
+    scale = np.abs(z["grad"]).max(axis=1, keepdims=True)
+    assert (np.abs(g - z["grad"]) / scale).max() < 1e-6
+    lp_p, g_p, _ = H.plancheck_eval(arr, theta)
+    np.testing.assert_allclose(lp_p, z["lp"], rtol=1e-6)
+    assert (np.abs(g_p - z["grad"]) / scale).max() < 2e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", REF_SOURCE, ids=os.path.basename)
+def test_k1_matches_reference_source(path):
+    """K1 against the reference's own source at BASELINE.json's tolerances (1e-5 / 1e-4 relative)."""
+    from bpl_next_b200 import Problem
+
+    arr, z = _ref_case(path)
+    p = Problem(arr)
+    lp, grad, _ = p.logdensity_host(z["theta"].astype(np.float32))
+    np.testing.assert_allclose(lp, z["lp"], rtol=1e-5)
+    scale = np.abs(z["grad"]).max(axis=1, keepdims=True)
+    assert (np.abs(grad - z["grad"]) / scale).max() < 1e-4
+    p.close()
+
+
 def _grid_inputs(z):
     s = {k[2:]: z[k] for k in z.files if k.startswith("s_")}
     fx = {k[2:]: z[k] for k in z.files if k.startswith("f_")}
@@ -82,3 +132,28 @@ def test_k3_matches_golden(path):
     grid, outcome = score_grid_host(model, s, fx, mg)
     np.testing.assert_allclose(grid, z["grid"], rtol=0, atol=1e-6)
     np.testing.assert_allclose(outcome, z["outcome"], rtol=0, atol=5e-6)
+
+
+# grids from the reference's predict source (scripts/make_ref_shim_grid_golden.py), same inputs as grid_<model>.npz
+@pytest.mark.parametrize("path", REF_GRIDS, ids=os.path.basename)
+def test_predict_oracle_matches_reference_source(path):
+    z = np.load(path)
+    model, s, fx, mg = _grid_inputs(z)
+    kw = {k: fx[k] for k in ("neutral_venue", "home_conf", "away_conf") if k in fx}
+    grid, _, _ = op.predict_score_grid_proba(model, s, fx["home_team"], fx["away_team"], mg, **kw)
+    out = op.predict_outcome_proba(model, s, fx["home_team"], fx["away_team"], mg, **kw)
+    np.testing.assert_allclose(grid, z["grid"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(np.stack([out["home_win"], out["draw"], out["away_win"]], 1), z["outcome"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", REF_GRIDS, ids=os.path.basename)
+def test_k3_matches_reference_source(path):
+    """K3 against the reference's predict source at BASELINE.json's tolerance (1e-6 absolute)."""
+    from bpl_next_b200 import score_grid_host
+
+    z = np.load(path)
+    model, s, fx, mg = _grid_inputs(z)
+    grid, outcome = score_grid_host(model, s, fx, mg)
+    np.testing.assert_allclose(grid, z["grid"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(outcome, z["outcome"], rtol=0, atol=2e-6)

@@ -1,7 +1,8 @@
 """CPU: the oracle restatement against its pins (SURVEY.md Appendix E anchors, finite differences, layout).
 
-The reference cannot run in this image (no jax / numpyro): these are the pins the "parity unpinned"
-note of oracle/__init__.py refers to."""
+The reference cannot run as published in this image (no jax / numpyro).  Its source is checked in tests/test_golden.py
+(vectors from oracle/ref_shim.py); these are the independent pins for the layer that check does not reach (numpyro's own
+arithmetic), as described in oracle/__init__.py."""
 import numpy as np
 import pytest
 import torch
