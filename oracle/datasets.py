@@ -82,6 +82,9 @@ def ref_shim_cases():
         "neutral": ("neutral", neutral_dummy_data(), {}),
         "neutral_weighted": ("neutral", neutral_dummy_data(), dict(epsilon=0.2, rescale_weights=True)),
         "neutral_wc": ("neutral_wc", neutral_dummy_data(), dict(epsilon=0.2)),
+        # the data of BASELINE.json's configs[1] and configs[2], as bench.py prepares them
+        "config_2": ("extended", config_2(), dict(epsilon=0.01)),
+        "config_3": ("neutral_wc", config_3(), dict(epsilon=0.1)),
     }
 
 

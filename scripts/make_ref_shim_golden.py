@@ -33,8 +33,9 @@ for case, (model, cls, td, kw) in CASES.items():
     offs = {k: v for k, v in om.layout_offsets(layout).items() if k != "__D__"}
     D = om.num_params(model, arr.num_teams, K, arr.num_conferences or 0, 0)
     rng = np.random.default_rng(7)
-    n = 6
-    theta = rng.uniform(-1.0, 1.0, (n, D)) * np.array([0.3, 0.6, 1.0, 1.0, 1.5, 2.0])[:, None]
+    radii = np.array([0.3, 0.6, 1.0, 1.0, 1.5, 2.0]) if D < 200 else np.array([0.3, 1.0, 2.0])  # (the big configs: three)
+    n = len(radii)
+    theta = rng.uniform(-1.0, 1.0, (n, D)) * radii[:, None]
     lps, grads = [], []
     for i in range(n):
         vals = {}

@@ -74,7 +74,7 @@ def _ref_case(path):
 
 
 def test_reference_source_vectors_present():
-    assert len(REF_SOURCE) == 6
+    assert len(REF_SOURCE) == 8
 
 
 @pytest.mark.parametrize("path", REF_SOURCE, ids=os.path.basename)
