@@ -157,3 +157,55 @@ def test_k3_matches_reference_source(path):
     grid, outcome = score_grid_host(model, s, fx, mg)
     np.testing.assert_allclose(grid, z["grid"], rtol=0, atol=1e-6)
     np.testing.assert_allclose(outcome, z["outcome"], rtol=0, atol=2e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", REF_GRIDS, ids=os.path.basename)
+def test_predictor_api_matches_reference_source(path):
+    """The mirrored predictor classes, given the same posterior samples as the reference's classes, against what the
+    reference's own predict_score_n_proba / predict_concede_n_proba / predict_score_proba / knockout code returned."""
+    import bpl_next_b200 as bp
+
+    z = np.load(path)
+    model, s, fx, mg = _grid_inputs(z)
+    cls = {"dixon_coles": bp.DixonColesMatchPredictor, "extended": bp.ExtendedDixonColesMatchPredictor,
+           "neutral": bp.NeutralDixonColesMatchPredictor, "neutral_wc": bp.NeutralDixonColesMatchPredictorWC}[model]
+    m = cls()
+    T = s["attack"].shape[1]
+    m.teams = np.array([str(i) for i in range(T)])
+    m._teams_dict = {str(i): i for i in range(T)}
+    for k, v in s.items():
+        setattr(m, k, v)
+    h, a = [str(i) for i in fx["home_team"]], [str(i) for i in fx["away_team"]]
+    n = np.arange(mg + 1)
+    one, zero = np.ones(len(h), dtype=int), np.zeros(len(h), dtype=int)
+    if model == "neutral_wc":
+        Cf = s["confederation_strength"].shape[1]
+        m.conferences = np.array([str(i) for i in range(Cf)])
+        m._conferences_dict = {str(i): i for i in range(Cf)}
+        hc, ac, nv = [str(i) for i in fx["home_conf"]], [str(i) for i in fx["away_conf"]], fx["neutral_venue"].astype(int)
+        got = dict(score_home=m.predict_score_n_proba(n, h[0], a[0], hc[0], ac[0], home=True, neutral_venue=int(nv[0]), max_goals=mg),
+                   score_away=m.predict_score_n_proba(n, a[0], h[0], ac[0], hc[0], home=False, neutral_venue=int(nv[0]), max_goals=mg),
+                   concede_home=m.predict_concede_n_proba(n, h[0], a[0], hc[0], ac[0], home=True, neutral_venue=int(nv[0]), max_goals=mg),
+                   concede_away=m.predict_concede_n_proba(n, a[0], h[0], ac[0], hc[0], home=False, neutral_venue=int(nv[0]), max_goals=mg),
+                   score_1_0=m.predict_score_proba(h, a, hc, ac, one, zero, nv))
+        ko = m.predict_outcome_proba(h, a, hc, ac, nv, knockout=True, max_goals=mg)
+    elif model == "neutral":
+        nv = fx["neutral_venue"].astype(int)
+        got = dict(score_home=m.predict_score_n_proba(n, h[0], a[0], home=True, neutral_venue=int(nv[0]), max_goals=mg),
+                   score_away=m.predict_score_n_proba(n, a[0], h[0], home=False, neutral_venue=int(nv[0]), max_goals=mg),
+                   concede_home=m.predict_concede_n_proba(n, h[0], a[0], home=True, neutral_venue=int(nv[0]), max_goals=mg),
+                   concede_away=m.predict_concede_n_proba(n, a[0], h[0], home=False, neutral_venue=int(nv[0]), max_goals=mg),
+                   score_1_0=m.predict_score_proba(h, a, one, zero, nv))
+        ko = m.predict_outcome_proba(h, a, nv, knockout=True, max_goals=mg)
+    else:
+        got = dict(score_home=m.predict_score_n_proba(n, h[0], a[0], home=True, max_goals=mg),
+                   score_away=m.predict_score_n_proba(n, a[0], h[0], home=False, max_goals=mg),
+                   concede_home=m.predict_concede_n_proba(n, h[0], a[0], home=True, max_goals=mg),
+                   concede_away=m.predict_concede_n_proba(n, a[0], h[0], home=False, max_goals=mg),
+                   score_1_0=m.predict_score_proba(h, a, one, zero))
+        ko = None
+    for k, v in got.items():
+        np.testing.assert_allclose(np.asarray(v), z["api_" + k], rtol=0, atol=2e-6, err_msg=k)
+    if ko is not None:
+        np.testing.assert_allclose(np.stack([ko["home_win"], ko["away_win"]], 1), z["api_knockout"], rtol=0, atol=5e-6)
