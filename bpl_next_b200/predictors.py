@@ -246,7 +246,11 @@ class DixonColesMatchPredictor(_BplxPredictor):
     def fit(self, training_data, random_state: int = 42, num_warmup: int = 500, num_samples: int = 1000,
             mcmc_kwargs: Optional[Dict[str, Any]] = None, run_kwargs: Optional[Dict[str, Any]] = None):
         arr, s = self._fit(training_data, random_state, num_warmup, num_samples, mcmc_kwargs)
-        self.attack = s["std_attack"][:, None] * s["attack_decentered"]  # dixon_coles.py:52-61
+        return self._set_posterior(arr, s)
+
+    def _set_posterior(self, arr, s):
+        """Constrained draws of the latent sites -> the sites the reference records (dixon_coles.py:52-61)."""
+        self.attack = s["std_attack"][:, None] * s["attack_decentered"]
         self.defence = s["mean_defence"][:, None] + s["std_defence"][:, None] * s["defence_decentered"]
         self.home_advantage = s["home_advantage"]
         self.corr_coef = s["corr_coef"]
@@ -265,8 +269,12 @@ class ExtendedDixonColesMatchPredictor(_BplxPredictor):
             epsilon: Optional[float] = None, rescale_weights: bool = False,
             mcmc_kwargs: Optional[Dict[str, Any]] = None, run_kwargs: Optional[Dict[str, Any]] = None):
         arr, s = self._fit(training_data, random_state, num_warmup, num_samples, mcmc_kwargs, epsilon, rescale_weights)
+        return self._set_posterior(arr, s)
+
+    def _set_posterior(self, arr, s):
+        """Constrained draws of the latent sites -> the sites the reference records (extended_dixon_coles.py:182-187)."""
         am, dm = self._prior_means(arr, s)
-        self.attack = am + s["standardised_attack"] * s["std_attack"][:, None]  # :182-187
+        self.attack = am + s["standardised_attack"] * s["std_attack"][:, None]
         self.defence = dm + s["standardised_defence"] * s["std_defence"][:, None]
         self.home_advantage = s["mean_home_advantage"][:, None] + s["std_home_advantage"][:, None] * s["home_advantage_decentered"]
         self.corr_coef = s["corr_coef"]
@@ -300,6 +308,10 @@ class NeutralDixonColesMatchPredictor(_BplxPredictor):
             num_warmup: int = 500, num_samples: int = 1000, mcmc_kwargs: Optional[Dict[str, Any]] = None,
             run_kwargs: Optional[Dict[str, Any]] = None):
         arr, s = self._fit(training_data, random_state, num_warmup, num_samples, mcmc_kwargs, epsilon, rescale_weights)
+        return self._set_posterior(arr, s)
+
+    def _set_posterior(self, arr, s):
+        """Constrained draws of the latent sites -> the sites the reference records."""
         am, dm = self._prior_means(arr, s)
         self.attack = am + s["standardised_attack"] * s["std_attack"][:, None]
         self.defence = dm + s["standardised_defence"] * s["std_defence"][:, None]

@@ -36,7 +36,7 @@ for case, (model, cls, td, kw) in CASES.items():
     radii = np.array([0.3, 0.6, 1.0, 1.0, 1.5, 2.0]) if D < 200 else np.array([0.3, 1.0, 2.0])  # (the big configs: three)
     n = len(radii)
     theta = rng.uniform(-1.0, 1.0, (n, D)) * radii[:, None]
-    lps, grads = [], []
+    lps, grads, dets = [], [], {}
     for i in range(n):
         vals = {}
         for name, (o, shape, _tr) in offs.items():
@@ -52,8 +52,10 @@ for case, (model, cls, td, kw) in CASES.items():
                 flat[o:o + cnt] = np.asarray(g[name]).reshape(-1)
         lps.append(lp)
         grads.append(flat)
+        for k, v in det.items():  # the deterministic sites the reference's fit() reads back from the samples
+            dets.setdefault(k, []).append(np.asarray(v))
     np.savez_compressed(os.path.join(OUT, f"ref_shim_{case}.npz"), theta=theta, lp=np.array(lps), grad=np.array(grads),
-                        model=model, kwargs=repr(kw))
+                        model=model, kwargs=repr(kw), **{"det_" + k: np.array(v) for k, v in dets.items()})
     # the oracle on the same positions, right away (the committed test repeats this without the reference)
     lo, go, _ = om.log_density_and_grad(H.to_oracle(arr), theta)
     err_lp = np.max(np.abs(lo - np.array(lps)) / np.maximum(1.0, np.abs(np.array(lps))))

@@ -209,3 +209,37 @@ def test_predictor_api_matches_reference_source(path):
         np.testing.assert_allclose(np.asarray(v), z["api_" + k], rtol=0, atol=2e-6, err_msg=k)
     if ko is not None:
         np.testing.assert_allclose(np.stack([ko["home_win"], ko["away_win"]], 1), z["api_knockout"], rtol=0, atol=5e-6)
+
+
+@pytest.mark.parametrize("path", REF_SOURCE, ids=os.path.basename)
+def test_recorded_sites_match_reference_source(path):
+    """`fit()` turns the latent draws into the sites the reference records (attack, defence, venue effects, rho,
+    corr_coef, ...): the mirror's transforms + `_set_posterior` against the deterministic sites of the reference's own
+    model trace at the same unconstrained positions."""
+    import bpl_next_b200 as bp
+    from bpl_next_b200.predictors import constrain
+    from oracle import datasets
+
+    name = os.path.basename(path)[len("ref_shim_"):-len(".npz")]
+    model, td, kw = datasets.ref_shim_cases()[name]
+    arr, meta = bdata.prepare(model, td, epsilon=kw.get("epsilon"), rescale_weights=kw.get("rescale_weights", False))
+    z = np.load(path)
+    K = 0 if arr.covariates is None else arr.covariates.shape[1]
+    offs = om.layout_offsets(om.site_layout(model, arr.num_teams, K, arr.num_conferences or 0, 0))
+    layout = {k: (o, int(np.prod(shape)) if shape else 1, tr) for k, (o, shape, tr) in offs.items() if k != "__D__"}
+    layout = {k: v for k, v in layout.items() if v[1] > 0}
+    s = constrain(z["theta"], layout)
+    s["corr_coef"] = om.log_density_and_grad(H.to_oracle(arr), z["theta"])[2].astype(np.float32)
+    cls = {"dixon_coles": bp.DixonColesMatchPredictor, "extended": bp.ExtendedDixonColesMatchPredictor,
+           "neutral": bp.NeutralDixonColesMatchPredictor, "neutral_wc": bp.NeutralDixonColesMatchPredictorWC}[model]
+    m = cls()
+    m._meta, m.teams, m._teams_dict = meta, meta["teams"], meta["teams_dict"]
+    m._set_posterior(arr, s)
+    checked = 0
+    for key in z.files:
+        if not key.startswith("det_"):
+            continue
+        got = getattr(m, key[4:])
+        np.testing.assert_allclose(np.asarray(got, dtype=np.float64), z[key], rtol=2e-5, atol=2e-6, err_msg=key)
+        checked += 1
+    assert checked >= 3
