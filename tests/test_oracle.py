@@ -120,3 +120,31 @@ def test_predict_oracle_properties():
     assert np.all(grid >= 0) and np.all(grid <= 1)
     out = op.predict_outcome_proba("extended", s, h, a, 15)
     np.testing.assert_allclose(out["home_win"] + out["draw"] + out["away_win"], 1.0, atol=1e-5)
+
+
+def test_distribution_and_transform_arithmetic_against_scipy():
+    """The layer the reference-source check does not reach (numpyro's own arithmetic) against an independent library:
+    the four log-densities the models use against scipy.stats, and the two transforms' log|det J| against the closed
+    forms d exp(u)/du = exp(u), d sigmoid(u)/du = sigmoid(u)(1 - sigmoid(u)) and against autograd."""
+    import scipy.stats as st
+
+    rng = np.random.default_rng(0)
+    x = torch.tensor(rng.normal(size=200) * 3.0, dtype=torch.float64)
+    loc, scale = 0.3, 1.7
+    np.testing.assert_allclose(om._normal_lp(x, loc, scale).numpy(), st.norm.logpdf(x.numpy(), loc, scale), rtol=1e-12)
+    pos = torch.tensor(np.abs(rng.normal(size=200)) * 2.0 + 1e-3, dtype=torch.float64)
+    np.testing.assert_allclose(om._halfnormal_lp(pos, 1.3).numpy(), st.halfnorm.logpdf(pos.numpy(), scale=1.3), rtol=1e-12)
+    u01 = torch.tensor(rng.uniform(1e-4, 1 - 1e-4, 200), dtype=torch.float64)
+    for c1, c0 in ((2.0, 2.0), (2.0, 4.0)):  # the two Beta priors of the models (corr_coef_raw, u)
+        np.testing.assert_allclose(om._beta_lp(u01, c1, c0).numpy(), st.beta.logpdf(u01.numpy(), c1, c0), rtol=1e-11)
+    k = torch.tensor(rng.poisson(2.0, 200).astype(np.float64))
+    rate = torch.tensor(rng.uniform(0.05, 14.0, 200), dtype=torch.float64)
+    np.testing.assert_allclose(om._poisson_lp(k, rate).numpy(), st.poisson.logpmf(k.numpy(), rate.numpy()), rtol=1e-11)
+    u = torch.tensor(rng.normal(size=200) * 4.0, dtype=torch.float64, requires_grad=True)
+    val, lj = om._exp_site(u)
+    np.testing.assert_allclose(lj.detach().numpy(), np.log(np.exp(u.detach().numpy())), rtol=1e-12, atol=1e-12)
+    val, lj = om._sigmoid_site(u)
+    sg = 1.0 / (1.0 + np.exp(-u.detach().numpy()))
+    np.testing.assert_allclose(lj.detach().numpy(), np.log(sg * (1.0 - sg)), rtol=1e-10)
+    (dval,) = torch.autograd.grad(val.sum(), u)
+    np.testing.assert_allclose(np.log(dval.numpy()), lj.detach().numpy(), rtol=1e-10)
