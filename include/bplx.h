@@ -113,6 +113,14 @@ int bplx_problem_stats(const bplx_problem* p, long long* out, int n);
  * the potential energy, and grad is d lp / d theta.) */
 size_t bplx_logdensity_workspace_bytes(const bplx_problem* p, int num_chains);
 
+/*
+ * Asynchronous on `stream`, capturable in a CUDA graph.  The kernel is launched with programmatic stream
+ * serialization: its set-up (parameters, static plan) may overlap the end of the previous kernel of the stream, and
+ * everything that reads theta or writes an output waits for that kernel to complete -- stream order is what the caller
+ * sees.  Results are a pure function of the inputs (bit-reproducible).  A log-density that overflowed float32 far from
+ * the typical set is reported as NaN, never as +inf.  While the call runs, grad doubles as scratch.
+ */
+
 int bplx_logdensity_fwdbwd(const bplx_problem* p, int num_chains, int layout, int ld,
                            const float* theta,   /* device, [C, D] or [D, ld] */
                            float* lp,            /* device, [C] */
@@ -121,7 +129,8 @@ int bplx_logdensity_fwdbwd(const bplx_problem* p, int num_chains, int layout, in
                            void* workspace, size_t workspace_bytes,
                            void* stream);
 
-/* host-buffer variant (chain-major [C, D]); copies in/out inside the call, returns when done. */
+/* host-buffer variant (chain-major [C, D]); copies in/out inside the call, returns when done.  Page-locked (pinned)
+ * arrays are copied by DMA without staging, and lp / corr_coef are then written by the kernel straight into them. */
 int bplx_logdensity_fwdbwd_host(bplx_problem* p, int num_chains,
                                 const float* theta, float* lp, float* grad, float* corr_coef);
 
