@@ -194,3 +194,50 @@ def test_dependent_launch_does_not_change_results(monkeypatch):
         assert r.launches == runs[0].launches
         assert torch.equal(r.samples, runs[0].samples) and torch.equal(r.lp, runs[0].lp)
     p.close()
+
+
+def test_posterior_matches_independent_cpu_sampler():
+    """Posterior means and spreads of a GPU fit (K1 + the NUTS kernel) against tests/golden/posterior_dixon_coles.npz:
+    plain HMC on the float64 CPU oracle density, an independent sampler sharing no code with the CUDA path
+    (scripts/make_posterior_golden.py; R-hat <= 1.006, ESS >= 1e4 there).  Every component must agree within 5 combined
+    Monte-Carlo standard errors -- BASELINE.json: "posterior means and quantiles within Monte-Carlo standard error"."""
+    import os
+    import torch
+    from bpl_next_b200 import Problem, diagnostics as dg
+    from oracle import datasets
+    from tests import helpers as H
+
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "posterior_dixon_coles.npz"))
+    arr = H.from_training_data("dixon_coles", datasets.dummy_data())
+    p = Problem(arr)
+    C = 512
+    g = torch.Generator(device="cuda").manual_seed(21)
+    theta0 = torch.rand((p.D, C), generator=g, device="cuda") * 4 - 2
+
+    def potential(theta, lp, grad):
+        p.logdensity(theta, chain_minor=True, lp=lp, grad=grad)
+
+    run = bn.sample(potential, theta0, num_warmup=400, num_samples=120, seed=9)
+    x = run.samples  # [N, D, C] unconstrained
+    lay = p.layout
+
+    def site(name):
+        o, n, _ = lay[name]
+        return x[:, o:o + n, :]
+
+    std_a, std_d = torch.exp(site("std_attack")), torch.exp(site("std_defence"))
+    N = x.shape[0]
+    flat = x.permute(0, 2, 1).reshape(N * C, p.D).contiguous()
+    cc = p.logdensity(flat)[2].reshape(N, C)[:, None, :]
+    q = {"attack": std_a * site("attack_decentered"), "defence": site("mean_defence") + std_d * site("defence_decentered"),
+         "home_advantage": site("home_advantage"), "std_attack": std_a, "std_defence": std_d, "corr_coef": cc}
+    assert float(dg.split_rhat(x).max()) < 1.02
+    for k, v in q.items():
+        ess = dg.effective_sample_size(v.contiguous()).double().cpu().numpy()
+        mean = v.double().mean(dim=(0, 2)).cpu().numpy()
+        sd = v.double().permute(1, 0, 2).reshape(v.shape[1], -1).std(dim=1).cpu().numpy()
+        mcse = np.sqrt((sd / np.sqrt(ess)) ** 2 + gold[k + "_mcse"] ** 2)
+        z = np.abs(mean - gold[k + "_mean"]) / mcse
+        assert z.max() < 5.0, (k, z.max(), mean, gold[k + "_mean"])
+        np.testing.assert_allclose(sd, gold[k + "_sd"], rtol=0.08, err_msg=k)
+    p.close()
