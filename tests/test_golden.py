@@ -14,7 +14,7 @@ from tests import helpers as H
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 DENSITY = sorted(f for f in glob.glob(os.path.join(GOLD, "*.npz"))
-                 if not os.path.basename(f).startswith(("grid_", "ref_shim_", "refgrid_")))
+                 if not os.path.basename(f).startswith(("grid_", "ref_shim_", "refgrid_", "posterior_")))
 REF_SOURCE = sorted(glob.glob(os.path.join(GOLD, "ref_shim_*.npz")))
 REF_GRIDS = sorted(glob.glob(os.path.join(GOLD, "refgrid_*.npz")))
 GRIDS = sorted(glob.glob(os.path.join(GOLD, "grid_*.npz")))
