@@ -12,11 +12,16 @@ from tests import helpers as H
 from bpl_next_b200 import diagnostics as dg
 
 torch.set_num_threads(os.cpu_count() or 8)
-arr = H.from_training_data("dixon_coles", datasets.dummy_data())
+MODEL = sys.argv[1] if len(sys.argv) > 1 else "dixon_coles"  # or neutral_wc
+if MODEL == "dixon_coles":
+    arr = H.from_training_data("dixon_coles", datasets.dummy_data())
+else:
+    arr = H.from_training_data("neutral_wc", datasets.neutral_dummy_data(), epsilon=0.2)
 d = H.to_oracle(arr)
 T = arr.num_teams
-D = om.num_params("dixon_coles", T)
-offs = om.layout_offsets(om.site_layout("dixon_coles", T))
+Cf = arr.num_conferences or 0
+D = om.num_params(MODEL, T, 0, Cf)
+offs = om.layout_offsets(om.site_layout(MODEL, T, 0, Cf))
 rng = np.random.default_rng(123)
 C, L = 64, 12
 
@@ -79,8 +84,14 @@ def site(name):
 
 
 std_a, std_d = np.exp(site("std_attack")), np.exp(site("std_defence"))
-q = {"attack": std_a * site("attack_decentered"), "defence": site("mean_defence") + std_d * site("defence_decentered"),
-     "home_advantage": site("home_advantage"), "std_attack": std_a, "std_defence": std_d}
+if MODEL == "dixon_coles":
+    q = {"attack": std_a * site("attack_decentered"), "defence": site("mean_defence") + std_d * site("defence_decentered"),
+         "home_advantage": site("home_advantage"), "std_attack": std_a, "std_defence": std_d}
+else:
+    q = {"attack": std_a * site("standardised_attack"), "defence": site("mean_defence") + std_d * site("standardised_defence"),
+         "std_attack": std_a, "std_defence": std_d, "confederation_strength": site("confederation_strength_decentered")}
+    for nm in ("home_attack", "away_attack", "home_defence", "away_defence"):
+        q[nm] = site("mean_" + nm) + np.exp(site("std_" + nm)) * site(nm + "_decentered")
 cc = np.stack([om.log_density_and_grad(d, draws[i])[2] for i in range(0, N, 3)], 0)  # every third draw is plenty
 q["corr_coef"] = cc[:, :, None]
 out = {}
@@ -91,4 +102,4 @@ for k, v in q.items():
     mean, sd = v.mean(axis=(0, 1)), v.reshape(-1, v.shape[-1]).std(axis=0)
     out[k + "_mean"], out[k + "_sd"], out[k + "_mcse"], out[k + "_rhat"] = mean, sd, sd / np.sqrt(ess), rhat
     print(f"{k:16s} rhat max {rhat.max():.3f} ess min {ess.min():.0f} mean[0] {mean[0]:+.4f} sd[0] {sd[0]:.4f} mcse[0] {(sd / np.sqrt(ess))[0]:.4f}")
-np.savez_compressed(os.path.join(ROOT, "tests", "golden", "posterior_dixon_coles.npz"), **out)
+np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"posterior_{MODEL}.npz"), **out)
