@@ -13,8 +13,8 @@ from bpl_next_b200 import diagnostics as dg
 
 torch.set_num_threads(os.cpu_count() or 8)
 MODEL = sys.argv[1] if len(sys.argv) > 1 else "dixon_coles"  # or neutral_wc
-if MODEL == "dixon_coles":
-    arr = H.from_training_data("dixon_coles", datasets.dummy_data())
+if MODEL in ("dixon_coles", "extended"):
+    arr = H.from_training_data(MODEL, datasets.dummy_data())
 else:
     arr = H.from_training_data("neutral_wc", datasets.neutral_dummy_data(), epsilon=0.2)
 d = H.to_oracle(arr)
@@ -87,6 +87,11 @@ std_a, std_d = np.exp(site("std_attack")), np.exp(site("std_defence"))
 if MODEL == "dixon_coles":
     q = {"attack": std_a * site("attack_decentered"), "defence": site("mean_defence") + std_d * site("defence_decentered"),
          "home_advantage": site("home_advantage"), "std_attack": std_a, "std_defence": std_d}
+elif MODEL == "extended":
+    sig = 1.0 / (1.0 + np.exp(-site("u")))
+    q = {"attack": std_a * site("standardised_attack"), "defence": site("mean_defence") + std_d * site("standardised_defence"),
+         "home_advantage": site("mean_home_advantage") + np.exp(site("std_home_advantage")) * site("home_advantage_decentered"),
+         "rho": 2.0 * sig - 1.0, "std_attack": std_a, "std_defence": std_d}
 else:
     q = {"attack": std_a * site("standardised_attack"), "defence": site("mean_defence") + std_d * site("standardised_defence"),
          "std_attack": std_a, "std_defence": std_d, "confederation_strength": site("confederation_strength_decentered")}

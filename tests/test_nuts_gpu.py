@@ -196,7 +196,7 @@ def test_dependent_launch_does_not_change_results(monkeypatch):
     p.close()
 
 
-@pytest.mark.parametrize("model", ["dixon_coles", "neutral_wc"])
+@pytest.mark.parametrize("model", ["dixon_coles", "extended", "neutral_wc"])
 def test_posterior_matches_independent_cpu_sampler(model):
     """Posterior means and spreads of a GPU fit (K1 + the NUTS kernel) against tests/golden/posterior_<model>.npz:
     plain HMC on the float64 CPU oracle density, an independent sampler sharing no code with the CUDA path
@@ -209,8 +209,8 @@ def test_posterior_matches_independent_cpu_sampler(model):
     from tests import helpers as H
 
     gold = np.load(os.path.join(os.path.dirname(__file__), "golden", f"posterior_{model}.npz"))
-    if model == "dixon_coles":
-        arr = H.from_training_data("dixon_coles", datasets.dummy_data())
+    if model in ("dixon_coles", "extended"):
+        arr = H.from_training_data(model, datasets.dummy_data())
     else:
         arr = H.from_training_data("neutral_wc", datasets.neutral_dummy_data(), epsilon=0.2)
     p = Problem(arr)
@@ -237,6 +237,10 @@ def test_posterior_matches_independent_cpu_sampler(model):
     if model == "dixon_coles":
         q = {"attack": std_a * site("attack_decentered"), "defence": site("mean_defence") + std_d * site("defence_decentered"),
              "home_advantage": site("home_advantage")}
+    elif model == "extended":
+        q = {"attack": std_a * site("standardised_attack"), "defence": site("mean_defence") + std_d * site("standardised_defence"),
+             "home_advantage": site("mean_home_advantage") + torch.exp(site("std_home_advantage")) * site("home_advantage_decentered"),
+             "rho": 2.0 * torch.sigmoid(site("u")) - 1.0}
     else:
         q = {"attack": std_a * site("standardised_attack"), "defence": site("mean_defence") + std_d * site("standardised_defence"),
              "confederation_strength": site("confederation_strength_decentered")}
