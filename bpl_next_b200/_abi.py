@@ -88,6 +88,8 @@ def declare(lib):
     lib.bplx_score_grid.restype = i
     lib.bplx_score_grid_host.argtypes = [C.POINTER(Samples), C.POINTER(Fixtures), i, C.c_float, vp, vp]
     lib.bplx_score_grid_host.restype = i
+    lib.bplx_reload_env.argtypes = []
+    lib.bplx_reload_env.restype = None
     lib.bplx_last_error.argtypes = []
     lib.bplx_last_error.restype = C.c_char_p
     lib.bplx_version.argtypes = []

@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <mutex>
 #include <new>
 
 #include "common.cuh"
@@ -23,6 +24,22 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void note_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+static EnvSwitches g_env;
+static std::once_flag g_env_once;
+void reload_env_switches() {
+  EnvSwitches e;
+  e.no_pdl = getenv("BPLX_NO_PDL") != nullptr;
+  e.nuts_generic = getenv("BPLX_NUTS_GENERIC") != nullptr;
+  e.no_tail_split = getenv("BPLX_NO_TAIL_SPLIT") != nullptr;
+  if (const char* v = getenv("BPLX_SPLIT")) e.split = atoi(v);
+  if (const char* v = getenv("BPLX_HOST_CHUNKS")) e.host_chunks = atoi(v);
+  g_env = e;
+}
+const EnvSwitches& env_switches() {
+  std::call_once(g_env_once, reload_env_switches);
+  return g_env;
+}
 
 constexpr size_t kUploadSlack = (size_t)kMaxSplit * kMaxWarps * sizeof(EntryClip) + 64;
 template <typename T>
@@ -96,8 +113,7 @@ static int enqueue(const bplx_problem* p, int C, int layout, int ld, const float
       si = i;
       break;
     }
-  if (const char* e = getenv("BPLX_SPLIT")) {  // testing / tuning: force 1, 2, 4 or 8 CTAs per group
-    const int want = atoi(e);
+  if (const int want = env_switches().split) {  // testing / tuning: force 1, 2, 4 or 8 CTAs per group
     for (int i = 0; i < kNumSplits; i++)
       if ((1 << i) == want && p->s1[i] && (i == 0 || p->max_clusters[i] > 0)) si = i;
   }
@@ -263,10 +279,8 @@ int bplx_logdensity_fwdbwd_host(bplx_problem* p, int C, const float* theta, floa
   // (only worth it when a chunk still fills the GPU: below ~16k chains K1 is latency-bound and chunking serialises it;
   //  measured on configs[1], 4,096 chains: 104 us in one piece, 138 us in four)
   int nchunk = C >= 32768 ? 4 : (C >= 16384 ? 2 : 1);
-  if (const char* e = getenv("BPLX_HOST_CHUNKS")) {  // tuning: 1, 2 or 4 pipelined chunks
-    const int want = atoi(e);
+  if (const int want = env_switches().host_chunks)  // tuning: 1, 2 or 4 pipelined chunks
     if (want == 1 || want == 2 || want == 4) nchunk = want;
-  }
   if (nchunk == 1) {  // one piece: everything in order on one stream, no events (each costs microseconds at this scale)
     // lp and corr_coef are one coalesced 128-byte store per warp: when the caller's arrays are page-locked the kernel
     // writes them straight into host memory (posted PCIe writes) instead of two more copies of 6.6 us each
@@ -313,8 +327,7 @@ static int check_grid_args(const bplx_samples* s, const bplx_fixtures* f, int ma
   BPLX_REQUIRE(max_goals >= 1 && max_goals <= 63, BPLX_E_INVALID, "max_goals must be in [1, 63] (got %d)", max_goals);
   BPLX_REQUIRE(s->attack && s->defence && s->corr_coef && f->home_team && f->away_team, BPLX_E_INVALID,
                "score grid: attack, defence, corr_coef, home_team, away_team must not be NULL");
-  if (s->model != BPLX_DIXON_COLES || true)
-    BPLX_REQUIRE(s->home_attack, BPLX_E_INVALID, "score grid: home_attack (home advantage) must not be NULL");
+  BPLX_REQUIRE(s->home_attack, BPLX_E_INVALID, "score grid: home_attack (home advantage) must not be NULL");
   if (s->model == BPLX_NEUTRAL || s->model == BPLX_NEUTRAL_WC)
     BPLX_REQUIRE(s->away_attack && s->home_defence && s->away_defence, BPLX_E_INVALID,
                  "score grid: neutral models need away_attack, home_defence, away_defence");
@@ -371,6 +384,15 @@ int bplx_score_grid_host(const bplx_samples* s, const bplx_fixtures* f, int max_
   BPLX_REQUIRE(grid != nullptr, BPLX_E_INVALID, "grid is NULL");
   const size_t S = s->num_samples, T = s->num_teams, F = f->num_fixtures, g = max_goals + 1;
   const size_t Cf = s->model == BPLX_NEUTRAL_WC ? s->num_conferences : 0;
+  for (size_t i = 0; i < F; i++) {  // host arrays: an out-of-range index would read past the staged sample rows
+    BPLX_REQUIRE(f->home_team[i] < T && f->away_team[i] < T, BPLX_E_INVALID,
+                 "score grid: team index out of range at fixture %zu (%u, %u; num_teams %zu)", i,
+                 (unsigned)f->home_team[i], (unsigned)f->away_team[i], T);
+    if (Cf)
+      BPLX_REQUIRE(f->home_conf[i] < Cf && f->away_conf[i] < Cf, BPLX_E_INVALID,
+                   "score grid: confederation index out of range at fixture %zu (%u, %u; num_conferences %zu)", i,
+                   (unsigned)f->home_conf[i], (unsigned)f->away_conf[i], Cf);
+  }
   std::vector<void*> allocs;
   auto cleanup = [&]() {
     for (void* d : allocs) cudaFree(d);
@@ -438,6 +460,10 @@ int bplx_score_grid_host(const bplx_samples* s, const bplx_fixtures* f, int max_
   return rc;
 }
 
+void bplx_reload_env(void) {
+  env_switches();
+  reload_env_switches();
+}
 const char* bplx_last_error(void) { return g_err; }
 int bplx_version(void) { return BPLX_VERSION; }
 unsigned long long bplx_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

@@ -58,6 +58,35 @@ __device__ __forceinline__ void reduce_y(float (&v)[N], float* red) {
   }
 }
 
+// Streaming diagnostics (include/bplx_nuts.h): draw number k (0-based, post warm-up) of the chain / parameter at element
+// offset o of a [D][ld] plane; `plane` = D * ld elements.
+__device__ __forceinline__ void diag_collect(const bplx_nuts_params& P, int k, size_t o, size_t plane, float x) {
+  const int L = P.diag_lags, N = P.num_samples, h = N / 2;
+  float ref = x;
+  if (k == 0) P.dg_ref[o] = x;
+  else ref = P.dg_ref[o];
+  const float v = x - ref;
+  float* s = P.dg_sums + o;
+  s[0] += v;
+  s[plane] = fmaf(v, v, s[plane]);
+  if (k < h) {
+    s[2 * plane] += v;
+    s[3 * plane] = fmaf(v, v, s[3 * plane]);
+  }
+  if (k >= N - h) {
+    s[4 * plane] += v;
+    s[5 * plane] = fmaf(v, v, s[5 * plane]);
+  }
+  const int nl = k < L ? k : L;
+  for (int l = 1; l <= nl; l++) {
+    const float prev = P.dg_ring[(size_t)((k - l) % L) * plane + o];
+    float* q = P.dg_lag + (size_t)(l - 1) * plane + o;
+    *q = fmaf(v, prev, *q);
+  }
+  P.dg_ring[(size_t)(k % L) * plane + o] = v;
+  if (k < L) P.dg_head[(size_t)k * plane + o] = v;
+}
+
 }  // namespace
 
 // block = (32 chains, Y slices).  Thread (x, y) owns parameters d = y, y+Y, ... of chain x; the scalar state machine
@@ -256,6 +285,8 @@ __global__ void __launch_bounds__(32 * kNutsMaxY) nuts_step_kernel(const bplx_nu
       if (at_end) st.window += 1;
     } else {
       const int k = st.t - P.num_warmup;
+      if (P.diag_lags > 0)
+        for (int d = y; d < D; d += Y) diag_collect(P, k, (size_t)d * ld + c, (size_t)D * ld, zP[d]);
       if (k % P.thin == 0 && k / P.thin < P.num_keep) {
         const int slot = k / P.thin;
         float* out = P.samples + (size_t)slot * D * ld + c;
@@ -649,6 +680,11 @@ __global__ void __launch_bounds__(512) nuts_step_fast_kernel(const bplx_nuts_par
       if (at_end) st.window += 1;
     } else {
       const int k = st.t - P.num_warmup;
+      if (P.diag_lags > 0) {
+#pragma unroll
+        for (int j = 0; j < NPT; j++)
+          if (has[j]) diag_collect(P, k, off[j], (size_t)D * ld, zP[j]);
+      }
       if (k % P.thin == 0 && k / P.thin < P.num_keep) {
         const int slot = k / P.thin;
         stv(P.samples + (size_t)slot * D * ld, zP);
@@ -790,10 +826,12 @@ int bplx_nuts_step(const bplx_nuts_params* p, void* stream) {
   BPLX_REQUIRE(p && p->C > 0 && p->D > 0 && p->ld >= p->C, BPLX_E_INVALID, "nuts: bad C / D / ld");
   BPLX_REQUIRE(p->max_tree_depth >= 1 && p->max_tree_depth <= 12 && p->thin >= 1, BPLX_E_INVALID,
                "nuts: max_tree_depth must be in [1, 12] and thin >= 1");
+  BPLX_REQUIRE(p->diag_lags >= 0 && (p->diag_lags == 0 || (p->dg_ref && p->dg_sums && p->dg_lag && p->dg_ring && p->dg_head)),
+               BPLX_E_INVALID, "nuts: diag_lags > 0 needs the dg_* accumulators");
   int Y = (p->D + 3) / 4;  // about four parameters per thread, at most kNutsMaxY slices per chain
   Y = Y < 1 ? 1 : (Y > kNutsMaxY ? kNutsMaxY : Y);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const bool generic = getenv("BPLX_NUTS_GENERIC") != nullptr;  // testing: the stage-by-stage kernel for every size
+  const bool generic = env_switches().nuts_generic;  // testing: the stage-by-stage kernel for every size
   cudaLaunchConfig_t cfg{};
   cfg.stream = s;
   cudaLaunchAttribute at[1];

@@ -133,7 +133,15 @@ def prepare(model: str, training_data: Dict[str, Any], epsilon=None, rescale_wei
     if model in ("neutral", "neutral_wc"):
         arr.neutral_venue = np.asarray(training_data["neutral_venue"]).astype(DTYPES["venue"])
         gw = np.asarray(training_data["game_weights"], dtype=np.float32)
-        td = np.asarray(training_data["time_diff"], dtype=np.float32)
+        if model == "neutral":  # neutral_dixon_coles.py:308-318: read with .get(), required only when epsilon is set
+            td = training_data.get("time_diff")
+            if td is None:
+                if epsilon is not None:
+                    raise ValueError("time_diff must be provided in training_data to include exponential time decay in model.")
+                td = np.zeros(M, dtype=np.float32)
+        else:  # neutral_dixon_coles_WC.py:270: read unconditionally
+            td = training_data["time_diff"]
+        td = np.asarray(td, dtype=np.float32)
         if model == "neutral":  # neutral_dixon_coles.py:251-257
             w = np.ones(M, dtype=np.float32)
             if epsilon is not None:

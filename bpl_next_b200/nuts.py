@@ -34,7 +34,9 @@ class NutsParams(C.Structure):
         ("chain", C.c_void_p),
     ] + [(n, C.c_void_p) for n in ("p_half", "inv_mass", "zL", "rL", "gL", "zR", "rR", "gR", "zP", "gP", "r_sum", "zQ",
                                    "gQ", "r_sum_sub", "r_ckpts", "r_sum_ckpts", "wf_mean", "wf_m2", "samples",
-                                   "sample_lp", "sample_accept", "active_count")]
+                                   "sample_lp", "sample_accept", "active_count")] + [
+        ("diag_lags", C.c_int32),
+    ] + [(n, C.c_void_p) for n in ("dg_ref", "dg_sums", "dg_lag", "dg_ring", "dg_head")]
 
 
 def adaptation_schedule(num_steps: int):
@@ -88,13 +90,19 @@ class NutsRun:
     num_leapfrog: np.ndarray     # [C] over warm-up + sampling
     launches: int                # log-density evaluations = kernel launches of the potential
     inv_mass: torch.Tensor       # [D, C]
+    transitions: Optional[np.ndarray] = None  # [C] transitions completed (== num_warmup + num_samples unless cut short)
+    diag: Optional[dict] = None  # streaming accumulators (diagnostics.streaming_summary): ref, sums, lag, ring, head, lags, n
 
 
 def sample(potential: Callable[[torch.Tensor, torch.Tensor, torch.Tensor], None], theta0: torch.Tensor,
            num_warmup: int = 500, num_samples: int = 1000, thin: int = 1, seed: int = 42, max_tree_depth: int = 10,
            target_accept: float = 0.8, step_size: float = 1.0, chain_offset: int = 0, check_every: int = 32,
-           max_launches: Optional[int] = None, use_graph: bool = True) -> NutsRun:
-    """``theta0``: ``[D, C]`` float32 CUDA tensor (chain-minor) of initial unconstrained positions."""
+           max_launches: Optional[int] = None, use_graph: bool = True, diag_lags: int = 0) -> NutsRun:
+    """``theta0``: ``[D, C]`` float32 CUDA tensor (chain-minor) of initial unconstrained positions.
+
+    ``thin`` stores every thin-th post-warm-up draw only; ``diag_lags > 0`` keeps per-chain streaming accumulators of
+    ALL post-warm-up draws (moments of the whole chain and of its halves, lagged products up to ``diag_lags``) inside
+    the step kernel, so split R-hat and ESS need no stored draws (``diagnostics.streaming_summary``)."""
     if not theta0.is_cuda:
         raise RuntimeError("bpl_next_b200.nuts needs CUDA tensors: there is no CPU fallback")
     lib = _declare(_abi.lib())
@@ -103,7 +111,8 @@ def sample(potential: Callable[[torch.Tensor, torch.Tensor, torch.Tensor], None]
     f32 = dict(dtype=torch.float32, device=dev)
     num_keep = (num_samples + thin - 1) // thin
     # state: 18 + 2 * max_tree_depth vectors of [D, C]; output: num_keep of them.  Fail early and say what to change.
-    need = 4 * D * Cn * (18 + 2 * max_tree_depth + num_keep) + 8 * num_keep * Cn
+    diag_lags = max(0, min(int(diag_lags), max(num_samples - 1, 0)))
+    need = 4 * D * Cn * (18 + 2 * max_tree_depth + num_keep + ((7 + 3 * diag_lags) if diag_lags else 0)) + 8 * num_keep * Cn
     free, _total = torch.cuda.mem_get_info(dev)
     if need > 0.95 * free:
         raise MemoryError(
@@ -138,6 +147,14 @@ def sample(potential: Callable[[torch.Tensor, torch.Tensor, torch.Tensor], None]
     p.r_ckpts, p.r_sum_ckpts = r_ckpts.data_ptr(), r_sum_ckpts.data_ptr()
     p.samples, p.sample_lp, p.sample_accept = samples.data_ptr(), sample_lp.data_ptr(), sample_accept.data_ptr()
     p.active_count = active.data_ptr()
+    diag = None
+    p.diag_lags = diag_lags
+    if diag_lags:
+        diag = {"ref": torch.zeros((D, Cn), **f32), "sums": torch.zeros((6, D, Cn), **f32),
+                "lag": torch.zeros((diag_lags, D, Cn), **f32), "ring": torch.zeros((diag_lags, D, Cn), **f32),
+                "head": torch.zeros((diag_lags, D, Cn), **f32), "lags": diag_lags, "n": num_samples}
+        p.dg_ref, p.dg_sums, p.dg_lag = diag["ref"].data_ptr(), diag["sums"].data_ptr(), diag["lag"].data_ptr()
+        p.dg_ring, p.dg_head = diag["ring"].data_ptr(), diag["head"].data_ptr()
 
     limit = max_launches if max_launches is not None else (num_warmup + num_samples + 1) * (2 ** max_tree_depth) + 8
 
@@ -172,4 +189,4 @@ def sample(potential: Callable[[torch.Tensor, torch.Tensor, torch.Tensor], None]
     _abi.check(lib.bplx_nuts_summary(C.byref(p), summ.ctypes.data))
     return NutsRun(samples=samples, lp=sample_lp, accept=sample_accept, step_size=summ[:, 1].copy(),
                    num_divergent=summ[:, 2].astype(np.int64), num_leapfrog=summ[:, 3].astype(np.int64),
-                   launches=launches, inv_mass=vecs["inv_mass"])
+                   launches=launches, inv_mass=vecs["inv_mass"], transitions=summ[:, 0].astype(np.int64), diag=diag)

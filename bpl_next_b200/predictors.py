@@ -102,6 +102,98 @@ class _BplxPredictor:
         s["corr_coef"] = cc.cpu().numpy()
         return arr, s
 
+    def fit_streaming(self, training_data, epsilon=None, rescale_weights: bool = False, random_state: int = 42,
+                      num_warmup: int = 500, num_samples: int = 1000, num_chains: int = 1024, thin: int = 10,
+                      diag_lags: int = 24, max_tree_depth: int = 10, max_launches: Optional[int] = None,
+                      set_posterior: bool = False) -> Dict[str, Any]:
+        """Many-chain ``fit`` that never stores all draws: the chains are partitioned over the ``torch.distributed`` ranks
+        (no collective while sampling); every chain keeps streaming moment / lagged-product accumulators in the step
+        kernel and only every ``thin``-th draw is stored.  At the end the R-hat / ESS moments are all-reduced
+        (``diagnostics.streaming_summary``) and the per-chain sampler summaries all-gathered; with ``set_posterior`` the
+        thinned draws are gathered too and become the fitted attributes (the ``[S, T]`` layout of
+        ``neutral_dixon_coles_WC.py:308-334``), so ``predict_*`` works as after ``fit``.  Returns the run summary."""
+        import time as _time
+
+        from . import diagnostics as dg
+
+        if self.model == "dixon_coles":
+            arr, meta = bdata.prepare(self.model, training_data)
+        else:
+            arr, meta = bdata.prepare(self.model, training_data, epsilon=epsilon, rescale_weights=rescale_weights)
+        self.teams, self._teams_dict, self._meta = meta["teams"], meta["teams_dict"], meta
+        self.problem = p = Problem(arr)
+        rank, nranks = parallel.world()
+        c0, cn = parallel.shard(num_chains, rank, nranks)
+        if cn == 0:
+            raise ValueError(f"num_chains={num_chains} is smaller than the number of ranks ({nranks})")
+        # numpyro init_to_uniform(radius=2), a pure function of (seed, global chain index range)
+        g = torch.Generator(device="cuda").manual_seed(int(random_state) + 7919 * rank)
+        theta0 = (torch.rand((p.D, cn), generator=g, device="cuda") * 4.0 - 2.0).contiguous()
+
+        def potential(theta, lp, grad):
+            p.logdensity(theta, chain_minor=True, lp=lp, grad=grad)
+
+        torch.cuda.synchronize()
+        t0 = _time.perf_counter()
+        run = bnuts.sample(potential, theta0, num_warmup=num_warmup, num_samples=num_samples, thin=thin,
+                           seed=int(random_state), chain_offset=c0, max_tree_depth=max_tree_depth,
+                           max_launches=max_launches, diag_lags=diag_lags)
+        torch.cuda.synchronize()
+        t_sample = _time.perf_counter() - t0
+        self.nuts_run = run
+        complete_local = bool((run.transitions >= num_warmup + num_samples).all())
+        # ---- the exchange: diagnostics moments (all-reduce), per-chain sampler summaries (all-gather) ---------------
+        t0 = _time.perf_counter()
+        summ = dg.streaming_summary(run.diag)
+        per_chain = torch.from_numpy(np.stack([run.step_size, run.num_divergent.astype(np.float32),
+                                               run.num_leapfrog.astype(np.float32),
+                                               run.transitions.astype(np.float32)], axis=1).astype(np.float32)).cuda()
+        if nranks > 1:
+            import torch.distributed as dist
+            parts = [torch.empty((parallel.shard(num_chains, r, nranks)[1], 4), dtype=torch.float32, device="cuda")
+                     for r in range(nranks)]
+            dist.all_gather(parts, per_chain)
+            per_chain = torch.cat(parts, dim=0)
+            launches = torch.tensor([float(run.launches)], device="cuda")
+            dist.all_reduce(launches, op=dist.ReduceOp.MAX)
+            launches = int(launches.item())
+        else:
+            launches = int(run.launches)
+        torch.cuda.synchronize()
+        t_exchange = _time.perf_counter() - t0
+        pc = per_chain.cpu().numpy()
+        complete = bool((pc[:, 3] >= num_warmup + num_samples).all())
+        self.posterior_mean, self.posterior_sd = summ["mean"].cpu().numpy(), summ["sd"].cpu().numpy()
+        self.rhat, self.ess = summ.get("rhat"), summ["ess"]
+        out = {"complete": complete, "chains": int(pc.shape[0]), "draws_per_chain": num_samples, "thin": thin,
+               "stored_draws_per_chain": int(run.samples.shape[0]), "diag_lags": int(summ["lags"]),
+               "ess_min": float(summ["ess"].min().item()) if complete else 0.0,
+               "ess_median": float(summ["ess"].median().item()) if complete else 0.0,
+               "rhat_max": float(summ["rhat"].max().item()) if complete and "rhat" in summ else None,
+               "lag_window_hit": int(summ["lag_window_hit"]),
+               "leapfrogs_total": float(pc[:, 2].sum()), "leapfrogs_max_chain": float(pc[:, 2].max()),
+               "logdensity_launches": launches, "divergences": int(pc[:, 1].sum()),
+               "step_size_median": float(np.median(pc[:, 0])),
+               "match_evals_total": float(pc[:, 2].sum()) * arr.num_matches,
+               "sampling_s": t_sample, "exchange_s": t_exchange,
+               "exchange": "all_reduce of (lags + 8) x D moment sums, all_gather of [chains, 4] sampler summaries"
+                           + (", all_gather of the thinned draws" if set_posterior else "")}
+        if set_posterior:
+            K, D, C = run.samples.shape
+            flat_dev = run.samples.permute(2, 0, 1).reshape(C * K, D).contiguous()
+            if nranks > 1:
+                import torch.distributed as dist
+                sizes = [parallel.shard(num_chains, r, nranks)[1] * K for r in range(nranks)]
+                parts = [torch.empty((n, D), dtype=flat_dev.dtype, device=flat_dev.device) for n in sizes]
+                dist.all_gather(parts, flat_dev)
+                flat_dev = torch.cat(parts, dim=0)
+            _, _, cc = p.logdensity(flat_dev)
+            torch.cuda.synchronize()
+            s = constrain(flat_dev.cpu().numpy(), p.layout)
+            s["corr_coef"] = cc.cpu().numpy()
+            self._set_posterior(arr, s)
+        return out
+
     @staticmethod
     def _prior_means(arr, s):
         S = len(s["mean_defence"])

@@ -141,6 +141,15 @@ def _fixtures_struct(fixtures: dict, ptr):
     return f
 
 
+def score_grid_workspace_bytes(model: str, samples: Dict[str, torch.Tensor], fixtures: Dict[str, torch.Tensor],
+                               max_goals: int) -> int:
+    """Bytes of device workspace ``score_grid`` needs for these shapes (``bplx_score_grid_workspace_bytes``)."""
+    lib = _abi.lib()
+    s = _samples_struct(model, samples, lambda t: int(t.data_ptr()))
+    f = _fixtures_struct(fixtures, lambda t: int(t.data_ptr()))
+    return int(lib.bplx_score_grid_workspace_bytes(C.byref(s), C.byref(f), max_goals))
+
+
 def score_grid(model: str, samples: Dict[str, torch.Tensor], fixtures: Dict[str, torch.Tensor], max_goals: int,
                scale: Optional[float] = None, want_outcome: bool = True, workspace=None, grid=None, outcome=None,
                stream=None):

@@ -185,6 +185,9 @@ int bplx_score_grid_host(const bplx_samples* s, const bplx_fixtures* f, int max_
                          float* grid, float* outcome);
 
 /* ---- misc --------------------------------------------------------------------------------- */
+/* The library reads its testing / tuning switches (BPLX_NO_PDL, BPLX_SPLIT, BPLX_HOST_CHUNKS, BPLX_NUTS_GENERIC,
+ * BPLX_NO_TAIL_SPLIT) from the environment once, at first use -- never on a launch path; call this after changing them. */
+void bplx_reload_env(void);
 const char* bplx_last_error(void);
 int bplx_version(void);
 /* number of kernel launches this library has enqueued from this process (for bench accounting) */

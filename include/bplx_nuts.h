@@ -50,6 +50,17 @@ typedef struct bplx_nuts_params {
   float* sample_lp;              /* [num_keep][ld] */
   float* sample_accept;          /* [num_keep][ld] mean acceptance probability of the draw's tree */
   int32_t* active_count;         /* device scalar */
+  /* streaming diagnostics (optional: diag_lags == 0 turns them off).  Per chain and parameter, over the post-warm-up
+   * draws x_0 .. x_{N-1} shifted by the chain's first draw (v_k = x_k - x_0), updated when a chain collects a draw:
+   *   dg_sums[0..5] = sum v, sum v^2 over the whole chain, over the first N/2 draws, over the last N/2 draws
+   *   dg_lag[l-1]   = sum_k v_k v_{k-l},  l = 1 .. diag_lags
+   *   dg_ring       = the last diag_lags values (slot k mod diag_lags),  dg_head = the first diag_lags values
+   * Split R-hat and the bulk ESS (autocovariances up to lag diag_lags) follow from these and sums over chains
+   * (bpl_next_b200/diagnostics.py: streaming_summary), so no draw has to be stored to diagnose a run. */
+  int32_t diag_lags;
+  float* dg_ref;                 /* [D][ld]              x_0 */
+  float* dg_sums;                /* [6][D][ld]           zero-initialised by the caller */
+  float *dg_lag, *dg_ring, *dg_head; /* [diag_lags][D][ld] each, zero-initialised by the caller */
 } bplx_nuts_params;
 
 size_t bplx_nuts_chain_bytes(void);

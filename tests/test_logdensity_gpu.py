@@ -162,12 +162,12 @@ def test_results_are_bit_reproducible():
 @pytest.mark.parametrize("split", [1, 2, 4, 8])
 @pytest.mark.parametrize("model,kw", [("extended", dict(weighted=True, K=3)), ("neutral_wc", dict(multi_conf=True, K=2, T=13, M=400)),
                                       ("dixon_coles", dict())])
-def test_cluster_split(model, kw, split, monkeypatch):
+def test_cluster_split(model, kw, split, bplx_env):
     """Few-chain mode: 1, 2, 4 or 8 CTAs (one thread-block cluster) share a group of chains; same numbers."""
     import torch
     from bpl_next_b200 import Problem
 
-    monkeypatch.setenv("BPLX_SPLIT", str(split))
+    bplx_env(BPLX_SPLIT=split)
     arr = H.small_problem(model, seed=3, **kw)
     p = Problem(arr)
     for C in (45, 7):

@@ -81,7 +81,7 @@ def test_dixon_coles_posterior_is_stationary_across_seeds():
 
 
 @pytest.mark.parametrize("D,C", [(6, 70), (44, 96), (64, 33)])
-def test_register_resident_step_matches_stage_by_stage_kernel(D, C, monkeypatch):
+def test_register_resident_step_matches_stage_by_stage_kernel(D, C, bplx_env):
     """Small models run the NUTS bookkeeping out of registers (nuts_step_fast_kernel); with the same block geometry it
     does the same arithmetic in the same order as the stage-by-stage kernel, so whole runs must agree bit for bit:
     draws, acceptance statistics, leapfrog counts, adapted step sizes and mass matrices."""
@@ -99,10 +99,7 @@ def test_register_resident_step_matches_stage_by_stage_kernel(D, C, monkeypatch)
     theta0 = torch.rand((D, C), generator=g, device="cuda") * 4 - 2
     runs = []
     for generic in (False, True):
-        if generic:
-            monkeypatch.setenv("BPLX_NUTS_GENERIC", "1")
-        else:
-            monkeypatch.delenv("BPLX_NUTS_GENERIC", raising=False)
+        bplx_env(BPLX_NUTS_GENERIC="1" if generic else None)
         runs.append(bn.sample(potential, theta0.clone(), num_warmup=120, num_samples=40, seed=7, use_graph=False))
     a, b = runs
     assert a.launches == b.launches
@@ -165,7 +162,7 @@ def test_runs_are_reproducible_with_the_dixon_coles_kernel():
     p.close()
 
 
-def test_dependent_launch_does_not_change_results(monkeypatch):
+def test_dependent_launch_does_not_change_results(bplx_env):
     """K1 and the NUTS step start their preambles before the previous kernel of the stream has finished (programmatic
     dependent launch).  Anything read too early would show up as a different run: with and without it, eager and as a
     CUDA graph, the draws must be identical."""
@@ -184,10 +181,7 @@ def test_dependent_launch_does_not_change_results(monkeypatch):
 
     runs = []
     for no_pdl in (False, True):
-        if no_pdl:
-            monkeypatch.setenv("BPLX_NO_PDL", "1")
-        else:
-            monkeypatch.delenv("BPLX_NO_PDL", raising=False)
+        bplx_env(BPLX_NO_PDL="1" if no_pdl else None)
         for graph in (True, False):
             runs.append(bn.sample(potential, theta0.clone(), num_warmup=50, num_samples=15, seed=3, use_graph=graph))
     for r in runs[1:]:

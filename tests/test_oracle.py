@@ -148,3 +148,25 @@ def test_distribution_and_transform_arithmetic_against_scipy():
     np.testing.assert_allclose(lj.detach().numpy(), np.log(sg * (1.0 - sg)), rtol=1e-10)
     (dval,) = torch.autograd.grad(val.sum(), u)
     np.testing.assert_allclose(np.log(dval.numpy()), lj.detach().numpy(), rtol=1e-10)
+
+
+@pytest.mark.parametrize("model,kw", [("dixon_coles", {}), ("extended", dict(K=3)), ("extended", dict(K=0, weighted=False)),
+                                      ("neutral", dict(K=2)), ("neutral_wc", dict(K=0, multi_conf=True)),
+                                      ("neutral_wc", dict(K=3))])
+def test_closed_form_baseline_matches_autograd_oracle(model, kw):
+    """oracle/closed_form.py (the CPU baseline bench.py times: SURVEY Appendix B by hand) against autograd of the
+    line-by-line restatement, float64; radius 2 puts clipped rates into the extended cases."""
+    import torch
+
+    from oracle import closed_form as cf
+
+    for seed in range(3):
+        arr = H.small_problem(model, seed=seed, T=9, M=120, **kw)
+        d = H.to_oracle(arr)
+        D = om.num_params(model, arr.num_teams, arr.num_covariates, arr.num_conferences)
+        th = H.random_theta(D, 5, seed=seed, radius=2.0 if model == "extended" else 1.5)
+        lp, g, cc = om.log_density_and_grad(d, th)
+        lp2, g2, cc2 = cf.log_density_and_grad(d, th, dtype=torch.float64)
+        np.testing.assert_allclose(lp2, lp, rtol=1e-12)
+        np.testing.assert_allclose(cc2, cc, rtol=0, atol=1e-14)
+        assert np.abs(g - g2).max() <= 1e-11 * np.abs(g).max()

@@ -63,6 +63,22 @@ def _worker(rank, nranks, port, q):
                                                           (mine.mean(1) ** 2).sum(0), cn)
         ok_mom = n == C and np.allclose(sx.numpy(), draws.sum((0, 1))) and np.allclose(sx2.numpy(), (draws ** 2).sum((0, 1))) \
             and np.allclose(sm2.numpy(), (draws.mean(1) ** 2).sum(0))
+        # the overlapped variant (fixture ranges exchanged on a side stream on the GPU; sequential on CPU): same grid
+        sg = parallel.ShardedScoreGrid("extended", local, fx, 10, S, chunks=3, local_fn=_cpu_grid)
+        grid2, out2 = sg.run()
+        ok_grid = ok_grid and len(sg.ranges) == 3 and bool(np.allclose(grid2.numpy(), ref, atol=1e-6)) \
+            and bool(np.allclose(out2.numpy(), out.numpy(), atol=1e-6))
+        # streaming diagnostics: per-rank accumulators, sums over chains all-reduced = the single-process diagnostics
+        from bpl_next_b200 import diagnostics as dg
+        g = torch.Generator().manual_seed(3)
+        x = torch.cumsum(torch.randn((120, 3, 10), generator=g), 0) * 0.1 + torch.randn((120, 3, 10), generator=g)
+        c0, cn = parallel.shard(10, rank, nranks)
+        s_loc = dg.streaming_summary(dg.accumulate_reference(x[..., c0:c0 + cn].contiguous(), 30))
+        solo = [dist.new_group([r]) for r in range(nranks)][rank]  # (every rank creates every group, in the same order)
+        s_all = dg.streaming_summary(dg.accumulate_reference(x, 30), group=solo)
+        ok_mom = ok_mom and s_loc["num_chains"] == 10 and np.allclose(s_loc["ess"].numpy(), s_all["ess"].numpy(), rtol=1e-9) \
+            and np.allclose(s_loc["rhat"].numpy(), s_all["rhat"].numpy(), rtol=1e-12) \
+            and np.allclose(s_loc["mean"].numpy(), s_all["mean"].numpy(), rtol=1e-12)
         q.put((rank, ok_grid, bool(ok_mom), float(out.sum(1).mean())))
     finally:
         dist.destroy_process_group()
