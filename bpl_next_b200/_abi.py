@@ -80,6 +80,12 @@ def declare(lib):
     lib.bplx_logdensity_workspace_bytes.restype = sz
     lib.bplx_logdensity_fwdbwd.argtypes = [vp, i, i, i, vp, vp, vp, vp, vp, sz, vp]
     lib.bplx_logdensity_fwdbwd.restype = i
+    lib.bplx_loglik_num_inputs.argtypes = [vp]
+    lib.bplx_loglik_num_inputs.restype = i
+    lib.bplx_loglik_layout.argtypes = [vp]
+    lib.bplx_loglik_layout.restype = C.c_char_p
+    lib.bplx_loglik_fwdbwd.argtypes = [vp, i, i, i, vp, vp, vp, vp, vp, sz, vp]
+    lib.bplx_loglik_fwdbwd.restype = i
     lib.bplx_logdensity_fwdbwd_host.argtypes = [vp, i, vp, vp, vp, vp]
     lib.bplx_logdensity_fwdbwd_host.restype = i
     lib.bplx_score_grid_workspace_bytes.argtypes = [C.POINTER(Samples), C.POINTER(Fixtures), i]

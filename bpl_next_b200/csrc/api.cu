@@ -77,11 +77,21 @@ static size_t workspace_bytes(const KernelParams& kp, int C) {
 }
 
 static int enqueue(const bplx_problem* p, int C, int layout, int ld, const float* theta, float* lp, float* grad,
-                   float* corr_coef, void* ws, size_t ws_bytes, cudaStream_t stream, bool pdl = false) {
+                   float* corr_coef, void* ws, size_t ws_bytes, cudaStream_t stream, bool pdl = false, bool lik = false) {
   BPLX_REQUIRE(p != nullptr, BPLX_E_INVALID, "problem is NULL");
   BPLX_REQUIRE(C > 0, BPLX_E_INVALID, "num_chains must be positive (got %d)", C);
   BPLX_REQUIRE(theta && lp && grad, BPLX_E_INVALID, "theta, lp and grad must not be NULL");
   KernelParams kp = p->kp;
+  if (lik) {  // the same plan read through the likelihood-only site layout: constrained tables in, no priors
+    BPLX_REQUIRE(kp.model != BPLX_DYNAMIC, BPLX_E_UNSUPPORTED, "bplx_loglik_fwdbwd: DYNAMIC is not supported");
+    kp.lik_only = 1;
+    kp.off = p->lik_off;
+    for (int i = 0; i < 12; i++) kp.hyper[i] = p->lik_hyper[i];
+    kp.nhyper = p->lik_nhyper;
+    kp.D = p->lik_D;
+    kp.K = 0;
+    kp.const_term = p->lik_const;
+  }
   if (layout == BPLX_CHAIN_MAJOR) {
     kp.sd = 1;
     kp.sc = ld > 0 ? ld : kp.D;
@@ -153,6 +163,12 @@ int bplx_problem_create(const bplx_problem_desc* desc, bplx_problem** out) {
   }
   p->kp = hp.kp;
   p->layout = hp.layout;
+  p->lik_off = hp.lik_off;
+  for (int i = 0; i < 12; i++) p->lik_hyper[i] = hp.lik_hyper[i];
+  p->lik_nhyper = hp.lik_nhyper;
+  p->lik_D = hp.lik_D;
+  p->lik_const = hp.lik_const;
+  p->lik_layout = hp.lik_layout;
   KernelParams& kp = p->kp;
 #define UP(vec, ptr)                                 \
   if ((rc = upload(p, hp.vec, &(ptr))) != BPLX_OK) return fail(rc)
@@ -242,6 +258,19 @@ int bplx_logdensity_fwdbwd(const bplx_problem* p, int num_chains, int layout, in
                            float* grad, float* corr_coef, void* workspace, size_t workspace_bytes, void* stream) {
   return enqueue(p, num_chains, layout, ld, theta, lp, grad, corr_coef, workspace, workspace_bytes,
                  static_cast<cudaStream_t>(stream), /*pdl=*/true);
+}
+
+int bplx_loglik_num_inputs(const bplx_problem* p) {
+  if (!p) return BPLX_E_INVALID;
+  return p->kp.model == BPLX_DYNAMIC ? BPLX_E_UNSUPPORTED : p->lik_D;
+}
+
+const char* bplx_loglik_layout(const bplx_problem* p) { return p ? p->lik_layout.c_str() : ""; }
+
+int bplx_loglik_fwdbwd(const bplx_problem* p, int num_chains, int layout, int ld, const float* tables, float* loglik,
+                       float* grad, float* corr_coef, void* workspace, size_t workspace_bytes, void* stream) {
+  return enqueue(p, num_chains, layout, ld, tables, loglik, grad, corr_coef, workspace, workspace_bytes,
+                 static_cast<cudaStream_t>(stream), /*pdl=*/true, /*lik=*/true);
 }
 
 int bplx_logdensity_fwdbwd_host(bplx_problem* p, int C, const float* theta, float* lp, float* grad, float* corr_coef) {
@@ -337,9 +366,20 @@ static int check_grid_args(const bplx_samples* s, const bplx_fixtures* f, int ma
   return BPLX_OK;
 }
 
+static size_t grid_plan(const bplx_samples* s, const bplx_fixtures* f, int max_goals, GridParams* gp, const char** err) {
+  gp->model = s->model;
+  gp->S = s->num_samples;
+  gp->T = s->num_teams;
+  gp->Cf = s->model == BPLX_NEUTRAL_WC ? s->num_conferences : 0;
+  gp->F = f->num_fixtures;
+  gp->g = max_goals + 1;
+  return score_grid_plan(gp, err);
+}
+
 size_t bplx_score_grid_workspace_bytes(const bplx_samples* s, const bplx_fixtures* f, int max_goals) {
-  if (!s || !f || max_goals < 1) return 0;
-  return score_grid_workspace(s->num_samples, f->num_fixtures, max_goals + 1, nullptr, nullptr);
+  if (!s || !f || max_goals < 1 || s->num_samples <= 0 || s->num_teams <= 0 || f->num_fixtures <= 0) return 0;
+  GridParams gp{};
+  return grid_plan(s, f, max_goals, &gp, nullptr);
 }
 
 int bplx_score_grid(const bplx_samples* s, const bplx_fixtures* f, int max_goals, float scale, float* grid,
@@ -348,16 +388,13 @@ int bplx_score_grid(const bplx_samples* s, const bplx_fixtures* f, int max_goals
   if (rc != BPLX_OK) return rc;
   BPLX_REQUIRE(grid != nullptr, BPLX_E_INVALID, "grid is NULL");
   GridParams gp{};
-  gp.model = s->model;
-  gp.S = s->num_samples;
-  gp.T = s->num_teams;
-  gp.Cf = s->model == BPLX_NEUTRAL_WC ? s->num_conferences : 0;
-  gp.F = f->num_fixtures;
-  gp.g = max_goals + 1;
+  const char* perr = nullptr;
+  const size_t need = grid_plan(s, f, max_goals, &gp, &perr);
+  BPLX_REQUIRE(need > 0, BPLX_E_UNSUPPORTED, "%s", perr ? perr : "score grid: unsupported shape");
   gp.scale = scale;
-  const size_t need = score_grid_workspace(gp.S, gp.F, gp.g, &gp.nsplit, &gp.samples_per_split);
   BPLX_REQUIRE(workspace && workspace_bytes >= need, BPLX_E_WORKSPACE,
                "workspace too small: %zu bytes given, %zu needed", workspace_bytes, need);
+  BPLX_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15u) == 0, BPLX_E_INVALID, "workspace must be 16-byte aligned");
   gp.attack = s->attack;
   gp.defence = s->defence;
   gp.ha = s->home_attack;
@@ -371,7 +408,9 @@ int bplx_score_grid(const bplx_samples* s, const bplx_fixtures* f, int max_goals
   gp.hconf = f->home_conf;
   gp.aconf = f->away_conf;
   gp.nv = f->neutral_venue;
-  gp.partial = static_cast<float*>(workspace);
+  gp.table = static_cast<float*>(workspace);
+  gp.partial = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) +
+                                        ((size_t)gp.S * gp.row_floats * 4 + 255) / 256 * 256);
   gp.grid = grid;
   gp.outcome = outcome;
   return launch_score_grid(gp, static_cast<cudaStream_t>(stream));
@@ -432,7 +471,7 @@ int bplx_score_grid_host(const bplx_samples* s, const bplx_fixtures* f, int max_
   df.home_conf = Cf ? (const uint8_t*)up(f->home_conf, F) : nullptr;
   df.away_conf = Cf ? (const uint8_t*)up(f->away_conf, F) : nullptr;
   df.neutral_venue = (neu && f->neutral_venue) ? (const uint8_t*)up(f->neutral_venue, F) : nullptr;
-  const size_t ws_bytes = score_grid_workspace((int)S, (int)F, (int)g, nullptr, nullptr);
+  const size_t ws_bytes = bplx_score_grid_workspace_bytes(s, f, max_goals);
   void *d_ws = nullptr, *d_grid = nullptr, *d_out = nullptr;
   if (rc == BPLX_OK) {
     if (cudaMalloc(&d_ws, ws_bytes) == cudaSuccess) allocs.push_back(d_ws); else rc = BPLX_E_NOMEM;

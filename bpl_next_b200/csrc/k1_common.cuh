@@ -51,6 +51,15 @@ __device__ __forceinline__ float ld_cg(const float* p) { return __ldcg(p); }  //
 __device__ __forceinline__ Hyp load_hyp_raw(const KernelParams& kp, const Lane& ln) {
   const ThetaOffsets& o = kp.off;
   Hyp hy;
+  if (kp.lik_only) {  // constrained tables come in: identity location / scale (log std = 0)
+    hy.mu_d = hy.sig_a = hy.sig_d = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      hy.mu[i] = o.mean[i] >= 0 ? ln.ld(o.mean[i]) : 0.0f;
+      hy.sig[i] = 0.0f;
+    }
+    return hy;
+  }
   hy.mu_d = ln.ld(o.mean_defence);
   hy.sig_a = ln.ld(o.log_std_attack);
   hy.sig_d = ln.ld(o.log_std_defence);
@@ -66,7 +75,7 @@ __device__ __forceinline__ Hyp finish_hyp(const KernelParams& kp, Hyp hy) {
   hy.sig_a = expf(hy.sig_a);
   hy.sig_d = expf(hy.sig_d);
 #pragma unroll
-  for (int i = 0; i < 4; i++) hy.sig[i] = o.log_std[i] >= 0 ? expf(hy.sig[i]) : 0.0f;
+  for (int i = 0; i < 4; i++) hy.sig[i] = (o.log_std[i] >= 0 || (kp.lik_only && i < kp.ndec)) ? expf(hy.sig[i]) : 0.0f;
   return hy;
 }
 __device__ __forceinline__ Hyp load_hyp(const KernelParams& kp, const Lane& ln) { return finish_hyp(kp, load_hyp_raw(kp, ln)); }
@@ -189,6 +198,104 @@ struct Ring {
     issue(k + kStages);
   }
 };
+
+// Walks the 16-byte items of a list piece: four per trip, then at most one block of two and one single -- every block
+// straight-line code.  (The compiler's own remainder of an unrolled loop is a rolled loop that costs three times as
+// many instructions per item, and with lists of 20-90 entries a quarter of phase 1 ran in it.)
+template <typename F>
+__device__ __forceinline__ void walk16(uint32_t& a, const uint32_t e_end, F&& item) {
+  while (a + 64 <= e_end) {
+    item(a);
+    item(a + 16);
+    item(a + 32);
+    item(a + 48);
+    a += 64;
+  }
+  if (a + 32 <= e_end) {
+    item(a);
+    item(a + 16);
+    a += 32;
+  }
+  if (a < e_end) {
+    item(a);
+    a += 16;
+  }
+}
+
+// The tau terms of one phase-2 piece (bpl/_util.py:54-91): entries with tau = 1 - c X Y, then 1 + c X, then 1 + c Y.
+//   *lt  sum w log2 tau;  *du  d/d corr_coef;  *gx, *gy  d/d (log X, log Y) of the list's own team
+// kTauPlain: model without rate clipping.  kTauClipped: rates clipped at 15 (DIXON_COLES, EXTENDED).  kTauUnclipped:
+// same model, but the chain maxima say no rate of these 32 chains is at the clip -- the clipped arithmetic with
+// min(x, 15) = x and every guard true, bit for bit, minus the instructions.
+enum { kTauPlain = 0, kTauUnclipped = 1, kTauClipped = 2 };
+template <int MODE>
+__device__ __forceinline__ void tau_piece(uint32_t& a, const Hdr& L, const float2 own, const bool home, const float cc,
+                                          const uint32_t tab, float& lt_out, float& du_out, float& gx_out, float& gy_out) {
+  // every 16 bytes hold two entries (opponent row offset, w): their arithmetic runs as packed pairs (.x = first entry)
+  const float2 one = make_float2(1.0f, 1.0f);
+  float2 lt = make_float2(0.0f, 0.0f), uxy = lt, sxy_x = lt, sxy_y = lt;
+  {
+    const uint32_t e_end = a + L.n0 * (uint32_t)sizeof(Entry);
+#pragma unroll 2
+    for (; a < e_end; a += 16) {
+      const uint4 q = lds128u(a);
+      const float2 ea = lds64(tab + q.x), eb = lds64(tab + q.z);
+      const float2 w = make_float2(__uint_as_float(q.y), __uint_as_float(q.w));
+      // the two rates first, then their product, as the reference groups it: (own.x own.y) (ea.x ea.y) overflows far
+      // from the typical set where the rates themselves do not
+      const float2 ra = mul2(own, ea), rb = mul2(own, eb);
+      float2 t;
+      if (MODE == kTauClipped) t = make_float2(fminf(ra.x, 15.0f) * fminf(ra.y, 15.0f), fminf(rb.x, 15.0f) * fminf(rb.y, 15.0f));
+      else t = make_float2(ra.x * ra.y, rb.x * rb.y);
+      float2 tau = fma2(bc2(-cc), t, one);
+      tau.x = fmaxf(tau.x, 0.0f);
+      tau.y = fmaxf(tau.y, 0.0f);
+      // sums of (w t) / tau as explicit fused multiply-adds, packed or scalar: the same rounding in every form (left
+      // as mul + add, ptxas contracts the packed pair into an FFMA2 in one form and not in another)
+      const float2 wt = mul2(w, t), rc = make_float2(rcp_approx(tau.x), rcp_approx(tau.y));
+      uxy = fma2(wt, rc, uxy);
+      if (MODE == kTauClipped) {
+        if (ra.x < 15.0f) sxy_x.x = fmaf(wt.x, rc.x, sxy_x.x);
+        if (rb.x < 15.0f) sxy_x.y = fmaf(wt.y, rc.y, sxy_x.y);
+        if (ra.y < 15.0f) sxy_y.x = fmaf(wt.x, rc.x, sxy_y.x);
+        if (rb.y < 15.0f) sxy_y.y = fmaf(wt.y, rc.y, sxy_y.y);
+      }
+      if (home) lt = fma2(w, make_float2(lg2_approx(tau.x), lg2_approx(tau.y)), lt);
+    }
+  }
+  float u1[2] = {0.0f, 0.0f}, s1[2] = {0.0f, 0.0f};
+#pragma unroll
+  for (int c = 0; c < 2; c++) {
+    const float oc = c == 0 ? own.x : own.y;
+    const uint32_t e_end = a + (c == 0 ? L.n1 : L.n2) * (uint32_t)sizeof(Entry);
+    float2 u = make_float2(0.0f, 0.0f), sm = u;
+#pragma unroll 2
+    for (; a < e_end; a += 16) {
+      const uint4 q = lds128u(a);
+      const float2 Rr = mul2(bc2(oc), make_float2(lds32(tab + q.x), lds32(tab + q.z)));  // `off` already selects .x or .y
+      const float2 w = make_float2(__uint_as_float(q.y), __uint_as_float(q.w));
+      const float2 R = MODE == kTauClipped ? make_float2(fminf(Rr.x, 15.0f), fminf(Rr.y, 15.0f)) : Rr;
+      float2 tau = fma2(bc2(cc), R, one);
+      tau.x = fmaxf(tau.x, 0.0f);
+      tau.y = fmaxf(tau.y, 0.0f);
+      const float2 wr = mul2(w, R), rc = make_float2(rcp_approx(tau.x), rcp_approx(tau.y));
+      u = fma2(wr, rc, u);
+      if (MODE == kTauClipped) {
+        if (Rr.x < 15.0f) sm.x = fmaf(wr.x, rc.x, sm.x);
+        if (Rr.y < 15.0f) sm.y = fmaf(wr.y, rc.y, sm.y);
+      }
+      if (home) lt = fma2(w, make_float2(lg2_approx(tau.x), lg2_approx(tau.y)), lt);
+    }
+    u1[c] = u.x + u.y;
+    s1[c] = MODE == kTauClipped ? sm.x + sm.y : u1[c];
+  }
+  const float uxy_s = uxy.x + uxy.y;
+  const float sx = MODE == kTauClipped ? sxy_x.x + sxy_x.y : uxy_s, sy = MODE == kTauClipped ? sxy_y.x + sxy_y.y : uxy_s;
+  lt_out = lt.x + lt.y;
+  du_out = u1[0] + u1[1] - uxy_s;
+  gx_out = cc * (s1[0] - sx);
+  gy_out = cc * (s1[1] - sy);
+}
 
 // the two arg-max matches of a chain, as every warp needs them in the team pass
 struct Fixup {

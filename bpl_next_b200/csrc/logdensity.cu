@@ -61,29 +61,6 @@ __device__ unsigned long long g_timeline[32 * 24];
 
 namespace bplx {
 
-// Walks the 16-byte items of a list piece: four per trip, then at most one block of two and one single -- every block
-// straight-line code.  (The compiler's own remainder of an unrolled loop is a rolled loop that costs three times as
-// many instructions per item, and with lists of 20-90 entries a quarter of phase 1 ran in it.)
-template <typename F>
-__device__ __forceinline__ void walk16(uint32_t& a, const uint32_t e_end, F&& item) {
-  while (a + 64 <= e_end) {
-    item(a);
-    item(a + 16);
-    item(a + 32);
-    item(a + 48);
-    a += 64;
-  }
-  if (a + 32 <= e_end) {
-    item(a);
-    item(a + 16);
-    a += 32;
-  }
-  if (a < e_end) {
-    item(a);
-    a += 16;
-  }
-}
-
 // One phase-1 piece of a model that clips its rates at 15 (DIXON_COLES, EXTENDED; bpl/dixon_coles.py:66-75): entries
 // (opponent row, w, w y_x, w y_y).  *lp  sum w (y log rate - rate) of a home list;  m1..m3  maxima of the two rates and
 // their product;  *gx, *gy  d/d (log X, log Y) of the list's own team.
@@ -127,81 +104,6 @@ __device__ __forceinline__ uint32_t float_key(float f) {
 }
 __device__ __forceinline__ float key_float(uint32_t k) {
   return __uint_as_float(k ^ ((k & 0x80000000u) ? 0x80000000u : 0xffffffffu));
-}
-
-// The tau terms of one phase-2 piece (bpl/_util.py:54-91): entries with tau = 1 - c X Y, then 1 + c X, then 1 + c Y.
-//   *lt  sum w log2 tau;  *du  d/d corr_coef;  *gx, *gy  d/d (log X, log Y) of the list's own team
-// kTauPlain: model without rate clipping.  kTauClipped: rates clipped at 15 (DIXON_COLES, EXTENDED).  kTauUnclipped:
-// same model, but the chain maxima say no rate of these 32 chains is at the clip -- the clipped arithmetic with
-// min(x, 15) = x and every guard true, bit for bit, minus the instructions.
-enum { kTauPlain = 0, kTauUnclipped = 1, kTauClipped = 2 };
-template <int MODE>
-__device__ __forceinline__ void tau_piece(uint32_t& a, const Hdr& L, const float2 own, const bool home, const float cc,
-                                          const uint32_t tab, float& lt_out, float& du_out, float& gx_out, float& gy_out) {
-  // every 16 bytes hold two entries (opponent row offset, w): their arithmetic runs as packed pairs (.x = first entry)
-  const float2 one = make_float2(1.0f, 1.0f);
-  float2 lt = make_float2(0.0f, 0.0f), uxy = lt, sxy_x = lt, sxy_y = lt;
-  {
-    const uint32_t e_end = a + L.n0 * (uint32_t)sizeof(Entry);
-#pragma unroll 2
-    for (; a < e_end; a += 16) {
-      const uint4 q = lds128u(a);
-      const float2 ea = lds64(tab + q.x), eb = lds64(tab + q.z);
-      const float2 w = make_float2(__uint_as_float(q.y), __uint_as_float(q.w));
-      // the two rates first, then their product, as the reference groups it: (own.x own.y) (ea.x ea.y) overflows far
-      // from the typical set where the rates themselves do not
-      const float2 ra = mul2(own, ea), rb = mul2(own, eb);
-      float2 t;
-      if (MODE == kTauClipped) t = make_float2(fminf(ra.x, 15.0f) * fminf(ra.y, 15.0f), fminf(rb.x, 15.0f) * fminf(rb.y, 15.0f));
-      else t = make_float2(ra.x * ra.y, rb.x * rb.y);
-      float2 tau = fma2(bc2(-cc), t, one);
-      tau.x = fmaxf(tau.x, 0.0f);
-      tau.y = fmaxf(tau.y, 0.0f);
-      // sums of (w t) / tau as explicit fused multiply-adds, packed or scalar: the same rounding in every form (left
-      // as mul + add, ptxas contracts the packed pair into an FFMA2 in one form and not in another)
-      const float2 wt = mul2(w, t), rc = make_float2(rcp_approx(tau.x), rcp_approx(tau.y));
-      uxy = fma2(wt, rc, uxy);
-      if (MODE == kTauClipped) {
-        if (ra.x < 15.0f) sxy_x.x = fmaf(wt.x, rc.x, sxy_x.x);
-        if (rb.x < 15.0f) sxy_x.y = fmaf(wt.y, rc.y, sxy_x.y);
-        if (ra.y < 15.0f) sxy_y.x = fmaf(wt.x, rc.x, sxy_y.x);
-        if (rb.y < 15.0f) sxy_y.y = fmaf(wt.y, rc.y, sxy_y.y);
-      }
-      if (home) lt = fma2(w, make_float2(lg2_approx(tau.x), lg2_approx(tau.y)), lt);
-    }
-  }
-  float u1[2] = {0.0f, 0.0f}, s1[2] = {0.0f, 0.0f};
-#pragma unroll
-  for (int c = 0; c < 2; c++) {
-    const float oc = c == 0 ? own.x : own.y;
-    const uint32_t e_end = a + (c == 0 ? L.n1 : L.n2) * (uint32_t)sizeof(Entry);
-    float2 u = make_float2(0.0f, 0.0f), sm = u;
-#pragma unroll 2
-    for (; a < e_end; a += 16) {
-      const uint4 q = lds128u(a);
-      const float2 Rr = mul2(bc2(oc), make_float2(lds32(tab + q.x), lds32(tab + q.z)));  // `off` already selects .x or .y
-      const float2 w = make_float2(__uint_as_float(q.y), __uint_as_float(q.w));
-      const float2 R = MODE == kTauClipped ? make_float2(fminf(Rr.x, 15.0f), fminf(Rr.y, 15.0f)) : Rr;
-      float2 tau = fma2(bc2(cc), R, one);
-      tau.x = fmaxf(tau.x, 0.0f);
-      tau.y = fmaxf(tau.y, 0.0f);
-      const float2 wr = mul2(w, R), rc = make_float2(rcp_approx(tau.x), rcp_approx(tau.y));
-      u = fma2(wr, rc, u);
-      if (MODE == kTauClipped) {
-        if (Rr.x < 15.0f) sm.x = fmaf(wr.x, rc.x, sm.x);
-        if (Rr.y < 15.0f) sm.y = fmaf(wr.y, rc.y, sm.y);
-      }
-      if (home) lt = fma2(w, make_float2(lg2_approx(tau.x), lg2_approx(tau.y)), lt);
-    }
-    u1[c] = u.x + u.y;
-    s1[c] = MODE == kTauClipped ? sm.x + sm.y : u1[c];
-  }
-  const float uxy_s = uxy.x + uxy.y;
-  const float sx = MODE == kTauClipped ? sxy_x.x + sxy_x.y : uxy_s, sy = MODE == kTauClipped ? sxy_y.x + sxy_y.y : uxy_s;
-  lt_out = lt.x + lt.y;
-  du_out = u1[0] + u1[1] - uxy_s;
-  gx_out = cc * (s1[0] - sx);
-  gy_out = cc * (s1[1] - sy);
 }
 
 template <bool CLIP>
@@ -257,7 +159,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
   const int ndec = kp.ndec;
   const bool dc = ndec == 0;
   const float raw_in = ln.ld(o.raw);  // (its sigmoid -- a division, hence branches -- waits until the prologue's end)
-  const float u_in = (warp == 0 && !dc) ? ln.ld(o.u) : 0.0f;
+  const bool lik = kp.lik_only != 0;
+  const float u_in = (warp == 0 && !dc && !lik) ? ln.ld(o.u) : 0.0f;
   struct TeamIn { float za, zd, dz[4], xs[4]; int fl, v0, v1; };
   auto load_team = [&](int t) {
     TeamIn in;
@@ -388,13 +291,13 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
         }
       }
     }
-    if (warp == 0) red_hyp[11 * 32 + lane] = dc ? 0.5f : sigmoid_clipped(u_in);
+    if (warp == 0) red_hyp[11 * 32 + lane] = (dc || lik) ? 0.5f : sigmoid_clipped(u_in);
     if (CLIP && warp < kp.T) {
       atomicMax(red_clip + lane, float_key(exA));
       atomicMax(red_clip + 32 + lane, float_key(exB));
     }
   }
-  const float r = sigmoid_clipped(raw_in);
+  const float r = lik ? raw_in : sigmoid_clipped(raw_in);  // (likelihood-only: corr_coef_raw itself comes in)
   BPLX_STAMP(1);
   sync_all();
 
@@ -678,7 +581,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
 
   BPLX_STAMP(8);
   // ---- team pass: raw slots -> parameter gradients, priors, hyper-parameter sums ---------------------------
-  const bool has_rho = !dc;
+  const bool has_rho = !dc && !lik;
+  const float pri = lik ? 0.0f : 1.0f;  // likelihood-only: no prior terms
   float u = 0.5f, rho = 0.0f, inv_s2 = 1.0f;
   if (has_rho) {
     u = red_hyp[11 * 32 + lane];
@@ -736,9 +640,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
         p_zd = -es;
         a_rho += es * za - rho * es * es + rho * inv_s2;
       } else {
-        lp_acc -= 0.5f * (za * za + zd * zd);
-        p_za = -za;
-        p_zd = -zd;
+        lp_acc -= pri * 0.5f * (za * za + zd * zd);
+        p_za = -pri * za;
+        p_zd = -pri * zd;
       }
       if (ln.active) {
         *ln.g(o.za + t) = fmaf(hy.sig_a, ra, p_za);
@@ -751,8 +655,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
 #pragma unroll
       for (int i = 0; i < 4; i++) {
         if (i < ndec) {
-          lp_acc -= 0.5f * dec[i] * dec[i];
-          if (ln.active) *ln.g(o.dec[i] + t) = fmaf(hy.sig[i], rx[i], -dec[i]);
+          lp_acc -= pri * 0.5f * dec[i] * dec[i];
+          if (ln.active) *ln.g(o.dec[i] + t) = fmaf(hy.sig[i], rx[i], -pri * dec[i]);
           a_mu[i] += rx[i];
           a_ls[i] = fmaf(hy.sig[i] * dec[i], rx[i], a_ls[i]);
         }
@@ -767,8 +671,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
   // confederation strengths: N(0,1) prior + sum over the virtual teams of the confederation
   for (int k = vwarp; k < kp.Cf; k += VW) {
     const float cf = ln.ld(o.conf + k);
-    float s = __ldg(kp.yconf + k) - cf;
-    lp_acc -= 0.5f * cf * cf;
+    float s = __ldg(kp.yconf + k) - pri * cf;
+    lp_acc -= pri * 0.5f * cf * cf;
     const int j0 = __ldg(kp.conf_vptr + k), j1 = __ldg(kp.conf_vptr + k + 1);
     for (int j = j0; j < j1; j++) s += ld_cg(ln.sc + (size_t)__ldg(kp.conf_vlist + j) * kp.Cpad);
 #pragma unroll
@@ -821,6 +725,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
         const float z = (x - hd.loc) * hd.inv_scale;
         lp -= 0.5f * z * z;
         gval = fmaf(-z, hd.inv_scale, acc);
+      } else if (hd.kind == 2) {  // likelihood-only: no prior
+        gval = acc;
       } else {  // HalfNormal(scale) on exp(x) + Jacobian x
         const float z = expf(x) * hd.inv_scale;
         lp += fmaf(-0.5f * z, z, x);
@@ -834,9 +740,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
       }
     } else if (item == kp.nhyper + 1) {
       // corr_coef_raw ~ Beta(2,2) + Jacobian; corr_coef = LB + r (UB - LB); also the likelihood + team-prior sum
-      lp += total(0) + 2.0f * (logf(r) + logf(1.0f - r));
+      lp += total(0) + (lik ? 0.0f : 2.0f * (logf(r) + logf(1.0f - r)));
       if (ln.active) {
-        *ln.g(o.raw) = 2.0f * (1.0f - 2.0f * r) + gc * r * (1.0f - r) * (UB - LB);
+        *ln.g(o.raw) = lik ? gc * (UB - LB) : 2.0f * (1.0f - 2.0f * r) + gc * r * (1.0f - r) * (UB - LB);
         if (kp.corr_coef) kp.corr_coef[chain] = cc;
       }
     } else {  // covariate coefficients: d/d beta[k] = sum_t Xs[t,k] * d/d (att | def)[t]; N(0,1) prior

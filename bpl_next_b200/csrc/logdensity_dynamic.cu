@@ -4,21 +4,70 @@
 // (bpl/dynamic_dixon_coles.py:63-247) with bpl/_util.py:17-93, for a batch of chains; lane = chain.
 // Team strengths follow a random walk over gameweeks, attack[j] = attack[j-1] + z[j] * std_attack[j]
 // (":192-218"; BPLX_FLAG_DYNAMIC_AS_WRITTEN reproduces the reference literally, where the walk never reaches
-// the rates), and a match only pairs teams of its own gameweek.  So:
-//   prefix pass   (team-owned)      the walk's prefix sums of every (gameweek, team) -> workspace
-//   phase 1 / 2   (gameweek-owned)  a warp owns whole gameweeks; at a gameweek's marker piece it rebuilds the
-//                                   tables of that gameweek in its private slice of shared memory, then walks the
-//                                   gameweek's list pieces exactly like K1 (logdensity.cu).  The arg-max search
-//                                   runs in phase 2 while the arg-max piece's gameweek is resident.
-//   suffix pass   (team-owned)      d/d attack[j] summed over the later gameweeks (the walk's transpose)
-//   gameweek pass (gameweek-owned)  priors, chain rule and the ten per-gameweek hyper-parameter gradients,
-//                                   which need no cross-warp reduction because one warp sees the whole gameweek.
+// the rates), and a match only pairs teams of its own gameweek.  D = 10 G + 2 + 2 K + 7 G T parameters per chain do not
+// fit on chip, so theta is streamed: the CTA walks the gameweeks in step with ONE set of tables for the current
+// gameweek (double-buffered), a warp owns teams (t -> warp t mod W), and every (gameweek, team) is completed in a single
+// visit, so each gradient entry is written once and never re-read (plan_dynamic.inc has the stream layout):
+//
+//   forward pass   gameweeks ascending: the walk's prefix sums (kept per team, also written to the workspace), the
+//                  gameweek's tables, and the HOME lists for the maxima of the corr_coef bounds (bpl/_util.py:17-31)
+//   bounds         maxima over warps -> LB, UB, corr_coef
+//   backward pass  gameweeks descending: tables again (from the stored prefix sums), then per team its rate lists
+//                  (Poisson part), tau lists (bpl/_util.py:54-91), the running suffix sums (the walk's transpose),
+//                  priors, chain rule and the final gradient of its seven sites; the ten per-gameweek hyper sums go
+//                  through shared memory to one warp per gameweek.  The entry that attained each maximum is found
+//                  while its gameweek is resident.
+//   fix-up         d corr_coef / d eta of the two arg-max matches needs d/d corr_coef of ALL tau
+//                  terms, known only now: it is linear, so it is applied as a correction to the few entries it reaches.
 #include <math.h>
 
 #include "k1_common.cuh"
 #include "problem.h"
 
 namespace bplx {
+
+namespace {
+
+// the pieces of a warp's stream, across stage boundaries (pieces never straddle a stage)
+struct PieceReader {
+  Ring* ring;
+  uint32_t k, a, a0, aend, base;
+  __device__ __forceinline__ void start(Ring* r, uint32_t base_) {
+    ring = r;
+    base = base_;
+    k = 0;
+    uint32_t bytes;
+    a0 = ring->acquire(0, &bytes);
+    a = a0;
+    aend = a0 + bytes;
+  }
+  // next real header (fillers skipped); *hoff = its byte offset in the global stream; entries follow at `a`
+  __device__ __forceinline__ Hdr next(uint32_t* hoff) {
+    for (;;) {
+      if (a + 16 > aend) {
+        ring->release(k);
+        k++;
+        uint32_t bytes;
+        a0 = ring->acquire(k, &bytes);
+        a = a0;
+        aend = a0 + bytes;
+        continue;
+      }
+      const Hdr L = unpack_hdr(lds128u(a));
+      if (L.flags & kStageEnd) {
+        a = aend;
+        continue;
+      }
+      *hoff = base + k * ring->S + (a - a0);
+      a += 16;
+      return L;
+    }
+  }
+};
+
+__device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }  // written once, never re-read here
+
+}  // namespace
 
 __global__ void __launch_bounds__(kMaxWarpsDyn * 32, 1) logdensity_dynamic_kernel(const __grid_constant__ KernelParams kp) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -33,11 +82,15 @@ __global__ void __launch_bounds__(kMaxWarpsDyn * 32, 1) logdensity_dynamic_kerne
   ln.sc = kp.scratch + chain;  // prefix sums: [(j*T + t)*2 + {att, def}][Cpad]
   ln.sd = kp.sd;
   ln.active = chain_raw < kp.C;
-  const uint32_t tab = smem_u32(smem) + warp * kp.tab_bytes + lane * 8;  // this warp's private tables
+  const uint32_t tab0 = smem_u32(smem) + lane * 8;
+  float* const state = reinterpret_cast<float*>(smem + kp.dyn_state) + lane;  // [(t*2 + {att, def}) * 32]
+  float* const part = reinterpret_cast<float*>(smem + kp.dyn_part) + lane;    // [((buf*W + warp)*10 + i) * 32]
+  float* const hyp = reinterpret_cast<float*>(smem + kp.dyn_hyp) + lane;      // [(buf*10 + i) * 32]
   unsigned long long* red_best = reinterpret_cast<unsigned long long*>(smem + kp.smem_red);  // [3][32]
   uint32_t* red_found = reinterpret_cast<uint32_t*>(smem + kp.smem_red + 768);               // [2][32]
   uint32_t* red_info = reinterpret_cast<uint32_t*>(smem + kp.smem_red + 1024);               // [2][32]
-  float* red_gc = reinterpret_cast<float*>(smem + kp.smem_red + 1280 + 12 * 128);             // [W][32]
+  float* red_gc = reinterpret_cast<float*>(smem + kp.smem_red + 1280);                        // [W][32]
+  float* red_lp = red_gc + W * 32;                                                            // [W][32]
   constexpr uint32_t ESZ = (uint32_t)sizeof(Entry);
   Ring ring;
   ring.init(smem_u32(smem) + kp.smem_ring + warp * (kStages * kp.stage_bytes),
@@ -60,154 +113,132 @@ __global__ void __launch_bounds__(kMaxWarpsDyn * 32, 1) logdensity_dynamic_kerne
   float lp_acc = 0.0f;
   const float r = sigmoid_clipped(ln.ld(o.raw));
   const float mu_d = ln.ld(o.mean_defence);
+  const int nbuf = kp.dyn_nbuf;
 
-  // ---- prefix pass: attack / defence of every (gameweek, team) ----------------------------------------
-  {
-    const uint32_t zr = (uint32_t)T * kRowBytes;  // zero rows of the private tables
-    if (kp.has1) {
-      sts64(tab + kp.tabP1 + zr, 0.0f, 0.0f);
-      sts64(tab + kp.tabQ1 + zr, 0.0f, 0.0f);
-    }
-    if (kp.has0) sts64(tab + kp.tabP0 + zr, 0.0f, 0.0f);
-    if (warp == 0) {
-      red_best[lane] = red_best[32 + lane] = red_best[64 + lane] = 0ull;
-      red_found[lane] = red_found[32 + lane] = 0xffffffffu;
-    }
-    for (int t = warp; t < T; t += W) {
-      float att = 0.0f, def = mu_d;
-      for (int k = 0; k < kp.K; k++) {
-        const float x = __ldg(kp.Xs + (size_t)t * kp.K + k);
-        att = fmaf(x, ln.ld(o.beta_a + k), att);
-        def = fmaf(x, ln.ld(o.beta_d + k), def);
+  if (warp == 0) {
+    const uint32_t zr = (uint32_t)T * kRowBytes;  // zero rows used by padding entries
+    for (int b = 0; b < nbuf; b++) {
+      const uint32_t tb = tab0 + b * kp.tab_bytes;
+      if (kp.has1) {
+        sts64(tb + kp.tabP1 + zr, 0.0f, 0.0f);
+        sts64(tb + kp.tabQ1 + zr, 0.0f, 0.0f);
       }
-      for (int j = 0; j < G; j++) {
-        const int jt = j * T + t;
-        if (kp.as_written) {
-          att = def = 0.0f;  // dynamic_dixon_coles.py:192-218: the .at[].set results are discarded
-        } else {
-          att = fmaf(ln.ld(o.za + jt), expf(ln.ld(o.log_std_attack + j)), att);
-          def = fmaf(ln.ld(o.zd + jt), expf(ln.ld(o.log_std_defence + j)), def);
-        }
+      if (kp.has0) sts64(tb + kp.tabP0 + zr, 0.0f, 0.0f);
+    }
+    red_best[lane] = red_best[32 + lane] = red_best[64 + lane] = 0ull;
+    red_found[lane] = red_found[32 + lane] = 0xffffffffu;
+  }
+  // the walk starts at the prior means: attack = X beta_a, defence = mean_defence + X beta_d
+  for (int t = warp; t < T; t += W) {
+    float a0 = 0.0f, d0 = mu_d;
+    for (int k = 0; k < kp.K; k++) {
+      const float x = __ldg(kp.Xs + (size_t)t * kp.K + k);
+      a0 = fmaf(x, ln.ld(o.beta_a + k), a0);
+      d0 = fmaf(x, ln.ld(o.beta_d + k), d0);
+    }
+    state[(t * 2) * 32] = a0;
+    state[(t * 2 + 1) * 32] = d0;
+  }
+  // per-gameweek hyper-parameters, computed by one warp one gameweek ahead: mu[4], sig[4], sig_attack, sig_defence
+  auto compute_hyp = [&](int j, int buf) {
+    float* h = hyp + buf * 10 * 32;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      h[i * 32] = ln.ld(o.mean[i] + j);
+      h[(4 + i) * 32] = expf(ln.ld(o.log_std[i] + j));
+    }
+    h[8 * 32] = expf(ln.ld(o.log_std_attack + j));
+    h[9 * 32] = expf(ln.ld(o.log_std_defence + j));
+  };
+  struct GwHyp { float mu[4], sig[4], sig_a, sig_d; };
+  auto read_hyp = [&](int buf) {
+    GwHyp h;
+    const float* p = hyp + buf * 10 * 32;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      h.mu[i] = p[i * 32];
+      h.sig[i] = p[(4 + i) * 32];
+    }
+    h.sig_a = p[8 * 32];
+    h.sig_d = p[9 * 32];
+    return h;
+  };
+  if (warp == 0) compute_hyp(0, 0);
+  __syncthreads();
+
+  // table rows of (gameweek j, team t); with_lp: add the static sum of w * y * log(lambda) (linear in the exponents)
+  auto build_row = [&](uint32_t tab, int t, int jt, float att, float def, const GwHyp& h, bool with_lp) {
+    float x[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) x[i] = fmaf(h.sig[i], ln.ld(o.dec[i] + jt), h.mu[i]);
+    float ex[6];
+    ex[eAh1] = att + x[0];
+    ex[eBh1] = -def - x[2];
+    ex[eBa1] = -def - x[3];
+    ex[eAa1] = att + x[1];
+    ex[eA0] = att;
+    ex[eB0] = -def;
+    const uint32_t row = (uint32_t)t * kRowBytes;
+    if (kp.has1) {
+      sts64(tab + kp.tabP1 + row, expf(ex[eAh1]), expf(ex[eBh1]));
+      sts64(tab + kp.tabQ1 + row, expf(ex[eBa1]), expf(ex[eAa1]));
+    }
+    if (kp.has0) sts64(tab + kp.tabP0 + row, expf(ex[eA0]), expf(ex[eB0]));
+    if (with_lp) {
+#pragma unroll
+      for (int e = 0; e < 6; e++) lp_acc = fmaf(__ldg(kp.yexp + (size_t)jt * 6 + e), ex[e], lp_acc);
+    }
+  };
+
+  // ---- forward pass ---------------------------------------------------------------------------------------
+  float best[3] = {0.0f, 0.0f, 0.0f};
+  uint32_t besth[3] = {0u, 0u, 0u};
+  PieceReader rdr;
+  rdr.start(&ring, b1_0);
+  for (int j = 0; j < G; j++) {
+    const int hb = j & 1;
+    const GwHyp h = read_hyp(hb);
+    if (j + 1 < G && warp == (j + 1) % W) compute_hyp(j + 1, hb ^ 1);
+    const uint32_t tab = tab0 + (nbuf == 2 ? hb : 0) * kp.tab_bytes;
+    for (int t = warp; t < T; t += W) {
+      const int jt = j * T + t;
+      float att = 0.0f, def = 0.0f;  // as written (dynamic_dixon_coles.py:192-218): the .at[].set results are discarded
+      if (!kp.as_written) {
+        att = fmaf(ln.ld(o.za + jt), h.sig_a, state[(t * 2) * 32]);
+        def = fmaf(ln.ld(o.zd + jt), h.sig_d, state[(t * 2 + 1) * 32]);
+        state[(t * 2) * 32] = att;
+        state[(t * 2 + 1) * 32] = def;
         if (ln.active) {
           ln.sc[(size_t)(2 * jt) * kp.Cpad] = att;
           ln.sc[(size_t)(2 * jt + 1) * kp.Cpad] = def;
         }
       }
+      if (__ldg(kp.team_flags + jt) & 1) build_row(tab, t, jt, att, def, h, false);
     }
-  }
-  __syncthreads();
-
-  // tables of gameweek j in this warp's slice; with_lp: add the static sum of w * y * log(lambda)
-  auto build_tables = [&](int j, bool with_lp) {
-    float mu[4], sig[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      mu[i] = ln.ld(o.mean[i] + j);
-      sig[i] = expf(ln.ld(o.log_std[i] + j));
+    __syncthreads();  // the gameweek's tables are complete
+    uint32_t hoff;
+    const Hdr Mk = rdr.next(&hoff);
+    for (uint32_t p = 0; p < Mk.n0; p++) {
+      const Hdr L = rdr.next(&hoff);
+      uint32_t a = rdr.a;
+      const uint32_t e_end = a + L.n0 * ESZ;
+      float2 own = lds64(tab + L.own_off);
+      if (L.kind >= kH0) { const float s = own.x; own.x = own.y; own.y = s; }
+      float m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
+      walk16(a, e_end, [&](const uint32_t at) {
+        const uint4 q = lds128u(at);  // two entries
+        const float2 ea = lds64(tab + q.x), eb = lds64(tab + q.z);
+        m1 = fmaxf(m1, fmaxf(ea.x, eb.x));
+        m2 = fmaxf(m2, fmaxf(ea.y, eb.y));
+        m3 = fmaxf(m3, fmaxf(ea.x * ea.y, eb.x * eb.y));
+      });
+      rdr.a = a;
+      const float v0 = own.x * m1, v1 = own.y * m2, v2 = (own.x * own.y) * m3;
+      if (v0 > best[0]) { best[0] = v0; besth[0] = hoff; }
+      if (v1 > best[1]) { best[1] = v1; besth[1] = hoff; }
+      if (v2 > best[2]) { best[2] = v2; besth[2] = hoff; }
     }
-    const int i0 = __ldg(kp.gw_tptr + j), i1 = __ldg(kp.gw_tptr + j + 1);
-    constexpr int B = 4;  // teams per batch: all loads of a batch are in flight together
-    for (int ib = i0; ib < i1; ib += B) {
-      int tt[B];
-      float att[B], def[B], dec[B][4];
-#pragma unroll
-      for (int b = 0; b < B; b++) {
-        tt[b] = __ldg(kp.gw_tlist + min(ib + b, i1 - 1));
-        const int jt = j * T + tt[b];
-        att[b] = ld_cg(ln.sc + (size_t)(2 * jt) * kp.Cpad);
-        def[b] = ld_cg(ln.sc + (size_t)(2 * jt + 1) * kp.Cpad);
-#pragma unroll
-        for (int i = 0; i < 4; i++) dec[b][i] = ln.ld(o.dec[i] + jt);
-      }
-#pragma unroll
-      for (int b = 0; b < B; b++) {
-        if (ib + b >= i1) break;
-        const int t = tt[b], jt = j * T + t;
-        float x[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) x[i] = fmaf(sig[i], dec[b][i], mu[i]);
-        float ex[6];
-        ex[eAh1] = att[b] + x[0];
-        ex[eBh1] = -def[b] - x[2];
-        ex[eBa1] = -def[b] - x[3];
-        ex[eAa1] = att[b] + x[1];
-        ex[eA0] = att[b];
-        ex[eB0] = -def[b];
-        const uint32_t row = (uint32_t)t * kRowBytes;
-        if (kp.has1) {
-          sts64(tab + kp.tabP1 + row, expf(ex[eAh1]), expf(ex[eBh1]));
-          sts64(tab + kp.tabQ1 + row, expf(ex[eBa1]), expf(ex[eAa1]));
-        }
-        if (kp.has0) sts64(tab + kp.tabP0 + row, expf(ex[eA0]), expf(ex[eB0]));
-        if (with_lp) {
-#pragma unroll
-          for (int e = 0; e < 6; e++) lp_acc = fmaf(__ldg(kp.yexp + (size_t)jt * 6 + e), ex[e], lp_acc);
-        }
-      }
-    }
-  };
-  auto slot = [&](int base, int jt) { return ln.g(base + jt); };
-
-  // ---- phase 1 ----------------------------------------------------------------------------------
-  float best[3] = {0.0f, 0.0f, 0.0f};
-  uint32_t besth[3] = {0u, 0u, 0u};
-  {
-    float g[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-    const uint32_t nst = ring.num_stages();
-    for (uint32_t k = 0; k < nst; k++) {
-      uint32_t bytes;
-      const uint32_t a0 = ring.acquire(k, &bytes);
-      uint32_t a = a0;
-      const uint32_t aend = a0 + bytes;
-      while (a + 16 <= aend) {
-        const uint32_t hoff = b1_0 + k * ring.S + (a - a0);
-        const Hdr L = unpack_hdr(lds128u(a));
-        a += 16;
-        if (L.flags & kGwFirst) build_tables((int)L.vteam, true);
-        if (L.team == 0xffffu) continue;  // marker or filler
-        const uint32_t e_end = a + L.n0 * ESZ;
-        if (L.flags & kTeamFirst) {
-#pragma unroll
-          for (int e = 0; e < 6; e++) g[e] = 0.0f;
-        }
-        float2 own = lds64(tab + L.own_off);
-        if (L.kind >= kH0) { const float s = own.x; own.x = own.y; own.y = s; }
-        const bool home = (L.kind & 1) == 0;
-        float ax0 = 0.0f, ay0 = 0.0f, ax1 = 0.0f, ay1 = 0.0f, m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
-#pragma unroll 4
-        for (; a < e_end; a += 16) {
-          const uint4 q = lds128u(a);  // two entries
-          const float2 ea = lds64(tab + q.x), eb = lds64(tab + q.z);
-          const float wa = __uint_as_float(q.y), wb = __uint_as_float(q.w);
-          ax0 = fmaf(wa, ea.x, ax0); ay0 = fmaf(wa, ea.y, ay0);
-          ax1 = fmaf(wb, eb.x, ax1); ay1 = fmaf(wb, eb.y, ay1);
-          if (home) {  // warp-uniform
-            m1 = fmaxf(m1, fmaxf(ea.x, eb.x));
-            m2 = fmaxf(m2, fmaxf(ea.y, eb.y));
-            m3 = fmaxf(m3, fmaxf(ea.x * ea.y, eb.x * eb.y));
-          }
-        }
-        if (home) {
-          const float v0 = own.x * m1, v1 = own.y * m2, v2 = (own.x * own.y) * m3;
-          if (v0 > best[0]) { best[0] = v0; besth[0] = hoff; }
-          if (v1 > best[1]) { best[1] = v1; besth[1] = hoff; }
-          if (v2 > best[2]) { best[2] = v2; besth[2] = hoff; }
-        }
-        const float SX = own.x * (ax0 + ax1), SY = own.y * (ay0 + ay1);
-        lp_acc -= 0.5f * (SX + SY);  // every match is in two lists
-        add_own(g, L.kind, -SX, -SY);
-        if ((L.flags & kTeamLast) && ln.active) {
-          const int jt = (int)L.vteam * T + (int)L.team;
-          *slot(o.za, jt) = g[eAh1] + g[eAa1] + g[eA0];
-          *slot(o.zd, jt) = -(g[eBh1] + g[eBa1] + g[eB0]);
-          *slot(o.dec[0], jt) = g[eAh1];
-          *slot(o.dec[1], jt) = g[eAa1];
-          *slot(o.dec[2], jt) = -g[eBh1];
-          *slot(o.dec[3], jt) = -g[eBa1];
-        }
-      }
-      ring.release(k);
-    }
+    if (nbuf == 1) __syncthreads();  // (one table buffer: nobody may still read it when the next gameweek is built)
   }
   const uint32_t b2_0 = __ldg(kp.warp_b2 + warp), b2_1 = __ldg(kp.warp_b2 + warp + 1);
   ring.begin(kp.stream2 + b2_0, b2_1 - b2_0);
@@ -217,6 +248,8 @@ __global__ void __launch_bounds__(kMaxWarpsDyn * 32, 1) logdensity_dynamic_kerne
   for (int q = 0; q < 3; q++)
     if (best[q] > 0.0f)
       atomicMax(red_best + q * 32 + lane, ((unsigned long long)__float_as_uint(best[q]) << 32) | besth[q]);
+  // the backward pass accumulates suffix sums in the per-team state
+  for (int t = warp; t < T; t += W) state[(t * 2) * 32] = state[(t * 2 + 1) * 32] = 0.0f;
   __syncthreads();
 #pragma unroll
   for (int q = 0; q < 3; q++) {
@@ -229,121 +262,181 @@ __global__ void __launch_bounds__(kMaxWarpsDyn * 32, 1) logdensity_dynamic_kerne
   const float LB = -1.0f / Lam;
   const float UB = fminf(1.0f / best[2], 1.0f);
   const float cc = fmaf(r, UB - LB, LB);
-  const uint32_t hoff0 = qlam == 0 ? besth[0] : besth[1], hoff1 = besth[2];
-  // gameweeks of the two arg-max pieces (0xffff = no search needed)
-  uint32_t gwsel = unpack_hdr(__ldg(reinterpret_cast<const uint4*>(kp.stream1 + hoff0))).vteam;
-  gwsel |= (best[2] > 1.0f ? unpack_hdr(__ldg(reinterpret_cast<const uint4*>(kp.stream1 + hoff1))).vteam : 0xffffu) << 16;
+  // the two arg-max pieces and their gameweeks (0xffff: no dependence on the rates -- UB = 1)
+  uint32_t s_hoff[2], s_gw[2];
+  s_hoff[0] = qlam == 0 ? besth[0] : besth[1];
+  s_hoff[1] = besth[2];
+  s_gw[0] = Lam > 0.0f ? unpack_hdr(__ldg(reinterpret_cast<const uint4*>(kp.stream1 + s_hoff[0]))).vteam : 0xffffu;
+  s_gw[1] = best[2] > 1.0f ? unpack_hdr(__ldg(reinterpret_cast<const uint4*>(kp.stream1 + s_hoff[1]))).vteam : 0xffffu;
 
-  // ---- phase 2: tau terms (bpl/_util.py:54-91) + arg-max search in the resident gameweek --------------
+  // the ten hyper-parameter sites of gameweek j: likelihood sums from the warps' partials + priors + Jacobians
+  auto reduce_hyper = [&](int j) {
+    const float* pb = part + (size_t)((j & 1) * W) * 10 * 32;
+    float s[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) s[i] = 0.0f;
+    for (int w = 0; w < W; w++) {
+#pragma unroll
+      for (int i = 0; i < 10; i++) s[i] += pb[(w * 10 + i) * 32];
+    }
+    const float lsa = ln.ld(o.log_std_attack + j), lsd = ln.ld(o.log_std_defence + j);
+    const float sig_a = expf(lsa), sig_d = expf(lsd);
+    lp_acc += fmaf(-0.5f * sig_a, sig_a, lsa) + fmaf(-0.5f * sig_d, sig_d, lsd);
+    if (ln.active) {
+      st_stream(ln.g(o.log_std_attack + j), fmaf(-sig_a, sig_a, 1.0f) + s[0]);
+      st_stream(ln.g(o.log_std_defence + j), fmaf(-sig_d, sig_d, 1.0f) + s[1]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const float mu = ln.ld(o.mean[i] + j), lsig = ln.ld(o.log_std[i] + j), sig = expf(lsig);
+      const float z = (mu - ((i & 1) ? -0.1f : 0.1f)) * 5.0f;  // N(+-0.1, 0.2)
+      lp_acc += -0.5f * z * z + fmaf(-0.5f * sig, sig, lsig);
+      if (ln.active) {
+        st_stream(ln.g(o.mean[i] + j), fmaf(-z, 5.0f, s[2 + i]));
+        st_stream(ln.g(o.log_std[i] + j), fmaf(-sig, sig, 1.0f) + s[6 + i]);
+      }
+    }
+  };
+
+  // ---- backward pass ----------------------------------------------------------------------------------
   float gc = 0.0f;
-  {
-    float g[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-    const uint32_t nst = ring.num_stages();
-    for (uint32_t k = 0; k < nst; k++) {
-      uint32_t bytes;
-      const uint32_t a0 = ring.acquire(k, &bytes);
-      uint32_t a = a0;
-      const uint32_t aend = a0 + bytes;
-      while (a + 16 <= aend) {
-        const Hdr L = unpack_hdr(lds128u(a));
-        a += 16;
-        if (L.flags & kGwFirst) {
-          const uint32_t j = L.vteam;
-          build_tables((int)j, false);
+  rdr.start(&ring, b2_0);
+  for (int j = G - 1; j >= 0; j--) {
+    const int hb = j & 1;
+    const GwHyp h = read_hyp(hb);
+    if (j > 0 && warp == (j - 1) % W) compute_hyp(j - 1, hb ^ 1);
+    const uint32_t tab = tab0 + (nbuf == 2 ? hb : 0) * kp.tab_bytes;
+    for (int t = warp; t < T; t += W) {
+      const int jt = j * T + t;
+      if (__ldg(kp.team_flags + jt) & 1) {
+        float att = 0.0f, def = 0.0f;
+        if (!kp.as_written) {
+          att = ld_cg(ln.sc + (size_t)(2 * jt) * kp.Cpad);
+          def = ld_cg(ln.sc + (size_t)(2 * jt + 1) * kp.Cpad);
+        }
+        build_row(tab, t, jt, att, def, h, true);
+      }
+    }
+    __syncthreads();  // tables complete; the hyper partials of gameweek j + 1 are all written
+    if (j + 1 < G && warp == (j + 1) % W) reduce_hyper(j + 1);
+    // arg-max search: the entry of the piece that attained the maximum, while its gameweek is resident; warp w looks
+    // at entries w, w + W, ...; ties (rates that overflowed to inf) go to the lowest entry -- atomicMin, not timing
 #pragma unroll 1
-          for (int which = 0; which < 2; which++) {
-            const bool need = ((gwsel >> (16 * which)) & 0xffffu) == j;
-            if (!__any_sync(kFull, need)) continue;
-            const uint32_t hoff = which == 0 ? hoff0 : hoff1;
-            const float target = which == 0 ? Lam : best[2];
-            const int q = which == 0 ? qlam : 2;
-            const Hdr P = unpack_hdr(__ldg(reinterpret_cast<const uint4*>(kp.stream1 + hoff)));
-            const uint32_t n = need ? P.n0 : 0u;
-            float2 own = lds64(tab + (need ? P.own_off : 0u));
-            if (P.kind >= kH0) { const float s = own.x; own.x = own.y; own.y = s; }
-            const unsigned char* ent = kp.stream1 + hoff + 16;
-            const uint32_t nmax = __reduce_max_sync(kFull, n);
-            uint32_t found = 0xffffffffu;
-            for (uint32_t i = 0; i < nmax; i++) {
-              if (i < n && found == 0xffffffffu) {
-                const uint32_t off = __ldg(reinterpret_cast<const uint32_t*>(ent + (size_t)i * ESZ));
-                const float2 ea = lds64(tab + off);
-                const float val = q == 0 ? own.x * ea.x : (q == 1 ? own.y * ea.y : (own.x * own.y) * (ea.x * ea.y));
-                if (val == target) found = (i << 24) | off;
-              }
-            }
-            if (found != 0xffffffffu) {
-              red_found[which * 32 + lane] = found;
-              red_info[which * 32 + lane] = P.team | (P.kind << 16) | (3u << 18);  // own team | kind | nothing clipped
-            }
-          }
-        }
-        if (L.team == 0xffffu) continue;
-        if (L.flags & kTeamFirst) {
-#pragma unroll
-          for (int e = 0; e < 6; e++) g[e] = 0.0f;
-        }
-        float2 own = lds64(tab + L.own_off);
-        if (L.kind >= kH0) { const float s = own.x; own.x = own.y; own.y = s; }
-        const bool home = (L.kind & 1) == 0;
-        float lt = 0.0f, uxy = 0.0f;
-        {  // tau = 1 - c X Y
-          const float Pxy = own.x * own.y;
-          const uint32_t e_end = a + L.n0 * ESZ;
-#pragma unroll 1
-          for (; a < e_end; a += 16) {
-            const uint4 q = lds128u(a);
-#pragma unroll
-            for (int jj = 0; jj < 2; jj++) {
-              const float2 ea = lds64(tab + (jj ? q.z : q.x));
-              const float w = __uint_as_float(jj ? q.w : q.y);
-              const float t = Pxy * (ea.x * ea.y);
-              const float tau = fmaxf(fmaf(-cc, t, 1.0f), 0.0f);
-              uxy = fmaf(w * t, rcp_approx(tau), uxy);
-              if (home) lt = fmaf(w, lg2_approx(tau), lt);
-            }
-          }
-        }
-        float u1[2] = {0.0f, 0.0f};  // tau = 1 + c X, then tau = 1 + c Y
-#pragma unroll
-        for (int c = 0; c < 2; c++) {
-          const float oc = c == 0 ? own.x : own.y;
-          const uint32_t e_end = a + (c == 0 ? L.n1 : L.n2) * ESZ;
-          float u = 0.0f;
-#pragma unroll 1
-          for (; a < e_end; a += 16) {
-            const uint4 q = lds128u(a);
-#pragma unroll
-            for (int jj = 0; jj < 2; jj++) {
-              const float R = oc * lds32(tab + (jj ? q.z : q.x));
-              const float w = __uint_as_float(jj ? q.w : q.y);
-              const float tau = fmaxf(fmaf(cc, R, 1.0f), 0.0f);
-              u = fmaf(w * R, rcp_approx(tau), u);
-              if (home) lt = fmaf(w, lg2_approx(tau), lt);
-            }
-          }
-          u1[c] = u;
-        }
-        if (home) {
-          lp_acc = fmaf(lt, kLn2, lp_acc);
-          gc += u1[0] + u1[1] - uxy;
-        }
-        add_own(g, L.kind, cc * (u1[0] - uxy), cc * (u1[1] - uxy));
-        if ((L.flags & kTeamLast) && ln.active) {
-          const int jt = (int)L.vteam * T + (int)L.team;
-          red_add(slot(o.za, jt), g[eAh1] + g[eAa1] + g[eA0]);
-          red_add(slot(o.zd, jt), -(g[eBh1] + g[eBa1] + g[eB0]));
-          red_add(slot(o.dec[0], jt), g[eAh1]);
-          red_add(slot(o.dec[1], jt), g[eAa1]);
-          red_add(slot(o.dec[2], jt), -g[eBh1]);
-          red_add(slot(o.dec[3], jt), -g[eBa1]);
+    for (int which = 0; which < 2; which++) {
+      const bool need = s_gw[which] == (uint32_t)j;
+      if (!__any_sync(kFull, need)) continue;
+      const float target = which == 0 ? Lam : best[2];
+      const int q = which == 0 ? qlam : 2;
+      const unsigned char* base = kp.stream1 + (need ? s_hoff[which] : b1_0);
+      const Hdr P = unpack_hdr(__ldg(reinterpret_cast<const uint4*>(base)));
+      const uint32_t n = need ? P.n0 : 0u;
+      float2 own = lds64(tab + (need ? P.own_off : 0u));
+      if (P.kind >= kH0) { const float s = own.x; own.x = own.y; own.y = s; }
+      const uint32_t nmax = __reduce_max_sync(kFull, n);
+      uint32_t found = 0xffffffffu;
+      for (uint32_t i = warp; i < nmax; i += W) {
+        if (i < n && found == 0xffffffffu) {
+          const uint32_t off = __ldg(reinterpret_cast<const uint32_t*>(base + 16 + (size_t)i * ESZ));
+          const float2 ea = lds64(tab + off);
+          const float val = q == 0 ? own.x * ea.x : (q == 1 ? own.y * ea.y : (own.x * own.y) * (ea.x * ea.y));
+          if (val == target) found = (i << 24) | off;
         }
       }
-      ring.release(k);
+      if (found != 0xffffffffu) {
+        atomicMin(red_found + which * 32 + lane, found);
+        red_info[which * 32 + lane] = P.team | (P.kind << 16);  // own team | kind: the same for every finder of this chain
+      }
     }
+    // the gameweek's pieces: every team of this warp is completed here
+    float hp[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) hp[i] = 0.0f;
+    float g[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    uint32_t hoff;
+    const Hdr Mk = rdr.next(&hoff);
+    for (uint32_t p = 0; p < Mk.n0; p++) {
+      const Hdr L = rdr.next(&hoff);
+      uint32_t a = rdr.a;
+      if (L.flags & kTeamFirst) {
+#pragma unroll
+        for (int e = 0; e < 6; e++) g[e] = 0.0f;
+      }
+      float2 own = lds64(tab + L.own_off);
+      if (L.kind >= kH0) { const float s = own.x; own.x = own.y; own.y = s; }
+      const bool home = (L.kind & 1) == 0;
+      if (!(L.flags & kPhase2)) {  // rates: sum w lambda over the list (every match is in two lists)
+        const uint32_t e_end = a + L.n0 * ESZ;
+        float2 acc0 = make_float2(0.0f, 0.0f), acc1 = acc0;
+        walk16(a, e_end, [&](const uint32_t at) {
+          const uint4 q = lds128u(at);
+          const float2 ea = lds64(tab + q.x), eb = lds64(tab + q.z);
+          acc0 = fma2(bc2(__uint_as_float(q.y)), ea, acc0);
+          acc1 = fma2(bc2(__uint_as_float(q.w)), eb, acc1);
+        });
+        const float SX = own.x * (acc0.x + acc1.x), SY = own.y * (acc0.y + acc1.y);
+        lp_acc -= 0.5f * (SX + SY);
+        add_own(g, L.kind, -SX, -SY);
+      } else {  // tau terms (bpl/_util.py:54-91)
+        float lt, du, gx, gy;
+        tau_piece<kTauPlain>(a, L, own, home, cc, tab, lt, du, gx, gy);
+        if (home) {
+          lp_acc = fmaf(lt, kLn2, lp_acc);
+          gc += du;
+        }
+        add_own(g, L.kind, gx, gy);
+      }
+      rdr.a = a;
+      if (L.flags & kTeamLast) {
+        // ---- (gameweek j, team t) is complete: suffix sums, priors, chain rule, its seven gradient entries -----
+        const int t = (int)L.team, jt = j * T + t;
+        const float4 ys = __ldg(reinterpret_cast<const float4*>(kp.yteam + (size_t)jt * 8));
+        const float2 ys2 = __ldg(reinterpret_cast<const float2*>(kp.yteam + (size_t)jt * 8 + 4));
+        const float za = ln.ld(o.za + jt), zd = ln.ld(o.zd + jt), ul = ln.ld(o.u + jt);
+        float dec[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) dec[i] = ln.ld(o.dec[i] + jt);
+        const float ra = g[eAh1] + g[eAa1] + g[eA0] + ys.x;
+        const float rd = -(g[eBh1] + g[eBa1] + g[eB0]) + ys.y;
+        const float rx[4] = {g[eAh1] + ys.z, g[eAa1] + ys.w, -g[eBh1] + ys2.x, -g[eBa1] + ys2.y};
+        float s_att = 0.0f, s_def = 0.0f;
+        if (!kp.as_written) {  // d/d attack[j] reaches every later gameweek's rates: the walk's transpose
+          s_att = state[(t * 2) * 32] + ra;
+          s_def = state[(t * 2 + 1) * 32] + rd;
+          state[(t * 2) * 32] = s_att;
+          state[(t * 2 + 1) * 32] = s_def;
+        }
+        // u ~ Beta(2,4) + Jacobian; za ~ N(0,1); zd ~ N(rho za, sqrt(1 - rho^2))  (dynamic_dixon_coles.py:128-143)
+        const float u = sigmoid_clipped(ul);
+        const float rho = 2.0f * u - 1.0f, inv_s2 = 1.0f / (1.0f - rho * rho);
+        const float e = zd - rho * za, es = e * inv_s2;
+        lp_acc += -0.5f * (za * za + e * es) + 0.5f * logf(inv_s2) + 2.0f * logf(u) + 4.0f * logf(1.0f - u);
+        const float a_rho = es * za - rho * es * es + rho * inv_s2;
+        if (ln.active) {
+          st_stream(ln.g(o.u + jt), 2.0f - 6.0f * u + a_rho * 2.0f * u * (1.0f - u));
+          st_stream(ln.g(o.za + jt), fmaf(h.sig_a, s_att, -za + rho * es));
+          st_stream(ln.g(o.zd + jt), fmaf(h.sig_d, s_def, -es));
+        }
+        hp[0] = fmaf(h.sig_a * za, s_att, hp[0]);
+        hp[1] = fmaf(h.sig_d * zd, s_def, hp[1]);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          lp_acc -= 0.5f * dec[i] * dec[i];
+          if (ln.active) st_stream(ln.g(o.dec[i] + jt), fmaf(h.sig[i], rx[i], -dec[i]));
+          hp[2 + i] += rx[i];
+          hp[6 + i] = fmaf(h.sig[i] * dec[i], rx[i], hp[6 + i]);
+        }
+      }
+    }
+    {
+      float* pb = part + (size_t)((hb * W + warp) * 10) * 32;
+#pragma unroll
+      for (int i = 0; i < 10; i++) pb[i * 32] = hp[i];
+    }
+    if (nbuf == 1) __syncthreads();
   }
   red_gc[warp * 32 + lane] = gc;
-  __syncthreads();  // tables are dead from here on; raw slots hold both phases
+  __syncthreads();  // partials of gameweek 0, the suffix sums of every team and every gradient entry are written
+  if (warp == 0) reduce_hyper(0);
   gc = 0.0f;
   for (int w = 0; w < W; w++) gc += red_gc[w * 32 + lane];
   {  // the 1-1 matches: tau = 1 - c for all of them
@@ -351,22 +444,24 @@ __global__ void __launch_bounds__(kMaxWarpsDyn * 32, 1) logdensity_dynamic_kerne
     gc -= kp.w11 / t11;
     if (warp == 0 && kp.w11 != 0.0f) lp_acc = fmaf(kp.w11, logf(t11), lp_acc);
   }
+  __syncthreads();  // (reduce_hyper(0) has written gameweek 0's hyper gradients: the fix-up below may add to them)
 
-  // ---- arg-max fix-up descriptors ---------------------------------------------------
+  // ---- arg-max fix-up, as a correction of the entries it reaches --------------------------
   Fixup fx;
   fx.h1 = 0u;
   fx.confs = 0u;
+  int f_gw[2], f_team[2][2];
 #pragma unroll
   for (int which = 0; which < 2; which++) {
     const uint32_t packed = red_found[which * 32 + lane];
-    fx.teams[which] = 0xffffffffu;
-    fx.vts[which] = 0xffffu;  // the gameweek
+    fx.teams[which] = fx.vts[which] = 0xffffffffu;
     fx.vx[which] = fx.vy[which] = 0.0f;
+    f_gw[which] = -1;
+    f_team[which][0] = f_team[which][1] = 0;
     if (packed != 0xffffffffu) {
       const uint32_t info = red_info[which * 32 + lane];
       const uint32_t f_off = packed & 0xffffffu;
       const bool h1 = ((info >> 16) & 3u) == kH1;
-      const uint32_t opp_t = ((f_off & ~7u) - (h1 ? kp.tabQ1 : kp.tabP0)) / kRowBytes;
       if (which == 0) {
         const float wgt = gc * (1.0f - r) / Lam;  // dc/dLB * dLB/d eta
         fx.vx[0] = qlam == 0 ? wgt : 0.0f;
@@ -376,157 +471,98 @@ __global__ void __launch_bounds__(kMaxWarpsDyn * 32, 1) logdensity_dynamic_kerne
         fx.vx[1] = fx.vy[1] = wgt;
       }
       fx.h1 |= (h1 ? 1u : 0u) << which;
-      fx.teams[which] = (info & 0xffffu) | (opp_t << 16);
-      fx.vts[which] = (gwsel >> (16 * which)) & 0xffffu;
+      f_gw[which] = (int)s_gw[which];
+      f_team[which][0] = (int)(info & 0xffffu);
+      f_team[which][1] = (int)(((f_off & ~7u) - (h1 ? kp.tabQ1 : kp.tabP0)) / kRowBytes);
     }
   }
-
-  // ---- suffix pass (team-owned): complete the raw slots; attack / defence slots <- sums over later gameweeks --
-  for (int t = warp; t < T; t += W) {
-    float s_att = 0.0f, s_def = 0.0f;
-    constexpr int B = 2;  // gameweeks per batch: all loads of a batch are in flight together
-    for (int jb = G - 1; jb >= 0; jb -= B) {
-      float ra[B], rd[B], rx[B][4];
+  float fix_md = 0.0f;  // what the fix-up adds to sum_t d/d defence[0, t] (mean_defence) -- and per team for the coefficients
+  for (int j = warp; j < G; j += W) {
 #pragma unroll
-      for (int b = 0; b < B; b++) {
-        const int j = max(jb - b, 0), jt = j * T + t;
-        const float4 ys = __ldg(reinterpret_cast<const float4*>(kp.yteam + (size_t)jt * 8));
-        const float2 ys2 = __ldg(reinterpret_cast<const float2*>(kp.yteam + (size_t)jt * 8 + 4));
-        ra[b] = ys.x; rd[b] = ys.y; rx[b][0] = ys.z; rx[b][1] = ys.w; rx[b][2] = ys2.x; rx[b][3] = ys2.y;
-        if (__ldg(kp.team_flags + jt) & 1) {  // phase 1 wrote the slots of this (gameweek, team)
-          ra[b] += ld_cg(slot(o.za, jt));
-          rd[b] += ld_cg(slot(o.zd, jt));
+    for (int which = 0; which < 2; which++) {
+      if (f_gw[which] < j) continue;  // (also: no fix-up for this chain)
 #pragma unroll
-          for (int i = 0; i < 4; i++) rx[b][i] += ld_cg(slot(o.dec[i], jt));
-        }
-      }
+      for (int side = 0; side < 2; side++) {
+        float dra = 0.0f, drd = 0.0f, drx[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        fold_fixup(fx, which, side, dra, drd, drx);
+        const int t = f_team[which][side], jt = j * T + t;
+        if (j == f_gw[which]) {  // the venue effects of the match's own gameweek
 #pragma unroll
-      for (int b = 0; b < B; b++) {
-        const int j = jb - b;
-        if (j < 0) break;
-        const int jt = j * T + t;
-#pragma unroll
-        for (int which = 0; which < 2; which++) {
-          if (fx.vts[which] == (uint32_t)j) {
-            if ((fx.teams[which] & 0xffffu) == (uint32_t)t) fold_fixup(fx, which, 0, ra[b], rd[b], rx[b]);
-            if ((fx.teams[which] >> 16) == (uint32_t)t) fold_fixup(fx, which, 1, ra[b], rd[b], rx[b]);
+          for (int i = 0; i < 4; i++) {
+            const float sig = expf(ln.ld(o.log_std[i] + j));
+            if (ln.active) {
+              *ln.g(o.dec[i] + jt) += sig * drx[i];
+              *ln.g(o.mean[i] + j) += drx[i];
+              *ln.g(o.log_std[i] + j) += sig * ln.ld(o.dec[i] + jt) * drx[i];
+            }
           }
         }
-        s_att += ra[b];
-        s_def += rd[b];
-        if (ln.active) {
-          *slot(o.za, jt) = kp.as_written ? 0.0f : s_att;
-          *slot(o.zd, jt) = kp.as_written ? 0.0f : s_def;
-#pragma unroll
-          for (int i = 0; i < 4; i++) *slot(o.dec[i], jt) = rx[b][i];
+        if (!kp.as_written && ln.active) {  // attack / defence of gameweek j <= the match's: every walk step up to it
+          const float sa = expf(ln.ld(o.log_std_attack + j)), sd = expf(ln.ld(o.log_std_defence + j));
+          *ln.g(o.za + jt) += sa * dra;
+          *ln.g(o.zd + jt) += sd * drd;
+          *ln.g(o.log_std_attack + j) += sa * ln.ld(o.za + jt) * dra;
+          *ln.g(o.log_std_defence + j) += sd * ln.ld(o.zd + jt) * drd;
         }
       }
     }
   }
-  __syncthreads();
-
-  // ---- gameweek pass (gameweek-owned): priors, chain rule, per-gameweek hyper-parameter gradients ------------
-  float lp = 0.0f;  // this warp's part of the prior terms
-  for (int j = warp; j < G; j += W) {
-    if (j == 0) {  // mean_defence and the covariate coefficients see the whole walk: sum_t d/d attack[0], defence[0]
-      float s = 0.0f;
-      for (int t = 0; t < T; t++) s += ld_cg(slot(o.zd, t));
-      lp -= 0.5f * mu_d * mu_d;
-      if (ln.active) *ln.g(o.mean_defence) = s - mu_d;
-      for (int k = 0; k < kp.K; k++) {
-        float sa = 0.0f, sd = 0.0f;
+  // mean_defence and the covariate coefficients see the whole walk: sum_t d/d attack[0, t], d/d defence[0, t]
+  float lp = 0.0f;
+  const int wlast = W > 1 ? 1 : 0;
+  if (warp == wlast) {
+    float fdra[2][2], fdrd[2][2];
+#pragma unroll
+    for (int which = 0; which < 2; which++)
+#pragma unroll
+      for (int side = 0; side < 2; side++) {
+        float dra = 0.0f, drd = 0.0f, drx[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (f_gw[which] >= 0 && !kp.as_written) fold_fixup(fx, which, side, dra, drd, drx);
+        fdra[which][side] = dra;
+        fdrd[which][side] = drd;
+        fix_md += drd;
+      }
+    float s = 0.0f;
+    if (!kp.as_written)
+      for (int t = 0; t < T; t++) s += state[(t * 2 + 1) * 32];
+    lp -= 0.5f * mu_d * mu_d;
+    if (ln.active) *ln.g(o.mean_defence) = s + fix_md - mu_d;
+    for (int k = 0; k < kp.K; k++) {
+      float sa = 0.0f, sd = 0.0f;
+      if (!kp.as_written) {
         for (int t = 0; t < T; t++) {
           const float x = __ldg(kp.Xs + (size_t)t * kp.K + k);
-          sa = fmaf(x, ld_cg(slot(o.za, t)), sa);
-          sd = fmaf(x, ld_cg(slot(o.zd, t)), sd);
+          sa = fmaf(x, state[(t * 2) * 32], sa);
+          sd = fmaf(x, state[(t * 2 + 1) * 32], sd);
         }
-        const float ba = ln.ld(o.beta_a + k), bd = ln.ld(o.beta_d + k);
-        lp -= 0.5f * (ba * ba + bd * bd);
-        if (ln.active) {
-          *ln.g(o.beta_a + k) = sa - ba;
-          *ln.g(o.beta_d + k) = sd - bd;
-        }
+#pragma unroll
+        for (int which = 0; which < 2; which++)
+#pragma unroll
+          for (int side = 0; side < 2; side++) {
+            const float x = __ldg(kp.Xs + (size_t)f_team[which][side] * kp.K + k);
+            sa = fmaf(x, fdra[which][side], sa);
+            sd = fmaf(x, fdrd[which][side], sd);
+          }
       }
-    }
-    const float lsa = ln.ld(o.log_std_attack + j), lsd = ln.ld(o.log_std_defence + j);
-    const float sig_a = expf(lsa), sig_d = expf(lsd);
-    float mu[4], lsig[4], sig[4], a_mu[4], a_ls[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      mu[i] = ln.ld(o.mean[i] + j);
-      lsig[i] = ln.ld(o.log_std[i] + j);
-      sig[i] = expf(lsig[i]);
-      a_mu[i] = a_ls[i] = 0.0f;
-    }
-    float a_ls_a = 0.0f, a_ls_d = 0.0f;
-    constexpr int B = 2;  // teams per batch: all loads of a batch are in flight together
-    for (int tb = 0; tb < T; tb += B) {
-      float za[B], zd[B], ul[B], s_att[B], s_def[B], dec[B][4], rx[B][4];
-#pragma unroll
-      for (int b = 0; b < B; b++) {
-        const int jt = j * T + min(tb + b, T - 1);
-        za[b] = ln.ld(o.za + jt); zd[b] = ln.ld(o.zd + jt); ul[b] = ln.ld(o.u + jt);
-        s_att[b] = ld_cg(slot(o.za, jt)); s_def[b] = ld_cg(slot(o.zd, jt));
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          dec[b][i] = ln.ld(o.dec[i] + jt);
-          rx[b][i] = ld_cg(slot(o.dec[i], jt));
-        }
-      }
-#pragma unroll
-      for (int b = 0; b < B; b++) {
-        if (tb + b >= T) break;
-        const int jt = j * T + tb + b;
-        const float u = sigmoid_clipped(ul[b]);
-        const float rho = 2.0f * u - 1.0f, inv_s2 = 1.0f / (1.0f - rho * rho);
-        const float e = zd[b] - rho * za[b], es = e * inv_s2;
-        // u ~ Beta(2,4) + Jacobian; za ~ N(0,1); zd ~ N(rho za, sqrt(1 - rho^2))  (dynamic_dixon_coles.py:128-143)
-        lp += -0.5f * (za[b] * za[b] + e * es) + 0.5f * logf(inv_s2) + 2.0f * logf(u) + 4.0f * logf(1.0f - u);
-        const float a_rho = es * za[b] - rho * es * es + rho * inv_s2;
-        if (ln.active) {
-          *slot(o.u, jt) = 2.0f - 6.0f * u + a_rho * 2.0f * u * (1.0f - u);
-          *slot(o.za, jt) = fmaf(sig_a, s_att[b], -za[b] + rho * es);
-          *slot(o.zd, jt) = fmaf(sig_d, s_def[b], -es);
-        }
-        a_ls_a = fmaf(sig_a * za[b], s_att[b], a_ls_a);
-        a_ls_d = fmaf(sig_d * zd[b], s_def[b], a_ls_d);
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          lp -= 0.5f * dec[b][i] * dec[b][i];
-          if (ln.active) *slot(o.dec[i], jt) = fmaf(sig[i], rx[b][i], -dec[b][i]);
-          a_mu[i] += rx[b][i];
-          a_ls[i] = fmaf(sig[i] * dec[b][i], rx[b][i], a_ls[i]);
-        }
-      }
-    }
-    // the ten hyper-parameters of gameweek j (dynamic_dixon_coles.py:74-98)
-    lp += fmaf(-0.5f * sig_a, sig_a, lsa) + fmaf(-0.5f * sig_d, sig_d, lsd);
-    if (ln.active) {
-      *ln.g(o.log_std_attack + j) = fmaf(-sig_a, sig_a, 1.0f) + a_ls_a;
-      *ln.g(o.log_std_defence + j) = fmaf(-sig_d, sig_d, 1.0f) + a_ls_d;
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const float z = (mu[i] - ((i & 1) ? -0.1f : 0.1f)) * 5.0f;  // N(+-0.1, 0.2)
-      lp += -0.5f * z * z + fmaf(-0.5f * sig[i], sig[i], lsig[i]);
+      const float ba = ln.ld(o.beta_a + k), bd = ln.ld(o.beta_d + k);
+      lp -= 0.5f * (ba * ba + bd * bd);
       if (ln.active) {
-        *ln.g(o.mean[i] + j) = fmaf(-z, 5.0f, a_mu[i]);
-        *ln.g(o.log_std[i] + j) = fmaf(-sig[i], sig[i], 1.0f) + a_ls[i];
+        *ln.g(o.beta_a + k) = sa - ba;
+        *ln.g(o.beta_d + k) = sd - bd;
       }
     }
-  }
-  if (warp == (W > 1 ? 1 : 0)) {  // corr_coef_raw ~ Uniform(0,1): Jacobian only; corr_coef = LB + r (UB - LB)
+    // corr_coef_raw ~ Uniform(0,1): Jacobian only; corr_coef = LB + r (UB - LB)
     lp += logf(r) + logf(1.0f - r);
     if (ln.active) {
       *ln.g(o.raw) = (1.0f - 2.0f * r) + gc * r * (1.0f - r) * (UB - LB);
       if (kp.corr_coef) kp.corr_coef[chain] = cc;
     }
   }
-  red_gc[warp * 32 + lane] = lp + lp_acc;  // every warp read its gc sum two barriers ago: the rows are free
+  red_lp[warp * 32 + lane] = lp + lp_acc;
   __syncthreads();
   if (warp == 0 && ln.active) {
     lp = kp.const_term;
-    for (int w = 0; w < W; w++) lp += red_gc[w * 32 + lane];
+    for (int w = 0; w < W; w++) lp += red_lp[w * 32 + lane];
     // a log-density is never +inf: that is an intermediate that overflowed float32 far from the typical set (a sampler
     // would accept such a point as the best ever seen); NaN is what the callers reject
     kp.lp[chain] = lp == INFINITY ? NAN : lp;

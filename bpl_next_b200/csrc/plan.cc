@@ -156,6 +156,7 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err, int 
   // ---- scalar hyper-parameter sites and every theta-independent constant --------
   const double kLogSqrt2Pi = 0.91893853320467274178, kLog2 = 0.69314718055994530942;
   double const_term = 0.0;
+  double const_lik = 0.0;  // the likelihood's own constant: -sum w (lgamma(yh+1) + lgamma(ya+1))
   {
     int n = 0;
     auto normal = [&](int off, int row, double loc, double scale) {
@@ -254,6 +255,7 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err, int 
     const double w = d.weights ? (double)d.weights[m] : 1.0;
     const int yh = d.home_goals[m], ya = d.away_goals[m];
     const_term -= w * (std::lgamma(yh + 1.0) + std::lgamma(ya + 1.0));
+    const_lik -= w * (std::lgamma(yh + 1.0) + std::lgamma(ya + 1.0));
     const int kh = nv ? kH0 : kH1, ka = nv ? kA0 : kA1;
     // X/Y meaning per kind: H1, A1, A0: X = lambda_h, Y = lambda_a.  H0: X = lambda_a, Y = lambda_h.
     RawEntry eh{(uint32_t)av, 0, w, nv ? w * ya : w * yh, nv ? w * yh : w * ya};
@@ -289,6 +291,37 @@ int build_plan(const bplx_problem_desc& d, HostPlan* out, std::string* err, int 
   }
   kp.w11 = (float)w11;
   kp.const_term = (float)const_term;
+  {  // likelihood-only view (bplx_loglik_fwdbwd): the sites the reference's rates read, as named by its `fit` attributes
+    ThetaOffsets z;
+    memset(&z, 0xff, sizeof z);
+    int dd = 0;
+    std::string& ls = P.lik_layout;
+    auto vec = [&](const char* n, int cnt) {
+      add_site(&ls, n, dd, cnt, "real");
+      const int r0 = dd;
+      dd += cnt;
+      return r0;
+    };
+    z.za = vec("attack", T);
+    z.zd = vec("defence", T);
+    int nh = 0;
+    if (model == BPLX_DIXON_COLES) {
+      z.mean[0] = vec("home_advantage", 1);
+      P.lik_hyper[nh++] = HyperDesc{z.mean[0], 4, 2, 0.0f, 1.0f};
+    } else if (model == BPLX_EXTENDED) {
+      z.dec[0] = vec("home_advantage", T);
+    } else {
+      static const char* nm[4] = {"home_attack", "away_attack", "home_defence", "away_defence"};
+      for (int i = 0; i < 4; i++) z.dec[i] = vec(nm[i], T);
+    }
+    if (wc) z.conf = vec("confederation_strength", Cf);
+    add_site(&ls, "corr_coef_raw", dd, 1, "unit");
+    z.raw = dd++;
+    P.lik_off = z;
+    P.lik_nhyper = nh;
+    P.lik_D = dd;
+    P.lik_const = (float)const_lik;
+  }
   P.yexp.resize(yexp.size());
   for (size_t i = 0; i < yexp.size(); i++) P.yexp[i] = (float)yexp[i];
   {  // the same static sums folded per team / per confederation

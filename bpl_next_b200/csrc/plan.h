@@ -23,6 +23,7 @@
 //                    Y = own'.y * opp.y, where own' is the own row (swapped for the neutral kinds).
 //   entry          : (byte offset of the opponent row, weight); identical (list, opponent) pairs
 //                    are merged with summed weights.
+//   (DYNAMIC: the streams are organised by gameweek instead -- see plan_dynamic.inc.)
 //   stream         : what a warp reads in one phase: its lists back to back, fetched stage by stage
 //                    (stage_bytes each) through the warp's TMA ring.  A list is stored as pieces, each
 //                    a 16-byte ListHdr followed by its entries (a multiple of 16 bytes); a piece never
@@ -46,7 +47,7 @@ constexpr int kChains = 32;       // chains per CTA: one lane per chain
 constexpr int kRowBytes = 256;    // one table row: float2 x 32 lanes
 constexpr int kMaxCov = 16;       // covariates supported by the kernel
 constexpr int kMaxWarps = 24;     // warps per CTA (register budget: 65536 / (24*32) = 85 per thread)
-constexpr int kMaxWarpsDyn = 16;  // DYNAMIC kernel: 128 registers per thread
+constexpr int kMaxWarpsDyn = 20;  // DYNAMIC kernel: one team (or a few) per warp, 102 registers per thread
 constexpr int kStages = 2;        // ring depth per warp (stage size: KernelParams::stage_bytes, 512 or 1024)
 constexpr int kAccRows = 13;      // hyper accumulators: lp, mu_d, ls_a, ls_d, mu[4], ls[4], rho
 constexpr int kPartRows = 16;     // rows per warp in the final cross-warp reduction
@@ -59,7 +60,9 @@ enum Exponent : int { eAh1 = 0, eBh1 = 1, eBa1 = 2, eAa1 = 3, eA0 = 4, eB0 = 5 }
 constexpr uint8_t kTeamFirst = 1;  // first piece of its team in this warp's stream: clear the accumulators
 constexpr uint8_t kTeamLast = 2;   // last one: write the team's raw slots
 constexpr uint8_t kVteamLast = 4;  // last piece of its virtual team: write the confederation scratch
-constexpr uint8_t kGwFirst = 8;    // DYNAMIC: marker piece (no entries) in front of a gameweek: rebuild the warp's tables
+constexpr uint8_t kGwFirst = 8;    // DYNAMIC: marker piece (no entries) in front of a warp's pieces of one gameweek; n0 = how many follow
+constexpr uint8_t kStageEnd = 16;  // DYNAMIC: filler -- the rest of this stage holds nothing
+constexpr uint8_t kPhase2 = 32;    // DYNAMIC (backward stream): tau piece (n0 / n1 / n2 classes); else a rate piece (n0 entries)
 
 // phase-1 entry (plain) and phase-2 entry: 8 bytes
 struct Entry {
@@ -104,7 +107,7 @@ struct ThetaOffsets {
 struct HyperDesc {
   int off;   // offset in theta
   int row;   // accumulator row holding the likelihood part of its gradient
-  int kind;  // 0 = normal, 1 = half-normal on exp(theta) (+ Jacobian)
+  int kind;  // 0 = normal, 1 = half-normal on exp(theta) (+ Jacobian), 2 = no prior (likelihood-only entry point)
   float loc, inv_scale;
 };
 
@@ -122,6 +125,8 @@ struct KernelParams {
   int D, nwarps;
   int ndec;        // decentred per-team venue sites: 0 (DC), 1 (EXT), 4 (NEU, WC)
   int clip;        // Extended: rates clipped at 15
+  int lik_only;    // bplx_loglik_fwdbwd: the inputs are the CONSTRAINED per-team tables (attack, defence, venue effects,
+                   // confederation strengths, corr_coef_raw in (0,1)); likelihood + tau only, no priors, no Jacobians
   int has1, has0;  // venue classes present
   uint32_t tabP1, tabQ1, tabP0;  // byte offsets of the tables (row V of each = zero row)
   uint32_t tab_bytes;            // table area (reused by the epilogue); DYNAMIC: per-warp table bytes
@@ -133,6 +138,8 @@ struct KernelParams {
   uint32_t smem_red_cl;          // [kMaxSplit][32] d/d corr_coef partials of a cluster (rank 0)
   uint32_t smem_p2;              // 0, or [2 sides][T][2 + ndec][32] f32: phase-2 slot sums when the split-1 plan deals a
                                  // team's home-side and away-side tau lists to different warps (small T, one CTA)
+  uint32_t dyn_state, dyn_part, dyn_hyp;  // DYNAMIC: [T][2][32] f32 walk state, [2][W][10][32] f32 hyper partials, [2][10][32] f32
+  int dyn_nbuf;                           // DYNAMIC: table buffers (2: gameweek j+1 is built while j is still read)
   int split_hint;                // largest cluster size worth using (small plans are latency-bound: 1)
   int force_clip_forms;          // testing (env BPLX_CLIP_FORMS at create): bit 0 / bit 1 = phase 1 / phase 2 always take the
                                  // clipping form of the arithmetic, even when no rate of the chains is near the clip
@@ -177,6 +184,13 @@ struct SplitStreams {  // the two phases' streams for nwarps * split virtual war
 
 struct HostPlan {
   KernelParams kp{};  // scalar fields filled; pointers null
+  // the likelihood-only view of the same plan (static models): input layout [attack T | defence T | venue effects
+  // ndec x T (DIXON_COLES: home_advantage, 1) | confederation strengths Cf | corr_coef_raw], see bplx_loglik_fwdbwd
+  ThetaOffsets lik_off{};
+  HyperDesc lik_hyper[12]{};
+  int lik_nhyper = 0, lik_D = 0;
+  float lik_const = 0.0f;
+  std::string lik_layout;
   std::vector<unsigned char> stream1, stream2;  // split 1
   std::vector<uint32_t> warp_b1, warp_b2;
   SplitStreams more[kNumSplits - 1];            // splits 2, 4, 8 (empty for DYNAMIC)

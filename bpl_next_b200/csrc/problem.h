@@ -11,6 +11,12 @@ struct bplx_problem {
   int device = 0;
   bplx::KernelParams kp{};  // static part filled at create; call arguments filled per launch
   std::string layout;
+  // likelihood-only view of the same plan (bplx_loglik_fwdbwd): offsets / sites of the packed per-team tables
+  bplx::ThetaOffsets lik_off{};
+  bplx::HyperDesc lik_hyper[12]{};
+  int lik_nhyper = 0, lik_D = 0;
+  float lik_const = 0.0f;
+  std::string lik_layout;
   // streams per split (1, 2, 4, 8 CTAs per chain group) and how many clusters of each size the device can hold at once
   const unsigned char* s1[bplx::kNumSplits] = {};
   const unsigned char* s2[bplx::kNumSplits] = {};

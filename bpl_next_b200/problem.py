@@ -95,6 +95,30 @@ class Problem:
             _dptr(ws), 0 if ws is None else ws.numel(), _stream_ptr(stream)))
         return lp, grad, corr_coef
 
+    # ---- likelihood-only entry (what a numpyro model that keeps its prior sites hands to numpyro.factor) -------
+    @property
+    def loglik_layout(self) -> Dict[str, Tuple[int, int, str]]:
+        return self._parse_layout(self._lib.bplx_loglik_layout(self._h).decode())
+
+    def loglik(self, tables: torch.Tensor, chain_minor: bool = False, stream=None):
+        """``tables``: the constrained per-team tables packed per ``loglik_layout`` (``[C, Dl]`` or ``[Dl, C]``).
+        Returns ``(loglik [C], grad (like tables), corr_coef [C])``: Poisson + tau terms only, no priors."""
+        assert tables.is_cuda and tables.dtype == torch.float32 and tables.is_contiguous()
+        Dl = int(self._lib.bplx_loglik_num_inputs(self._h))
+        if Dl < 0:
+            _abi.check(Dl)
+        Cn = tables.shape[1] if chain_minor else tables.shape[0]
+        if (tables.shape[0] if chain_minor else tables.shape[1]) != Dl:
+            raise ValueError(f"tables have {tables.shape} entries, the likelihood takes {Dl} per chain")
+        ll = torch.empty(Cn, dtype=torch.float32, device=tables.device)
+        grad = torch.empty_like(tables)
+        cc = torch.empty(Cn, dtype=torch.float32, device=tables.device)
+        ws = self.workspace(Cn)
+        _abi.check(self._lib.bplx_loglik_fwdbwd(
+            self._h, Cn, _abi.CHAIN_MINOR if chain_minor else _abi.CHAIN_MAJOR, 0, _dptr(tables), _dptr(ll),
+            _dptr(grad), _dptr(cc), _dptr(ws), 0 if ws is None else ws.numel(), _stream_ptr(stream)))
+        return ll, grad, cc
+
     # ---- host path (the reference-facing call: numpy in, numpy out) --------------------------------
     def logdensity_host(self, theta: np.ndarray, lp=None, grad=None, corr_coef=None):
         theta = np.ascontiguousarray(theta, dtype=np.float32)

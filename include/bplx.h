@@ -129,6 +129,26 @@ int bplx_logdensity_fwdbwd(const bplx_problem* p, int num_chains, int layout, in
                            void* workspace, size_t workspace_bytes,
                            void* stream);
 
+/*
+ * Likelihood-only entry point: what a numpyro `_model` that KEEPS its prior sites hands to `numpyro.factor`
+ * (bpl/dixon_coles.py:79-84; it replaces the rates -> Poisson -> tau block, e.g. bpl/neutral_dixon_coles_WC.py:188-232).
+ * Input per chain: the CONSTRAINED per-team tables packed as bplx_loglik_layout() says
+ *     attack[T] | defence[T] | home_advantage[1 or T]  or  home_attack, away_attack, home_defence, away_defence [T each]
+ *     | confederation_strength[Cf] | corr_coef_raw (in (0,1))
+ * Output: loglik[C] = sum_m w (Poisson log-pmfs) + sum_m w log tau, corr_coef[C] (the deterministic site), and
+ * grad = d loglik / d (every input), same layout as the input -- the cotangent a jax.custom_vjp multiplies through.
+ * No priors, no transforms, no Jacobians: those stay numpyro's.  Same launch / workspace rules as
+ * bplx_logdensity_fwdbwd (bplx_logdensity_workspace_bytes gives the workspace).  DYNAMIC: BPLX_E_UNSUPPORTED.
+ */
+int bplx_loglik_num_inputs(const bplx_problem* p);
+const char* bplx_loglik_layout(const bplx_problem* p); /* "name:offset:count:real;" records, "unit" for corr_coef_raw */
+int bplx_loglik_fwdbwd(const bplx_problem* p, int num_chains, int layout, int ld,
+                       const float* tables,  /* device, [C, Dl] or [Dl, ld], Dl = bplx_loglik_num_inputs */
+                       float* loglik,        /* device, [C] */
+                       float* grad,          /* device, same layout as tables */
+                       float* corr_coef,     /* device, [C], may be NULL */
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* host-buffer variant (chain-major [C, D]); copies in/out inside the call, returns when done.  Page-locked (pinned)
  * arrays are copied by DMA without staging, and lp / corr_coef are then written by the kernel straight into them. */
 int bplx_logdensity_fwdbwd_host(bplx_problem* p, int num_chains,

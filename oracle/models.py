@@ -500,3 +500,36 @@ def log_density_and_grad(d: MatchData, theta, dtype=torch.float64):
     lp, det = log_density(d, th)
     (g,) = torch.autograd.grad(lp.sum(), th)
     return lp.detach().numpy(), g.numpy(), det["corr_coef"].detach().numpy()
+
+
+# --------------------------------------------------------------------------------------
+# likelihood-only view: what the reference's `_model`s compute from the CONSTRAINED per-team tables
+# (checker of bplx_loglik_fwdbwd, the numpyro.factor / custom_vjp route of SURVEY.md 8(b))
+# --------------------------------------------------------------------------------------
+def likelihood_from_tables(d: MatchData, t: Dict[str, torch.Tensor]):
+    """Rates -> Poisson terms -> tau terms from per-team tables ``[..., T]`` (``home_advantage`` ``[...]`` for
+    DixonColes), ``confederation_strength [..., Cf]`` and ``corr_coef_raw [...]`` in (0, 1):
+    ``dixon_coles.py:63-84``, ``extended_dixon_coles.py:191-246``, ``neutral_dixon_coles.py:236-283``,
+    ``neutral_dixon_coles_WC.py:188-232``.  Returns (loglik [...], corr_coef [...])."""
+    h, a = _idx(d.home_team), _idx(d.away_team)
+    att, dfn = t["attack"], t["defence"]
+    dt = att.dtype
+    if d.model == "dixon_coles":
+        lam_h = torch.exp(att[..., h] - dfn[..., a] + t["home_advantage"][..., None])
+        lam_a = torch.exp(att[..., a] - dfn[..., h])
+    elif d.model == "extended":
+        lam_h = torch.clamp(torch.exp(att[..., h] - dfn[..., a] + t["home_advantage"][..., h]), max=15.0)
+        lam_a = torch.clamp(torch.exp(att[..., a] - dfn[..., h]), max=15.0)
+    elif d.model in ("neutral", "neutral_wc"):
+        n = torch.as_tensor(1 - np.asarray(d.neutral_venue, dtype=np.int64), dtype=dt)
+        eta_h = att[..., h] - dfn[..., a] + n * t["home_attack"][..., h] - n * t["away_defence"][..., a]
+        eta_a = att[..., a] - dfn[..., h] + n * t["away_attack"][..., a] - n * t["home_defence"][..., h]
+        if d.model == "neutral_wc":
+            conf = t["confederation_strength"]
+            hc, ac = _idx(d.home_conf), _idx(d.away_conf)
+            eta_h = eta_h + conf[..., hc] - conf[..., ac]
+            eta_a = eta_a + conf[..., ac] - conf[..., hc]
+        lam_h, lam_a = torch.exp(eta_h), torch.exp(eta_a)
+    else:
+        raise ValueError(d.model)
+    return _likelihood(d, lam_h, lam_a, t["corr_coef_raw"], dt)

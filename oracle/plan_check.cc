@@ -54,39 +54,44 @@ const ListHdr* hdr_at(const std::vector<unsigned char>& S, size_t off) {
 
 
 // ---- DYNAMIC: the same walk as logdensity_dynamic.cu, one chain, double precision ----------------------------
+// forward pass (gameweeks ascending: walk prefix, tables, home-list maxima) -> bounds -> backward pass (gameweeks
+// descending: tables, every (gameweek, team) completed in one visit, arg-max search) -> linear fix-up corrections.
 namespace {
+struct DynReader {  // pieces of one warp's stream, stage by stage (pieces never straddle a stage)
+  const std::vector<unsigned char>& S;
+  size_t begin, end, pos;
+  uint32_t stage;
+  DynReader(const std::vector<unsigned char>& s, size_t b, size_t e, uint32_t st) : S(s), begin(b), end(e), pos(b), stage(st) {}
+  // returns the next real header (skipping fillers); nullptr at the end of the stream
+  const ListHdr* next(size_t* hoff) {
+    for (;;) {
+      if (pos + sizeof(ListHdr) > end) return nullptr;
+      const ListHdr* L = hdr_at(S, pos);
+      if (L->flags & kStageEnd) {
+        pos = begin + ((pos - begin) / stage + 1) * stage;
+        continue;
+      }
+      *hoff = pos;
+      pos += sizeof(ListHdr);
+      return L;
+    }
+  }
+};
+
 int eval_dynamic(const HostPlan& P, const double* theta, double* lp_out, double* grad, double* corr_out) {
   const KernelParams& kp = P.kp;
   const ThetaOffsets& o = kp.off;
-  const int T = kp.T, K = kp.K, G = kp.G, D = kp.D;
+  const int T = kp.T, K = kp.K, G = kp.G, D = kp.D, W = kp.nwarps;
   for (int i = 0; i < D; i++) grad[i] = 0.0;
   double lp = 0;
   const double mu_d = theta[o.mean_defence];
-  // prefix pass
-  std::vector<double> att((size_t)G * T), def((size_t)G * T);
-  for (int t = 0; t < T; t++) {
-    double a = 0, d = mu_d;
-    for (int k = 0; k < K; k++) {
-      a += P.Xs[(size_t)t * K + k] * theta[o.beta_a + k];
-      d += P.Xs[(size_t)t * K + k] * theta[o.beta_d + k];
-    }
-    for (int j = 0; j < G; j++) {
-      const int jt = j * T + t;
-      if (kp.as_written) {
-        a = d = 0;
-      } else {
-        a += theta[o.za + jt] * std::exp(theta[o.log_std_attack + j]);
-        d += theta[o.zd + jt] * std::exp(theta[o.log_std_defence + j]);
-      }
-      att[jt] = a;
-      def[jt] = d;
-    }
-  }
   std::vector<Row> tab(kp.tab_bytes / kRowBytes + 4, Row{0, 0});
   auto row = [&](uint32_t off) -> Row& { return tab[off / kRowBytes]; };
+  std::vector<double> att((size_t)G * T, 0.0), def((size_t)G * T, 0.0);  // the kernel's workspace
   auto build = [&](int j, bool with_lp) {
-    for (int idx = P.gw_tptr[j]; idx < P.gw_tptr[j + 1]; idx++) {
-      const int t = P.gw_tlist[idx], jt = j * T + t;
+    for (int t = 0; t < T; t++) {
+      const int jt = j * T + t;
+      if (!(P.team_flags[jt] & 1)) continue;
       double x[4];
       for (int i = 0; i < 4; i++) x[i] = theta[o.mean[i] + j] + std::exp(theta[o.log_std[i] + j]) * theta[o.dec[i] + jt];
       double ex[6];
@@ -105,78 +110,79 @@ int eval_dynamic(const HostPlan& P, const double* theta, double* lp_out, double*
         for (int e = 0; e < 6; e++) lp += P.yexp[(size_t)jt * 6 + e] * ex[e];
     }
   };
-  // raw slots per (gameweek, team): att, def, x[4]
-  std::vector<double> R((size_t)G * T * 6, 0.0);
-  auto put = [&](int jt, const double g[6]) {
-    double* r = &R[(size_t)jt * 6];
-    r[0] += g[eAh1] + g[eAa1] + g[eA0];
-    r[1] -= g[eBh1] + g[eBa1] + g[eB0];
-    r[2] += g[eAh1];
-    r[3] += g[eAa1];
-    r[4] -= g[eBh1];
-    r[5] -= g[eBa1];
-  };
+  // ---- forward pass ------------------------------------------------------------------------------------------
+  {
+    std::vector<double> a(T), d(T);
+    for (int t = 0; t < T; t++) {
+      a[t] = 0;
+      d[t] = mu_d;
+      for (int k = 0; k < K; k++) {
+        a[t] += P.Xs[(size_t)t * K + k] * theta[o.beta_a + k];
+        d[t] += P.Xs[(size_t)t * K + k] * theta[o.beta_d + k];
+      }
+    }
+    for (int j = 0; j < G; j++)
+      for (int t = 0; t < T; t++) {
+        const int jt = j * T + t;
+        if (!kp.as_written) {
+          a[t] += theta[o.za + jt] * std::exp(theta[o.log_std_attack + j]);
+          d[t] += theta[o.zd + jt] * std::exp(theta[o.log_std_defence + j]);
+          att[jt] = a[t];
+          def[jt] = d[t];
+        }
+      }
+  }
   double best[3] = {0, 0, 0};
   size_t best_hdr[3] = {0, 0, 0};
-  std::vector<int> seen(G, 0);
-  for (int w = 0; w < kp.nwarps; w++) {
-    size_t pos = P.warp_b1[w];
-    const size_t end = P.warp_b1[w + 1];
-    int cur = -1;
-    while (pos < end) {
-      const size_t hoff = pos;
-      const ListHdr& L = *hdr_at(P.stream1, pos);
-      pos += sizeof(ListHdr);
-      if (L.flags & kGwFirst) {
-        cur = L.vteam;
-        if (seen[cur]++) return -130;
-        build(cur, true);
+  {
+    std::vector<DynReader> rd;
+    for (int w = 0; w < W; w++) rd.emplace_back(P.stream1, P.warp_b1[w], P.warp_b1[w + 1], kp.stage_bytes);
+    for (int j = 0; j < G; j++) {
+      build(j, false);
+      for (int w = 0; w < W; w++) {
+        size_t hoff;
+        const ListHdr* Mk = rd[w].next(&hoff);
+        if (!Mk || !(Mk->flags & kGwFirst) || Mk->vteam != j) return -130;
+        for (int p = 0; p < Mk->n0; p++) {
+          const ListHdr* L = rd[w].next(&hoff);
+          if (!L || (L->flags & (kGwFirst | kPhase2)) || L->vteam != j || (L->n0 & 1)) return -131;
+          if (!(L->kind == kH1 || L->kind == kH0) || (int)(L->team % W) != w) return -132;
+          if ((hoff - rd[w].begin) / kp.stage_bytes != (rd[w].pos + L->n0 * sizeof(Entry) - 1 - rd[w].begin) / kp.stage_bytes)
+            return -135;  // a piece straddles a stage
+          Row own = row(L->own_off);
+          if (L->kind >= kH0) std::swap(own.x, own.y);
+          double m1 = 0, m2 = 0, m3 = 0;
+          for (uint32_t i = 0; i < L->n0; i++, rd[w].pos += sizeof(Entry)) {
+            const Entry& e = *reinterpret_cast<const Entry*>(&P.stream1[rd[w].pos]);
+            const Row& op = row(e.off);
+            m1 = std::max(m1, op.x);
+            m2 = std::max(m2, op.y);
+            m3 = std::max(m3, op.x * op.y);
+          }
+          const double v[3] = {own.x * m1, own.y * m2, own.x * own.y * m3};
+          for (int q = 0; q < 3; q++)
+            if (v[q] > best[q] || (v[q] == best[q] && v[q] > 0 && hoff > best_hdr[q])) best[q] = v[q], best_hdr[q] = hoff;
+        }
       }
-      if (L.team == 0xffff) {
-        if (L.n0 | L.n1 | L.n2) return -131;
-        continue;
-      }
-      if ((int)L.vteam != cur || (L.n0 & 1)) return -132;
-      Row own = row(L.own_off);
-      if (L.kind >= kH0) std::swap(own.x, own.y);
-      const bool home = L.kind == kH1 || L.kind == kH0;
-      double ax = 0, ay = 0, m1 = 0, m2 = 0, m3 = 0;
-      for (uint32_t i = 0; i < L.n0; i++, pos += sizeof(Entry)) {
-        const Entry& e = *reinterpret_cast<const Entry*>(&P.stream1[pos]);
-        const Row& op = row(e.off);
-        ax += e.w * op.x;
-        ay += e.w * op.y;
-        m1 = std::max(m1, op.x);
-        m2 = std::max(m2, op.y);
-        m3 = std::max(m3, op.x * op.y);
-      }
-      const double SX = own.x * ax, SY = own.y * ay;
-      lp -= 0.5 * (SX + SY);
-      if (home) {
-        const double v[3] = {own.x * m1, own.y * m2, own.x * own.y * m3};
-        for (int q = 0; q < 3; q++)
-          if (v[q] > best[q]) best[q] = v[q], best_hdr[q] = hoff;
-      }
-      double gl[6] = {0, 0, 0, 0, 0, 0};
-      gl[kOwnX[L.kind]] -= SX;
-      gl[kOwnY[L.kind]] -= SY;
-      put((int)L.vteam * T + L.team, gl);
     }
-    if (pos != end) return -133;
+    for (int w = 0; w < W; w++) {
+      size_t hoff;
+      if (rd[w].next(&hoff) != nullptr) return -133;
+    }
   }
-  for (int j = 0; j < G; j++)
-    if (seen[j] != 1) return -134;
   const double Lam = std::max(best[0], best[1]);
   const double LB = -1.0 / Lam, UB = std::min(1.0 / best[2], 1.0);
   const double r = 1.0 / (1.0 + std::exp(-theta[o.raw]));
   const double cc = LB + r * (UB - LB);
   *corr_out = cc;
-  // arg-max matches: (gameweek, own team, opp team, kind)
+  const int qlam = best[0] >= best[1] ? 0 : 1;
   struct Hit { int j, own, opp, kind; bool ok; };
-  auto find = [&](int q) {
-    Hit h{0, 0, 0, 0, false};
+  Hit hit[2] = {{0, 0, 0, 0, false}, {0, 0, 0, 0, false}};
+  const int want_gw[2] = {(int)hdr_at(P.stream1, best_hdr[qlam])->vteam,
+                          best[2] > 1.0 ? (int)hdr_at(P.stream1, best_hdr[2])->vteam : -1};
+  auto find = [&](int which) {  // with the tables of the arg-max piece's gameweek resident
+    const int q = which == 0 ? qlam : 2;
     const ListHdr& L = *hdr_at(P.stream1, best_hdr[q]);
-    build(L.vteam, false);
     Row own = row(L.own_off);
     if (L.kind >= kH0) std::swap(own.x, own.y);
     for (uint32_t i = 0; i < L.n0; i++) {
@@ -184,153 +190,214 @@ int eval_dynamic(const HostPlan& P, const double* theta, double* lp_out, double*
       const Row& op = row(off);
       const double val = q == 0 ? own.x * op.x : q == 1 ? own.y * op.y : own.x * own.y * (op.x * op.y);
       if (val == best[q]) {
-        h = Hit{L.vteam, L.team, (int)((off - (L.kind == kH1 ? kp.tabQ1 : kp.tabP0)) / kRowBytes), L.kind, true};
+        hit[which] = Hit{L.vteam, L.team, (int)((off - (L.kind == kH1 ? kp.tabQ1 : kp.tabP0)) / kRowBytes), L.kind, true};
         break;
       }
     }
-    return h;
   };
-  const int qlam = best[0] >= best[1] ? 0 : 1;
-  const Hit hit0 = find(qlam);
-  Hit hit1{0, 0, 0, 0, false};
-  if (best[2] > 1.0) hit1 = find(2);
-  if (!hit0.ok || (best[2] > 1.0 && !hit1.ok)) return -100;
-  // phase 2
+  // ---- backward pass ---------------------------------------------------------------------------------------------
   double Gc = 0;
-  for (int w = 0; w < kp.nwarps; w++) {
-    size_t pos = P.warp_b2[w];
-    const size_t end = P.warp_b2[w + 1];
-    while (pos < end) {
-      const ListHdr& L = *hdr_at(P.stream2, pos);
-      pos += sizeof(ListHdr);
-      if (L.flags & kGwFirst) build(L.vteam, false);
-      if (L.team == 0xffff) continue;
-      if ((L.n0 | L.n1 | L.n2) & 1) return -120;
-      Row own = row(L.own_off);
-      if (L.kind >= kH0) std::swap(own.x, own.y);
-      const bool home = L.kind == kH1 || L.kind == kH0;
-      double gx = 0, gy = 0, lt = 0, dG = 0;
-      const uint32_t n[3] = {L.n0, L.n1, L.n2};
-      for (int cls = 0; cls < 3; cls++)
-        for (uint32_t k = 0; k < n[cls]; k++, pos += sizeof(Entry)) {
-          const Entry& e = *reinterpret_cast<const Entry*>(&P.stream2[pos]);
-          if (e.w == 0.0f) continue;
-          const Row& op = row(e.off);
-          const double X = own.x * op.x, Y = own.y * op.y;
-          if (cls == 0) {
-            const double tau = 1.0 - cc * X * Y, q = e.w * X * Y / tau;
-            lt += e.w * std::log(tau);
-            dG -= q;
-            gx -= cc * q;
-            gy -= cc * q;
-          } else if (cls == 1) {
-            const double tau = 1.0 + cc * X, q = e.w * X / tau;
-            lt += e.w * std::log(tau);
-            dG += q;
-            gx += cc * q;
+  std::vector<double> s_att(T, 0.0), s_def(T, 0.0);
+  std::vector<int> visited((size_t)G * T, 0);
+  {
+    std::vector<DynReader> rd;
+    for (int w = 0; w < W; w++) rd.emplace_back(P.stream2, P.warp_b2[w], P.warp_b2[w + 1], kp.stage_bytes);
+    for (int j = G - 1; j >= 0; j--) {
+      build(j, true);
+      for (int which = 0; which < 2; which++)
+        if (want_gw[which] == j) find(which);
+      const double sig_a = std::exp(theta[o.log_std_attack + j]), sig_d = std::exp(theta[o.log_std_defence + j]);
+      double a_ls_a = 0, a_ls_d = 0, a_mu[4] = {0, 0, 0, 0}, a_ls[4] = {0, 0, 0, 0}, sig[4];
+      for (int i = 0; i < 4; i++) sig[i] = std::exp(theta[o.log_std[i] + j]);
+      for (int w = 0; w < W; w++) {
+        size_t hoff;
+        const ListHdr* Mk = rd[w].next(&hoff);
+        if (!Mk || !(Mk->flags & kGwFirst) || Mk->vteam != j) return -120;
+        double g[6] = {0, 0, 0, 0, 0, 0};
+        int cur_team = -1;
+        for (int p = 0; p < Mk->n0; p++) {
+          const ListHdr* L = rd[w].next(&hoff);
+          if (!L || (L->flags & kGwFirst) || L->vteam != j || ((L->n0 | L->n1 | L->n2) & 1)) return -121;
+          if ((int)(L->team % W) != w) return -122;
+          if (L->flags & kTeamFirst) {
+            if (cur_team != -1) return -123;
+            cur_team = L->team;
+            for (int e = 0; e < 6; e++) g[e] = 0;
+          }
+          if (cur_team != (int)L->team) return -124;
+          const size_t nent = (size_t)L->n0 + ((L->flags & kPhase2) ? L->n1 + L->n2 : 0);
+          if (!(L->flags & kPhase2) && (L->n1 | L->n2)) return -125;
+          if (nent && (hoff - rd[w].begin) / kp.stage_bytes != (rd[w].pos + nent * sizeof(Entry) - 1 - rd[w].begin) / kp.stage_bytes)
+            return -126;
+          Row own = row(L->own_off);
+          if (L->kind >= kH0) std::swap(own.x, own.y);
+          const bool home = L->kind == kH1 || L->kind == kH0;
+          double gl[6] = {0, 0, 0, 0, 0, 0};
+          if (!(L->flags & kPhase2)) {
+            double ax = 0, ay = 0;
+            for (uint32_t i = 0; i < L->n0; i++, rd[w].pos += sizeof(Entry)) {
+              const Entry& e = *reinterpret_cast<const Entry*>(&P.stream2[rd[w].pos]);
+              const Row& op = row(e.off);
+              ax += e.w * op.x;
+              ay += e.w * op.y;
+            }
+            const double SX = own.x * ax, SY = own.y * ay;
+            lp -= 0.5 * (SX + SY);
+            gl[kOwnX[L->kind]] -= SX;
+            gl[kOwnY[L->kind]] -= SY;
           } else {
-            const double tau = 1.0 + cc * Y, q = e.w * Y / tau;
-            lt += e.w * std::log(tau);
-            dG += q;
-            gy += cc * q;
+            double gx = 0, gy = 0, lt = 0, dG = 0;
+            const uint32_t n[3] = {L->n0, L->n1, L->n2};
+            for (int cls = 0; cls < 3; cls++)
+              for (uint32_t k = 0; k < n[cls]; k++, rd[w].pos += sizeof(Entry)) {
+                const Entry& e = *reinterpret_cast<const Entry*>(&P.stream2[rd[w].pos]);
+                if (e.w == 0.0f) continue;
+                if (cls == 0) {
+                  const Row& op = row(e.off);
+                  const double X = own.x * op.x, Y = own.y * op.y;
+                  const double tau = 1.0 - cc * X * Y, q = e.w * X * Y / tau;
+                  lt += e.w * std::log(tau);
+                  dG -= q;
+                  gx -= cc * q;
+                  gy -= cc * q;
+                } else if (cls == 1) {
+                  const double X = own.x * row(e.off).x;
+                  const double tau = 1.0 + cc * X, q = e.w * X / tau;
+                  lt += e.w * std::log(tau);
+                  dG += q;
+                  gx += cc * q;
+                } else {
+                  if ((e.off & 7u) != 4u) return -127;  // `off` addresses the .y float
+                  const double Y = own.y * row(e.off).y;
+                  const double tau = 1.0 + cc * Y, q = e.w * Y / tau;
+                  lt += e.w * std::log(tau);
+                  dG += q;
+                  gy += cc * q;
+                }
+              }
+            if (home) {
+              lp += lt;
+              Gc += dG;
+            }
+            gl[kOwnX[L->kind]] += gx;
+            gl[kOwnY[L->kind]] += gy;
+          }
+          for (int e = 0; e < 6; e++) g[e] += gl[e];
+          if (L->flags & kTeamLast) {  // complete (gameweek j, team t)
+            const int t = L->team, jt = j * T + t;
+            if (visited[jt]++) return -128;
+            const float* ys = &P.yteam[(size_t)jt * 8];
+            const double ra = g[eAh1] + g[eAa1] + g[eA0] + ys[0], rdd = -(g[eBh1] + g[eBa1] + g[eB0]) + ys[1];
+            const double rx[4] = {g[eAh1] + ys[2], g[eAa1] + ys[3], -g[eBh1] + ys[4], -g[eBa1] + ys[5]};
+            s_att[t] += ra;
+            s_def[t] += rdd;
+            const double sa = kp.as_written ? 0.0 : s_att[t], sd = kp.as_written ? 0.0 : s_def[t];
+            const double za = theta[o.za + jt], zd = theta[o.zd + jt];
+            const double u = 1.0 / (1.0 + std::exp(-theta[o.u + jt]));
+            const double rho = 2.0 * u - 1.0, s2 = 1.0 - rho * rho;
+            const double e = zd - rho * za;
+            lp += -0.5 * za * za - 0.5 * e * e / s2 - 0.5 * std::log(s2) + 2.0 * std::log(u) + 4.0 * std::log(1.0 - u);
+            const double a_rho = e * za / s2 - rho * e * e / (s2 * s2) + rho / s2;
+            grad[o.u + jt] = 2.0 - 6.0 * u + a_rho * 2.0 * u * (1.0 - u);
+            grad[o.za + jt] = -za + rho * e / s2 + sig_a * sa;
+            grad[o.zd + jt] = -e / s2 + sig_d * sd;
+            a_ls_a += sig_a * za * sa;
+            a_ls_d += sig_d * zd * sd;
+            for (int i = 0; i < 4; i++) {
+              const double dec = theta[o.dec[i] + jt];
+              lp -= 0.5 * dec * dec;
+              grad[o.dec[i] + jt] = -dec + sig[i] * rx[i];
+              a_mu[i] += rx[i];
+              a_ls[i] += sig[i] * dec * rx[i];
+            }
+            cur_team = -1;
           }
         }
-      if (home) {
-        lp += lt;
-        Gc += dG;
+        if (cur_team != -1) return -129;
       }
-      double gl[6] = {0, 0, 0, 0, 0, 0};
-      gl[kOwnX[L.kind]] += gx;
-      gl[kOwnY[L.kind]] += gy;
-      put((int)L.vteam * T + L.team, gl);
+      lp += -0.5 * sig_a * sig_a + theta[o.log_std_attack + j] - 0.5 * sig_d * sig_d + theta[o.log_std_defence + j];
+      grad[o.log_std_attack + j] = -sig_a * sig_a + 1.0 + a_ls_a;
+      grad[o.log_std_defence + j] = -sig_d * sig_d + 1.0 + a_ls_d;
+      for (int i = 0; i < 4; i++) {
+        const double z = (theta[o.mean[i] + j] - ((i & 1) ? -0.1 : 0.1)) * 5.0;
+        lp += -0.5 * z * z - 0.5 * sig[i] * sig[i] + theta[o.log_std[i] + j];
+        grad[o.mean[i] + j] = -z * 5.0 + a_mu[i];
+        grad[o.log_std[i] + j] = -sig[i] * sig[i] + 1.0 + a_ls[i];
+      }
     }
-    if (pos != end) return -121;
+    for (int w = 0; w < W; w++) {
+      size_t hoff;
+      if (rd[w].next(&hoff) != nullptr) return -136;
+    }
+    for (size_t i = 0; i < visited.size(); i++)
+      if (visited[i] != 1) return -137;
   }
+  if (!hit[0].ok || (best[2] > 1.0 && !hit[1].ok)) return -100;
   lp += kp.w11 * std::log(1.0 - cc);
   Gc -= kp.w11 / (1.0 - cc);
-  // fix-up
-  {
-    const double wgt = Gc * (1.0 - r) / Lam;
-    double g1[6] = {0}, g2[6] = {0};
-    g1[qlam == 0 ? kOwnX[hit0.kind] : kOwnY[hit0.kind]] = wgt;
-    g2[qlam == 0 ? kOppX[hit0.kind] : kOppY[hit0.kind]] = wgt;
-    put(hit0.j * T + hit0.own, g1);
-    put(hit0.j * T + hit0.opp, g2);
-  }
-  if (best[2] > 1.0) {
-    const double wgt = -Gc * r / best[2];
-    double g1[6] = {0}, g2[6] = {0};
-    g1[kOwnX[hit1.kind]] += wgt, g2[kOppX[hit1.kind]] += wgt;
-    g1[kOwnY[hit1.kind]] += wgt, g2[kOppY[hit1.kind]] += wgt;
-    put(hit1.j * T + hit1.own, g1);
-    put(hit1.j * T + hit1.opp, g2);
-  }
-  // suffix pass
-  for (int t = 0; t < T; t++) {
-    double sa = 0, sd = 0;
-    for (int j = G - 1; j >= 0; j--) {
-      const int jt = j * T + t;
-      double* rr = &R[(size_t)jt * 6];
-      for (int i = 0; i < 6; i++) rr[i] += P.yteam[(size_t)jt * 8 + i];
-      sa += rr[0];
-      sd += rr[1];
-      rr[0] = kp.as_written ? 0.0 : sa;
-      rr[1] = kp.as_written ? 0.0 : sd;
-    }
-  }
-  // gameweek pass
-  {
-    double s = 0;
-    for (int t = 0; t < T; t++) s += R[(size_t)t * 6 + 1];
-    lp -= 0.5 * mu_d * mu_d;
-    grad[o.mean_defence] = s - mu_d;
-    for (int k = 0; k < K; k++) {
-      double sa = 0, sd = 0;
-      for (int t = 0; t < T; t++) {
-        sa += P.Xs[(size_t)t * K + k] * R[(size_t)t * 6 + 0];
-        sd += P.Xs[(size_t)t * K + k] * R[(size_t)t * 6 + 1];
-      }
-      const double ba = theta[o.beta_a + k], bd = theta[o.beta_d + k];
-      lp -= 0.5 * (ba * ba + bd * bd);
-      grad[o.beta_a + k] = sa - ba;
-      grad[o.beta_d + k] = sd - bd;
-    }
-  }
-  for (int j = 0; j < G; j++) {
-    const double sig_a = std::exp(theta[o.log_std_attack + j]), sig_d = std::exp(theta[o.log_std_defence + j]);
-    double a_ls_a = 0, a_ls_d = 0, a_mu[4] = {0, 0, 0, 0}, a_ls[4] = {0, 0, 0, 0}, sig[4];
-    for (int i = 0; i < 4; i++) sig[i] = std::exp(theta[o.log_std[i] + j]);
+  // mean_defence, covariate coefficients: the whole walk's sums
+  double g_md = -mu_d;
+  lp -= 0.5 * mu_d * mu_d;
+  std::vector<double> g_ba(K, 0.0), g_bd(K, 0.0);
+  if (!kp.as_written)
     for (int t = 0; t < T; t++) {
-      const int jt = j * T + t;
-      const double* rr = &R[(size_t)jt * 6];
-      const double za = theta[o.za + jt], zd = theta[o.zd + jt];
-      const double u = 1.0 / (1.0 + std::exp(-theta[o.u + jt]));
-      const double rho = 2.0 * u - 1.0, s2 = 1.0 - rho * rho;
-      const double e = zd - rho * za;
-      lp += -0.5 * za * za - 0.5 * e * e / s2 - 0.5 * std::log(s2) + 2.0 * std::log(u) + 4.0 * std::log(1.0 - u);
-      const double a_rho = e * za / s2 - rho * e * e / (s2 * s2) + rho / s2;
-      grad[o.u + jt] = 2.0 - 6.0 * u + a_rho * 2.0 * u * (1.0 - u);
-      grad[o.za + jt] = -za + rho * e / s2 + sig_a * rr[0];
-      grad[o.zd + jt] = -e / s2 + sig_d * rr[1];
-      a_ls_a += sig_a * za * rr[0];
-      a_ls_d += sig_d * zd * rr[1];
-      for (int i = 0; i < 4; i++) {
-        const double dec = theta[o.dec[i] + jt];
-        lp -= 0.5 * dec * dec;
-        grad[o.dec[i] + jt] = -dec + sig[i] * rr[2 + i];
-        a_mu[i] += rr[2 + i];
-        a_ls[i] += sig[i] * dec * rr[2 + i];
+      g_md += s_def[t];
+      for (int k = 0; k < K; k++) {
+        g_ba[k] += P.Xs[(size_t)t * K + k] * s_att[t];
+        g_bd[k] += P.Xs[(size_t)t * K + k] * s_def[t];
       }
     }
-    lp += -0.5 * sig_a * sig_a + theta[o.log_std_attack + j] - 0.5 * sig_d * sig_d + theta[o.log_std_defence + j];
-    grad[o.log_std_attack + j] = -sig_a * sig_a + 1.0 + a_ls_a;
-    grad[o.log_std_defence + j] = -sig_d * sig_d + 1.0 + a_ls_d;
-    for (int i = 0; i < 4; i++) {
-      const double z = (theta[o.mean[i] + j] - ((i & 1) ? -0.1 : 0.1)) * 5.0;
-      lp += -0.5 * z * z - 0.5 * sig[i] * sig[i] + theta[o.log_std[i] + j];
-      grad[o.mean[i] + j] = -z * 5.0 + a_mu[i];
-      grad[o.log_std[i] + j] = -sig[i] * sig[i] + 1.0 + a_ls[i];
+  for (int k = 0; k < K; k++) {
+    const double ba = theta[o.beta_a + k], bd = theta[o.beta_d + k];
+    lp -= 0.5 * (ba * ba + bd * bd);
+    g_ba[k] -= ba;
+    g_bd[k] -= bd;
+  }
+  // ---- fix-up: d corr_coef / d eta of the arg-max matches, applied as a linear correction -----
+  for (int which = 0; which < 2; which++) {
+    if (!hit[which].ok) continue;
+    double vx, vy;
+    if (which == 0) {
+      const double wgt = Gc * (1.0 - r) / Lam;
+      vx = qlam == 0 ? wgt : 0.0;
+      vy = qlam == 1 ? wgt : 0.0;
+    } else {
+      vx = vy = -Gc * r / best[2];
     }
+    const Hit& H = hit[which];
+    for (int side = 0; side < 2; side++) {
+      double gl[6] = {0, 0, 0, 0, 0, 0};
+      gl[side == 0 ? kOwnX[H.kind] : kOppX[H.kind]] += vx;
+      gl[side == 0 ? kOwnY[H.kind] : kOppY[H.kind]] += vy;
+      const int t = side == 0 ? H.own : H.opp, js = H.j;
+      const double dra = gl[eAh1] + gl[eAa1] + gl[eA0], drd = -(gl[eBh1] + gl[eBa1] + gl[eB0]);
+      const double drx[4] = {gl[eAh1], gl[eAa1], -gl[eBh1], -gl[eBa1]};
+      for (int i = 0; i < 4; i++) {
+        const double sg = std::exp(theta[o.log_std[i] + js]);
+        grad[o.dec[i] + js * T + t] += sg * drx[i];
+        grad[o.mean[i] + js] += drx[i];
+        grad[o.log_std[i] + js] += sg * theta[o.dec[i] + js * T + t] * drx[i];
+      }
+      if (!kp.as_written) {
+        for (int j = 0; j <= js; j++) {
+          const double sa = std::exp(theta[o.log_std_attack + j]), sd = std::exp(theta[o.log_std_defence + j]);
+          grad[o.za + j * T + t] += sa * dra;
+          grad[o.zd + j * T + t] += sd * drd;
+          grad[o.log_std_attack + j] += sa * theta[o.za + j * T + t] * dra;
+          grad[o.log_std_defence + j] += sd * theta[o.zd + j * T + t] * drd;
+        }
+        g_md += drd;
+        for (int k = 0; k < K; k++) {
+          g_ba[k] += P.Xs[(size_t)t * K + k] * dra;
+          g_bd[k] += P.Xs[(size_t)t * K + k] * drd;
+        }
+      }
+    }
+  }
+  grad[o.mean_defence] = g_md;
+  for (int k = 0; k < K; k++) {
+    grad[o.beta_a + k] = g_ba[k];
+    grad[o.beta_d + k] = g_bd[k];
   }
   lp += std::log(r) + std::log(1.0 - r);  // Uniform(0,1): Jacobian only
   grad[o.raw] = (1.0 - 2.0 * r) + Gc * r * (1.0 - r) * (UB - LB);

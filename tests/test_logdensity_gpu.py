@@ -281,3 +281,40 @@ def test_host_path_with_page_locked_outputs():
     assert np.array_equal(lp.numpy(), lp0) and np.array_equal(gr.numpy(), g0) and np.array_equal(cc.numpy(), c0)
     _check(arr, theta.astype(np.float64), lp.numpy().copy(), gr.numpy().copy(), cc.numpy().copy())
     p.close()
+
+
+@pytest.mark.parametrize("model,kw", [("dixon_coles", dict()), ("extended", dict(weighted=True)),
+                                      ("neutral", dict()), ("neutral_wc", dict(multi_conf=True, T=13, M=400))])
+@pytest.mark.parametrize("chain_minor", [False, True])
+def test_likelihood_only_entry_point(model, kw, chain_minor):
+    """bplx_loglik_fwdbwd (the numpyro.factor route): constrained per-team tables in; Poisson + tau terms,
+    corr_coef and d loglik / d tables out -- against the oracle's restatement of the reference's rate / likelihood lines."""
+    import torch
+    from bpl_next_b200 import Problem
+
+    arr = H.small_problem(model, seed=6, **kw)
+    d = H.to_oracle(arr)
+    p = Problem(arr)
+    lay = p.loglik_layout
+    Dl = sum(c for _, c, _ in lay.values())
+    C = 45
+    rng = np.random.default_rng(12)
+    tabs = rng.normal(0, 0.5, (C, Dl))
+    o, c, _ = lay["corr_coef_raw"]
+    tabs[:, o] = rng.uniform(0.05, 0.95, C)
+    t32 = torch.from_numpy(tabs.astype(np.float32)).cuda()
+    if chain_minor:
+        t32 = t32.t().contiguous()
+    ll, grad, cc = p.loglik(t32, chain_minor=chain_minor)
+    torch.cuda.synchronize()
+    g = (grad.t() if chain_minor else grad).cpu().numpy()
+    # oracle: autograd through the restated likelihood
+    x = torch.tensor(tabs.astype(np.float32).astype(np.float64), requires_grad=True)
+    scalar_sites = ("corr_coef_raw",) + (("home_advantage",) if model == "dixon_coles" else ())
+    tab = {name: (x[:, off] if name in scalar_sites else x[:, off:off + cnt]) for name, (off, cnt, _) in lay.items()}
+    ll_o, cc_o = om.likelihood_from_tables(d, tab)
+    (g_o,) = torch.autograd.grad(ll_o.sum(), x)
+    np.testing.assert_allclose(ll.cpu().numpy(), ll_o.detach().numpy(), rtol=LP_RTOL)
+    np.testing.assert_allclose(cc.cpu().numpy(), cc_o.detach().numpy(), rtol=1e-4, atol=1e-6)
+    err = np.abs(g - g_o.numpy()) / np.abs(g_o.numpy()).max(axis=1, keepdims=True)
+    assert err.max() < GRAD_RTOL, err.max()

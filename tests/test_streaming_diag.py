@@ -59,8 +59,9 @@ def test_step_kernel_accumulators_match_their_specification():
             os.environ.pop("BPLX_NUTS_GENERIC", None)
             _abi.lib().bplx_reload_env()
         ref = dg.accumulate_reference(run.samples, 16)
-        for k in ("ref", "sums", "lag", "ring", "head"):
-            np.testing.assert_allclose(run.diag[k].cpu().numpy(), ref[k].cpu().numpy(), rtol=2e-5, atol=1e-5, err_msg=k)
+        for k in ("ref", "sums", "lag", "ring", "head"):  # float32 sums in draw order vs torch's pairwise sums
+            want = ref[k].cpu().numpy()
+            np.testing.assert_allclose(run.diag[k].cpu().numpy(), want, rtol=2e-5, atol=2e-6 * max(1.0, np.abs(want).max()), err_msg=k)
         s = dg.streaming_summary(run.diag)
         np.testing.assert_allclose(s["rhat"].cpu().numpy(), dg.split_rhat(run.samples).cpu().numpy(), atol=1e-5)
         if s["lag_window_hit"] == 0:
