@@ -89,6 +89,16 @@ __device__ __forceinline__ void diag_collect(const bplx_nuts_params& P, int k, s
 
 }  // namespace
 
+// The generic kernel's loops over a thread's parameters d = y, y + Y, ... come in batches of kNutsBatch: every load of a
+// batch is issued before the first store, so a thread has kNutsBatch x (vectors read) requests in flight instead of one
+// round trip to L2 / HBM per parameter (the vectors may alias as far as the compiler knows, so it does not hoist the loads
+// itself; measured on configs[2], 32,768 chains x 1,339 parameters: the step was 4x the log-density kernel).  The
+// arithmetic and its order are unchanged: same bits as before, and as the register-resident kernel.
+constexpr int kNutsBatch = 4;
+#define BPLX_FOR_BATCH(d0) for (int d0 = y; d0 < D; d0 += kNutsBatch * Y)
+#define BPLX_IN_BATCH(u, d, d0) \
+  _Pragma("unroll") for (int u = 0, d = d0; u < kNutsBatch; u++, d += Y)
+
 // block = (32 chains, Y slices).  Thread (x, y) owns parameters d = y, y+Y, ... of chain x; the scalar state machine
 // is replicated in the Y threads of a chain (same inputs, same random numbers -> same decisions); only y == 0 writes it.
 __global__ void __launch_bounds__(32 * kNutsMaxY) nuts_step_kernel(const bplx_nuts_params P) {
@@ -130,13 +140,24 @@ __global__ void __launch_bounds__(32 * kNutsMaxY) nuts_step_kernel(const bplx_nu
   const Vec zE = st.going_right ? zR : zL, rE = st.going_right ? rR : rL, gE = st.going_right ? gR : gL;
   float acc1[1] = {0.0f};
   if (pending) {
-    for (int d = y; d < D; d += Y) {
-      const float g = gr[d];
-      const float r1 = fmaf(0.5f * eps, g, ph[d]);
-      acc1[0] = fmaf(imm[d] * r1, r1, acc1[0]);
-      rE[d] = r1;
-      zE[d] = th[d];
-      gE[d] = g;
+    BPLX_FOR_BATCH(d0) {
+      float g[kNutsBatch], p[kNutsBatch], m[kNutsBatch], t[kNutsBatch];
+      BPLX_IN_BATCH(u, d, d0) {
+        const bool ok = d < D;
+        g[u] = ok ? gr[d] : 0.0f;
+        p[u] = ok ? ph[d] : 0.0f;
+        m[u] = ok ? imm[d] : 0.0f;
+        t[u] = ok ? th[d] : 0.0f;
+      }
+      BPLX_IN_BATCH(u, d, d0) {
+        if (d < D) {
+          const float r1 = fmaf(0.5f * eps, g[u], p[u]);
+          acc1[0] = fmaf(m[u] * r1, r1, acc1[0]);
+          rE[d] = r1;
+          zE[d] = t[u];
+          gE[d] = g[u];
+        }
+      }
     }
   }
   reduce_y(acc1, red);
@@ -164,17 +185,28 @@ __global__ void __launch_bounds__(32 * kNutsMaxY) nuts_step_kernel(const bplx_nu
     idx_min = idx_max - (__ffs(~leaf) - 1) + 1;  // minus the number of trailing one bits
     const bool ckpt = (leaf & 1u) == 0u;
     const Vec ck = vec_k(P.r_ckpts, idx_max), cks = vec_k(P.r_sum_ckpts, idx_max);
-    for (int d = y; d < D; d += Y) {
-      const float r1 = rE[d];
-      const float rs = st.sub_num == 0 ? r1 : rSq[d] + r1;
-      rSq[d] = rs;
-      if (take) {
-        zQ[d] = th[d];
-        gQ[d] = gr[d];
+    BPLX_FOR_BATCH(d0) {
+      float r1[kNutsBatch], q[kNutsBatch], t[kNutsBatch], g[kNutsBatch];
+      BPLX_IN_BATCH(u, d, d0) {
+        const bool ok = d < D;
+        r1[u] = ok ? rE[d] : 0.0f;
+        q[u] = (ok && st.sub_num != 0) ? rSq[d] : 0.0f;
+        t[u] = (ok && take) ? th[d] : 0.0f;
+        g[u] = (ok && take) ? gr[d] : 0.0f;
       }
-      if (ckpt) {
-        ck[d] = r1;
-        cks[d] = rs;
+      BPLX_IN_BATCH(u, d, d0) {
+        if (d < D) {
+          const float rs = st.sub_num == 0 ? r1[u] : q[u] + r1[u];
+          rSq[d] = rs;
+          if (take) {
+            zQ[d] = t[u];
+            gQ[d] = g[u];
+          }
+          if (ckpt) {
+            ck[d] = r1[u];
+            cks[d] = rs;
+          }
+        }
       }
     }
     if (take) st.sub_pe = pe1;
@@ -189,11 +221,23 @@ __global__ void __launch_bounds__(32 * kNutsMaxY) nuts_step_kernel(const bplx_nu
     float dots[2] = {0.0f, 0.0f};
     if (need) {
       const Vec ck = vec_k(P.r_ckpts, i), cks = vec_k(P.r_sum_ckpts, i);
-      for (int d = y; d < D; d += Y) {
-        const float a = ck[d], b = rE[d], m = imm[d];
-        const float s = (rSq[d] - cks[d] + a) - 0.5f * (a + b);  // momentum sum of the subtree that starts at checkpoint i
-        dots[0] = fmaf(m * a, s, dots[0]);
-        dots[1] = fmaf(m * b, s, dots[1]);
+      BPLX_FOR_BATCH(d0) {
+        float a[kNutsBatch], b[kNutsBatch], m[kNutsBatch], q[kNutsBatch], k2[kNutsBatch];
+        BPLX_IN_BATCH(u, d, d0) {
+          const bool ok = d < D;
+          a[u] = ok ? ck[d] : 0.0f;
+          b[u] = ok ? rE[d] : 0.0f;
+          m[u] = ok ? imm[d] : 0.0f;
+          q[u] = ok ? rSq[d] : 0.0f;
+          k2[u] = ok ? cks[d] : 0.0f;
+        }
+        BPLX_IN_BATCH(u, d, d0) {
+          if (d < D) {
+            const float s = (q[u] - k2[u] + a[u]) - 0.5f * (a[u] + b[u]);  // momentum sum of the subtree that starts at checkpoint i
+            dots[0] = fmaf(m[u] * a[u], s, dots[0]);
+            dots[1] = fmaf(m[u] * b[u], s, dots[1]);
+          }
+        }
       }
     }
     reduce_y(dots, red);
@@ -215,17 +259,31 @@ __global__ void __launch_bounds__(32 * kNutsMaxY) nuts_step_kernel(const bplx_nu
   {
     float dots[2] = {0.0f, 0.0f};  // generalised U-turn of the whole trajectory (numpyro `_is_turning`, diagonal mass)
     if (sub_done) {
-      for (int d = y; d < D; d += Y) {
-        const float rs = rS[d] + rSq[d];
-        rS[d] = rs;
-        if (move) {
-          zP[d] = zQ[d];
-          gP[d] = gQ[d];
+      BPLX_FOR_BATCH(d0) {
+        float r0[kNutsBatch], q[kNutsBatch], zq[kNutsBatch], gq[kNutsBatch], a[kNutsBatch], b[kNutsBatch], m[kNutsBatch];
+        BPLX_IN_BATCH(u, d, d0) {
+          const bool ok = d < D;
+          r0[u] = ok ? rS[d] : 0.0f;
+          q[u] = ok ? rSq[d] : 0.0f;
+          zq[u] = (ok && move) ? zQ[d] : 0.0f;
+          gq[u] = (ok && move) ? gQ[d] : 0.0f;
+          a[u] = ok ? rL[d] : 0.0f;
+          b[u] = ok ? rR[d] : 0.0f;
+          m[u] = ok ? imm[d] : 0.0f;
         }
-        const float a = rL[d], b = rR[d], m = imm[d];
-        const float s = rs - 0.5f * (a + b);
-        dots[0] = fmaf(m * a, s, dots[0]);
-        dots[1] = fmaf(m * b, s, dots[1]);
+        BPLX_IN_BATCH(u, d, d0) {
+          if (d < D) {
+            const float rs = r0[u] + q[u];
+            rS[d] = rs;
+            if (move) {
+              zP[d] = zq[u];
+              gP[d] = gq[u];
+            }
+            const float s = rs - 0.5f * (a[u] + b[u]);
+            dots[0] = fmaf(m[u] * a[u], s, dots[0]);
+            dots[1] = fmaf(m[u] * b[u], s, dots[1]);
+          }
+        }
       }
     }
     if (__syncthreads_or(sub_done)) reduce_y(dots, red);
@@ -349,10 +407,22 @@ __global__ void __launch_bounds__(32 * kNutsMaxY) nuts_step_kernel(const bplx_nu
     }
     const float e2 = st.going_right ? st.step_size : -st.step_size;
     const Vec zF = st.going_right ? zR : zL, rF = st.going_right ? rR : rL, gF = st.going_right ? gR : gL;
-    for (int d = y; d < D; d += Y) {
-      const float rh = fmaf(0.5f * e2, gF[d], rF[d]);
-      ph[d] = rh;
-      th[d] = fmaf(e2 * imm[d], rh, zF[d]);
+    BPLX_FOR_BATCH(d0) {
+      float g[kNutsBatch], r0[kNutsBatch], m[kNutsBatch], z[kNutsBatch];
+      BPLX_IN_BATCH(u, d, d0) {
+        const bool ok = d < D;
+        g[u] = ok ? gF[d] : 0.0f;
+        r0[u] = ok ? rF[d] : 0.0f;
+        m[u] = ok ? imm[d] : 0.0f;
+        z[u] = ok ? zF[d] : 0.0f;
+      }
+      BPLX_IN_BATCH(u, d, d0) {
+        if (d < D) {
+          const float rh = fmaf(0.5f * e2, g[u], r0[u]);
+          ph[d] = rh;
+          th[d] = fmaf(e2 * m[u], rh, z[u]);
+        }
+      }
     }
     st.stage = kNutsEvalPending;
   }

@@ -12,7 +12,87 @@ from tests import helpers as H
 from bpl_next_b200 import diagnostics as dg
 
 torch.set_num_threads(os.cpu_count() or 8)
-MODEL = sys.argv[1] if len(sys.argv) > 1 else "dixon_coles"  # or neutral_wc
+MODEL = sys.argv[1] if len(sys.argv) > 1 else "dixon_coles"  # dixon_coles | extended | neutral_wc | tw
+rng = np.random.default_rng(123)
+C, L = 64, 12
+
+
+def run_hmc(d, D, N=900):
+    """Plain HMC (L leapfrogs, Metropolis correction, diagonal mass from warm-up) on the float64 oracle density."""
+    def U(theta):
+        return om.log_density_and_grad(d, theta)
+
+    def hmc_step(theta, lp, g, eps, inv_mass):
+        r0 = rng.normal(size=theta.shape) / np.sqrt(inv_mass)
+        th, r, gg = theta.copy(), r0.copy(), g.copy()
+        e = eps[:, None] * rng.uniform(0.8, 1.2, (len(eps), 1))
+        lp1 = lp
+        for _ in range(L):
+            r = r + 0.5 * e * gg
+            th = th + e * inv_mass * r
+            lp1, gg, _cc = U(th)
+            r = r + 0.5 * e * gg
+        h0 = -lp + 0.5 * (inv_mass * r0 * r0).sum(1)
+        h1 = -lp1 + 0.5 * (inv_mass * r * r).sum(1)
+        dh = h0 - h1
+        dh = np.where(np.isfinite(dh), dh, -np.inf)
+        acc_p = np.minimum(1.0, np.exp(np.minimum(dh, 0.0)))
+        take = rng.uniform(size=len(eps)) < acc_p
+        theta = np.where(take[:, None], th, theta)
+        g = np.where(take[:, None], gg, g)
+        lp = np.where(take, lp1, lp)
+        return theta, lp, g, acc_p
+
+    theta = rng.uniform(-0.5, 0.5, (C, D))
+    lp, g, _ = U(theta)
+    eps = np.full(C, 0.05)
+    inv_mass = np.ones(D)
+    t0 = time.time()
+    hist = []
+    for stage, iters in (("step", 200), ("mass", 200), ("step2", 200)):
+        for it in range(iters):
+            theta, lp, g, acc = hmc_step(theta, lp, g, eps, inv_mass)
+            eps = np.clip(eps * np.exp(0.08 * (acc - 0.8) * (1.0 if it < iters * 0.8 else 0.3)), 1e-4, 1.0)
+            if stage == "mass" and it >= 50:
+                hist.append(theta.copy())
+        if stage == "mass":
+            inv_mass = np.concatenate(hist, 0).var(axis=0) + 1e-3
+            eps = np.full(C, np.median(eps) * 3.0)
+        print(stage, "done, median eps %.4f mean accept %.2f, %.0f s" % (np.median(eps), acc.mean(), time.time() - t0), flush=True)
+    draws = np.zeros((N, C, D))
+    for it in range(N):
+        theta, lp, g, acc = hmc_step(theta, lp, g, eps, inv_mass)
+        draws[it] = theta
+    print("sampling done, mean accept %.2f, %.0f s" % (acc.mean(), time.time() - t0), flush=True)
+    return draws
+
+
+if MODEL == "tw":
+    # tests/test_extended_dixon_coles.py:28-47 of the reference asserts that doubling epsilon scales the posterior-mean
+    # attack gap of `timed_dummy_data` by > 1.5 -- on ONE chain of 1000 draws.  The converged value under this density:
+    out = {}
+    for eps_w in (1.0, 2.0):
+        arr = H.from_training_data("extended", datasets.timed_dummy_data(), epsilon=eps_w)
+        d = H.to_oracle(arr)
+        D = om.num_params("extended", arr.num_teams, 0, 0)
+        offs = om.layout_offsets(om.site_layout("extended", arr.num_teams, 0, 0))
+        draws = run_hmc(d, D, N=1500)
+        o_sa, o_za = offs["std_attack"][0], offs["standardised_attack"][0]
+        attack = np.exp(draws[:, :, o_sa:o_sa + 1]) * draws[:, :, o_za:o_za + 2]  # no covariates: prior mean 0
+        gap = attack[:, :, 1] - attack[:, :, 0]  # [N, C]
+        x = torch.from_numpy(np.ascontiguousarray(gap[:, None, :])).float()
+        ess = float(dg.effective_sample_size(x).numpy()[0])
+        out[f"gap_eps{int(eps_w)}_mean"] = gap.mean()
+        out[f"gap_eps{int(eps_w)}_mcse"] = gap.std() / np.sqrt(ess)
+        out[f"gap_eps{int(eps_w)}_rhat"] = float(dg.split_rhat(x).numpy()[0])
+        print(f"eps {eps_w}: attack gap {gap.mean():.4f} +- {gap.std() / np.sqrt(ess):.4f} (ess {ess:.0f}, rhat {out[f'gap_eps{int(eps_w)}_rhat']:.3f})")
+    r = out["gap_eps2_mean"] / out["gap_eps1_mean"]
+    out["ratio"] = r
+    out["ratio_mcse"] = abs(r) * np.sqrt((out["gap_eps1_mcse"] / out["gap_eps1_mean"]) ** 2 + (out["gap_eps2_mcse"] / out["gap_eps2_mean"]) ** 2)
+    print(f"ratio {r:.4f} +- {out['ratio_mcse']:.4f}")
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "posterior_time_weighting.npz"), **out)
+    sys.exit(0)
+
 if MODEL in ("dixon_coles", "extended"):
     arr = H.from_training_data(MODEL, datasets.dummy_data())
 else:
@@ -22,59 +102,8 @@ T = arr.num_teams
 Cf = arr.num_conferences or 0
 D = om.num_params(MODEL, T, 0, Cf)
 offs = om.layout_offsets(om.site_layout(MODEL, T, 0, Cf))
-rng = np.random.default_rng(123)
-C, L = 64, 12
-
-
-def U(theta):
-    lp, g, cc = om.log_density_and_grad(d, theta)
-    return lp, g, cc
-
-
-def hmc_step(theta, lp, g, eps, inv_mass):
-    r0 = rng.normal(size=theta.shape) / np.sqrt(inv_mass)
-    th, r, gg = theta.copy(), r0.copy(), g.copy()
-    e = eps[:, None] * rng.uniform(0.8, 1.2, (len(eps), 1))
-    lp1, cc1 = lp, None
-    for _ in range(L):
-        r = r + 0.5 * e * gg
-        th = th + e * inv_mass * r
-        lp1, gg, cc1 = U(th)
-        r = r + 0.5 * e * gg
-    h0 = -lp + 0.5 * (inv_mass * r0 * r0).sum(1)
-    h1 = -lp1 + 0.5 * (inv_mass * r * r).sum(1)
-    dh = h0 - h1
-    dh = np.where(np.isfinite(dh), dh, -np.inf)
-    acc_p = np.minimum(1.0, np.exp(np.minimum(dh, 0.0)))
-    take = rng.uniform(size=len(eps)) < acc_p
-    theta = np.where(take[:, None], th, theta)
-    g = np.where(take[:, None], gg, g)
-    lp = np.where(take, lp1, lp)
-    return theta, lp, g, acc_p
-
-
-theta = rng.uniform(-0.5, 0.5, (C, D))
-lp, g, _ = U(theta)
-eps = np.full(C, 0.05)
-inv_mass = np.ones(D)
-t0 = time.time()
-hist = []
-for stage, iters in (("step", 200), ("mass", 200), ("step2", 200)):
-    for it in range(iters):
-        theta, lp, g, acc = hmc_step(theta, lp, g, eps, inv_mass)
-        eps = np.clip(eps * np.exp(0.08 * (acc - 0.8) * (1.0 if it < iters * 0.8 else 0.3)), 1e-4, 1.0)
-        if stage == "mass" and it >= 50:
-            hist.append(theta.copy())
-    if stage == "mass":
-        inv_mass = np.concatenate(hist, 0).var(axis=0) + 1e-3
-        eps = np.full(C, np.median(eps) * 3.0)
-    print(stage, "done, median eps %.4f mean accept %.2f, %.0f s" % (np.median(eps), acc.mean(), time.time() - t0), flush=True)
 N = 900
-draws = np.zeros((N, C, D))
-for it in range(N):
-    theta, lp, g, acc = hmc_step(theta, lp, g, eps, inv_mass)
-    draws[it] = theta
-print("sampling done, mean accept %.2f, %.0f s" % (acc.mean(), time.time() - t0), flush=True)
+draws = run_hmc(d, D, N)
 
 
 def site(name):

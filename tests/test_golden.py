@@ -14,7 +14,7 @@ from tests import helpers as H
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 DENSITY = sorted(f for f in glob.glob(os.path.join(GOLD, "*.npz"))
-                 if not os.path.basename(f).startswith(("grid_", "ref_shim_", "refgrid_", "posterior_")))
+                 if not os.path.basename(f).startswith(("grid_", "ref_shim_", "refgrid_", "refdyn_", "posterior_")))
 REF_SOURCE = sorted(glob.glob(os.path.join(GOLD, "ref_shim_*.npz")))
 REF_GRIDS = sorted(glob.glob(os.path.join(GOLD, "refgrid_*.npz")))
 GRIDS = sorted(glob.glob(os.path.join(GOLD, "grid_*.npz")))
@@ -243,3 +243,48 @@ def test_recorded_sites_match_reference_source(path):
         np.testing.assert_allclose(np.asarray(got, dtype=np.float64), z[key], rtol=2e-5, atol=2e-6, err_msg=key)
         checked += 1
     assert checked >= 3
+
+
+# ---- the dynamic model's source (a7): tests/golden/refdyn_*.npz, scripts/make_ref_shim_dynamic_golden.py -------------------
+# The reference's DynamicNeutralDixonColesMatchPredictor.fit() + `_model` (bpl/dynamic_dixon_coles.py:63-296) executed
+# unmodified under oracle/ref_shim.py: as fitted (num_gameweeks = max(gameweek), JAX's clamped gather made explicit) and with
+# num_gameweeks = max + 1.  In both the walk never reaches the rates = the product's as-written mode.
+REF_DYNAMIC = sorted(glob.glob(os.path.join(GOLD, "refdyn_*.npz")))
+
+
+def _dyn_arrays(z):
+    cov = z["covariates"] if "covariates" in z.files else None
+    return bdata.MatchArrays(model="dynamic", num_teams=int(z["num_teams"]), home_team=z["home_team"], away_team=z["away_team"],
+                             home_goals=z["home_goals"], away_goals=z["away_goals"], neutral_venue=z["neutral_venue"],
+                             gameweek=z["gameweek"], num_gameweeks=int(z["num_gameweeks"]), covariates=cov, as_written=True)
+
+
+def test_dynamic_reference_source_vectors_present():
+    assert len(REF_DYNAMIC) == 4
+
+
+@pytest.mark.parametrize("path", REF_DYNAMIC, ids=os.path.basename)
+def test_oracle_matches_dynamic_reference_source(path):
+    z = np.load(path)
+    arr = _dyn_arrays(z)
+    lp, g, _ = om.log_density_and_grad(H.to_oracle(arr), z["theta"])
+    np.testing.assert_allclose(lp, z["lp"], rtol=1e-12)
+    scale = np.abs(z["grad"]).max(axis=1, keepdims=True)
+    assert (np.abs(g - z["grad"]) / scale).max() < 1e-12
+    lp_p, g_p, _ = H.plancheck_eval(arr, z["theta"])
+    np.testing.assert_allclose(lp_p, z["lp"], rtol=1e-6)
+    assert (np.abs(g_p - z["grad"]) / scale).max() < 2e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", REF_DYNAMIC, ids=os.path.basename)
+def test_k1d_matches_dynamic_reference_source(path):
+    from bpl_next_b200 import Problem
+
+    z = np.load(path)
+    p = Problem(_dyn_arrays(z))
+    lp, grad, _ = p.logdensity_host(z["theta"].astype(np.float32))
+    np.testing.assert_allclose(lp, z["lp"], rtol=1e-5)
+    scale = np.abs(z["grad"]).max(axis=1, keepdims=True)
+    assert (np.abs(grad - z["grad"]) / scale).max() < 1e-4
+    p.close()
