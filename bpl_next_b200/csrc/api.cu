@@ -71,7 +71,8 @@ static float* mapped_or(float* host, float* fallback) {
 
 static size_t workspace_bytes(const KernelParams& kp, int C) {
   const size_t Cpad = ((size_t)C + 31) / 32 * 32;
-  if (kp.model == BPLX_DYNAMIC) return (size_t)kp.G * kp.T * 2 * Cpad * sizeof(float);  // the walk's prefix sums
+  if (kp.model == BPLX_DYNAMIC)  // the walk's prefix sums (+ the per-gameweek hyper-parameter table when shared memory is short)
+    return ((size_t)kp.G * kp.T * 2 + (kp.dyn_hyp_ws ? (size_t)kp.G * 16 : 0)) * Cpad * sizeof(float);
   if (kp.Cf <= 0) return 0;
   return (size_t)kp.V * Cpad * sizeof(float);
 }

@@ -85,7 +85,11 @@ __global__ void __launch_bounds__(kMaxWarpsDyn * 32, 1) logdensity_dynamic_kerne
   const uint32_t tab0 = smem_u32(smem) + lane * 8;
   float* const state = reinterpret_cast<float*>(smem + kp.dyn_state) + lane;  // [(t*2 + {att, def}) * 32]
   float* const part = reinterpret_cast<float*>(smem + kp.dyn_part) + lane;    // [((buf*W + warp)*10 + i) * 32]
-  float* const hyp = reinterpret_cast<float*>(smem + kp.dyn_hyp) + lane;      // [(buf*10 + i) * 32]
+  // per-gameweek hyper-parameters [(j*16 + i) * hs]: shared memory when it fits, else the workspace behind the prefix sums
+  const int hs = kp.dyn_hyp_ws ? kp.Cpad : 32;
+  float* const hyp = kp.dyn_hyp_ws ? kp.scratch + (size_t)G * T * 2 * kp.Cpad + chain
+                                   : reinterpret_cast<float*>(smem + kp.dyn_hyp) + lane;
+  float* const fin = reinterpret_cast<float*>(smem + kp.dyn_fin) + lane;      // [(t*8 + i) * 32] sites of the current gameweek
   unsigned long long* red_best = reinterpret_cast<unsigned long long*>(smem + kp.smem_red);  // [3][32]
   uint32_t* red_found = reinterpret_cast<uint32_t*>(smem + kp.smem_red + 768);               // [2][32]
   uint32_t* red_info = reinterpret_cast<uint32_t*>(smem + kp.smem_red + 1024);               // [2][32]
@@ -139,38 +143,50 @@ __global__ void __launch_bounds__(kMaxWarpsDyn * 32, 1) logdensity_dynamic_kerne
     state[(t * 2) * 32] = a0;
     state[(t * 2 + 1) * 32] = d0;
   }
-  // per-gameweek hyper-parameters, computed by one warp one gameweek ahead: mu[4], sig[4], sig_attack, sig_defence
-  auto compute_hyp = [&](int j, int buf) {
-    float* h = hyp + buf * 10 * 32;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      h[i * 32] = ln.ld(o.mean[i] + j);
-      h[(4 + i) * 32] = expf(ln.ld(o.log_std[i] + j));
-    }
-    h[8 * 32] = expf(ln.ld(o.log_std_attack + j));
-    h[9 * 32] = expf(ln.ld(o.log_std_defence + j));
-  };
+  // per-gameweek hyper-parameters, all computed up front (one round trip, gameweek j by warp j mod W):
+  // [0..3] mu, [4..7] sig, [8] sig_attack, [9] sig_defence, [10..13] log sig, [14] log sig_attack, [15] log sig_defence
   struct GwHyp { float mu[4], sig[4], sig_a, sig_d; };
-  auto read_hyp = [&](int buf) {
+  auto read_hyp = [&](int j) {
     GwHyp h;
-    const float* p = hyp + buf * 10 * 32;
+    const float* p = hyp + (size_t)j * 16 * hs;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      h.mu[i] = p[i * 32];
-      h.sig[i] = p[(4 + i) * 32];
+      h.mu[i] = p[i * hs];
+      h.sig[i] = p[(4 + i) * hs];
     }
-    h.sig_a = p[8 * 32];
-    h.sig_d = p[9 * 32];
+    h.sig_a = p[8 * hs];
+    h.sig_d = p[9 * hs];
     return h;
   };
-  if (warp == 0) compute_hyp(0, 0);
+  for (int j = warp; j < G; j += W) {
+    float* h = hyp + (size_t)j * 16 * hs;
+    float v[10];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      v[i] = ln.ld(o.mean[i] + j);
+      v[4 + i] = ln.ld(o.log_std[i] + j);
+    }
+    v[8] = ln.ld(o.log_std_attack + j);
+    v[9] = ln.ld(o.log_std_defence + j);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      h[i * hs] = v[i];
+      h[(4 + i) * hs] = expf(v[4 + i]);
+      h[(10 + i) * hs] = v[4 + i];
+    }
+    h[8 * hs] = expf(v[8]);
+    h[9 * hs] = expf(v[9]);
+    h[14 * hs] = v[8];
+    h[15 * hs] = v[9];
+  }
   __syncthreads();
 
   // table rows of (gameweek j, team t); with_lp: add the static sum of w * y * log(lambda) (linear in the exponents)
-  auto build_row = [&](uint32_t tab, int t, int jt, float att, float def, const GwHyp& h, bool with_lp) {
+  auto build_row = [&](uint32_t tab, int t, int jt, float att, float def, const float (&dec)[4], const GwHyp& h,
+                       bool with_lp) {
     float x[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) x[i] = fmaf(h.sig[i], ln.ld(o.dec[i] + jt), h.mu[i]);
+    for (int i = 0; i < 4; i++) x[i] = fmaf(h.sig[i], dec[i], h.mu[i]);
     float ex[6];
     ex[eAh1] = att + x[0];
     ex[eBh1] = -def - x[2];
@@ -197,8 +213,7 @@ __global__ void __launch_bounds__(kMaxWarpsDyn * 32, 1) logdensity_dynamic_kerne
   rdr.start(&ring, b1_0);
   for (int j = 0; j < G; j++) {
     const int hb = j & 1;
-    const GwHyp h = read_hyp(hb);
-    if (j + 1 < G && warp == (j + 1) % W) compute_hyp(j + 1, hb ^ 1);
+    const GwHyp h = read_hyp(j);
     const uint32_t tab = tab0 + (nbuf == 2 ? hb : 0) * kp.tab_bytes;
     for (int t = warp; t < T; t += W) {
       const int jt = j * T + t;
@@ -213,7 +228,12 @@ __global__ void __launch_bounds__(kMaxWarpsDyn * 32, 1) logdensity_dynamic_kerne
           ln.sc[(size_t)(2 * jt + 1) * kp.Cpad] = def;
         }
       }
-      if (__ldg(kp.team_flags + jt) & 1) build_row(tab, t, jt, att, def, h, false);
+      if (__ldg(kp.team_flags + jt) & 1) {
+        float dec[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) dec[i] = ln.ld(o.dec[i] + jt);
+        build_row(tab, t, jt, att, def, dec, h, false);
+      }
     }
     __syncthreads();  // the gameweek's tables are complete
     uint32_t hoff;
@@ -269,31 +289,25 @@ __global__ void __launch_bounds__(kMaxWarpsDyn * 32, 1) logdensity_dynamic_kerne
   s_gw[0] = Lam > 0.0f ? unpack_hdr(__ldg(reinterpret_cast<const uint4*>(kp.stream1 + s_hoff[0]))).vteam : 0xffffu;
   s_gw[1] = best[2] > 1.0f ? unpack_hdr(__ldg(reinterpret_cast<const uint4*>(kp.stream1 + s_hoff[1]))).vteam : 0xffffu;
 
-  // the ten hyper-parameter sites of gameweek j: likelihood sums from the warps' partials + priors + Jacobians
+  // The ten hyper-parameter sites of gameweek j: likelihood sums from the warps' partials + priors + Jacobians.  Component
+  // c (0: std_attack, 1: std_defence, 2..5: mean_*, 6..9: std_*) is summed by warp c mod W, in a fixed order.
   auto reduce_hyper = [&](int j) {
     const float* pb = part + (size_t)((j & 1) * W) * 10 * 32;
-    float s[10];
-#pragma unroll
-    for (int i = 0; i < 10; i++) s[i] = 0.0f;
-    for (int w = 0; w < W; w++) {
-#pragma unroll
-      for (int i = 0; i < 10; i++) s[i] += pb[(w * 10 + i) * 32];
-    }
-    const float lsa = ln.ld(o.log_std_attack + j), lsd = ln.ld(o.log_std_defence + j);
-    const float sig_a = expf(lsa), sig_d = expf(lsd);
-    lp_acc += fmaf(-0.5f * sig_a, sig_a, lsa) + fmaf(-0.5f * sig_d, sig_d, lsd);
-    if (ln.active) {
-      st_stream(ln.g(o.log_std_attack + j), fmaf(-sig_a, sig_a, 1.0f) + s[0]);
-      st_stream(ln.g(o.log_std_defence + j), fmaf(-sig_d, sig_d, 1.0f) + s[1]);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const float mu = ln.ld(o.mean[i] + j), lsig = ln.ld(o.log_std[i] + j), sig = expf(lsig);
-      const float z = (mu - ((i & 1) ? -0.1f : 0.1f)) * 5.0f;  // N(+-0.1, 0.2)
-      lp_acc += -0.5f * z * z + fmaf(-0.5f * sig, sig, lsig);
-      if (ln.active) {
-        st_stream(ln.g(o.mean[i] + j), fmaf(-z, 5.0f, s[2 + i]));
-        st_stream(ln.g(o.log_std[i] + j), fmaf(-sig, sig, 1.0f) + s[6 + i]);
+    const float* hj = hyp + (size_t)j * 16 * hs;
+    for (int c = warp; c < 10; c += W) {
+      float s = 0.0f;
+      for (int w = 0; w < W; w++) s += pb[(w * 10 + c) * 32];
+      if (c < 2 || c >= 6) {  // HalfNormal(1) on exp(x) + Jacobian x
+        const int i = c < 2 ? 8 + c : c - 2;        // index of sig; its log sits 6 entries further
+        const float sig = hj[i * hs], lsig = hj[(i + 6) * hs];
+        lp_acc += fmaf(-0.5f * sig, sig, lsig);
+        const int site = c == 0 ? o.log_std_attack : (c == 1 ? o.log_std_defence : o.log_std[c - 6]);
+        if (ln.active) st_stream(ln.g(site + j), fmaf(-sig, sig, 1.0f) + s);
+      } else {  // mean_* ~ N(+-0.1, 0.2)
+        const int i = c - 2;
+        const float z = (hj[i * hs] - ((i & 1) ? -0.1f : 0.1f)) * 5.0f;
+        lp_acc -= 0.5f * z * z;
+        if (ln.active) st_stream(ln.g(o.mean[i] + j), fmaf(-z, 5.0f, s));
       }
     }
   };
@@ -303,22 +317,32 @@ __global__ void __launch_bounds__(kMaxWarpsDyn * 32, 1) logdensity_dynamic_kerne
   rdr.start(&ring, b2_0);
   for (int j = G - 1; j >= 0; j--) {
     const int hb = j & 1;
-    const GwHyp h = read_hyp(hb);
-    if (j > 0 && warp == (j - 1) % W) compute_hyp(j - 1, hb ^ 1);
+    const GwHyp h = read_hyp(j);
     const uint32_t tab = tab0 + (nbuf == 2 ? hb : 0) * kp.tab_bytes;
     for (int t = warp; t < T; t += W) {
+      // everything this (gameweek, team) needs from global memory is requested here, in one round trip; what the
+      // completion step below needs waits in the warp's stash
       const int jt = j * T + t;
-      if (__ldg(kp.team_flags + jt) & 1) {
-        float att = 0.0f, def = 0.0f;
-        if (!kp.as_written) {
-          att = ld_cg(ln.sc + (size_t)(2 * jt) * kp.Cpad);
-          def = ld_cg(ln.sc + (size_t)(2 * jt + 1) * kp.Cpad);
-        }
-        build_row(tab, t, jt, att, def, h, true);
+      const bool has = __ldg(kp.team_flags + jt) & 1;
+      float att = 0.0f, def = 0.0f;
+      if (has && !kp.as_written) {
+        att = ld_cg(ln.sc + (size_t)(2 * jt) * kp.Cpad);
+        def = ld_cg(ln.sc + (size_t)(2 * jt + 1) * kp.Cpad);
       }
+      float dec[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) dec[i] = ln.ld(o.dec[i] + jt);
+      const float za = ln.ld(o.za + jt), zd = ln.ld(o.zd + jt), ul = ln.ld(o.u + jt);
+      float* f = fin + (size_t)(t * 8) * 32;
+      f[0] = za;
+      f[32] = zd;
+      f[64] = ul;
+#pragma unroll
+      for (int i = 0; i < 4; i++) f[(3 + i) * 32] = dec[i];
+      if (has) build_row(tab, t, jt, att, def, dec, h, true);
     }
     __syncthreads();  // tables complete; the hyper partials of gameweek j + 1 are all written
-    if (j + 1 < G && warp == (j + 1) % W) reduce_hyper(j + 1);
+    if (j + 1 < G) reduce_hyper(j + 1);
     // arg-max search: the entry of the piece that attained the maximum, while its gameweek is resident; warp w looks
     // at entries w, w + W, ...; ties (rates that overflowed to inf) go to the lowest entry -- atomicMin, not timing
 #pragma unroll 1
@@ -391,10 +415,11 @@ __global__ void __launch_bounds__(kMaxWarpsDyn * 32, 1) logdensity_dynamic_kerne
         const int t = (int)L.team, jt = j * T + t;
         const float4 ys = __ldg(reinterpret_cast<const float4*>(kp.yteam + (size_t)jt * 8));
         const float2 ys2 = __ldg(reinterpret_cast<const float2*>(kp.yteam + (size_t)jt * 8 + 4));
-        const float za = ln.ld(o.za + jt), zd = ln.ld(o.zd + jt), ul = ln.ld(o.u + jt);
+        const float* f = fin + (size_t)(t * 8) * 32;
+        const float za = f[0], zd = f[32], ul = f[64];
         float dec[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) dec[i] = ln.ld(o.dec[i] + jt);
+        for (int i = 0; i < 4; i++) dec[i] = f[(3 + i) * 32];
         const float ra = g[eAh1] + g[eAa1] + g[eA0] + ys.x;
         const float rd = -(g[eBh1] + g[eBa1] + g[eB0]) + ys.y;
         const float rx[4] = {g[eAh1] + ys.z, g[eAa1] + ys.w, -g[eBh1] + ys2.x, -g[eBa1] + ys2.y};
@@ -406,10 +431,12 @@ __global__ void __launch_bounds__(kMaxWarpsDyn * 32, 1) logdensity_dynamic_kerne
           state[(t * 2 + 1) * 32] = s_def;
         }
         // u ~ Beta(2,4) + Jacobian; za ~ N(0,1); zd ~ N(rho za, sqrt(1 - rho^2))  (dynamic_dixon_coles.py:128-143)
-        const float u = sigmoid_clipped(ul);
-        const float rho = 2.0f * u - 1.0f, inv_s2 = 1.0f / (1.0f - rho * rho);
+        // (600+ of these per chain and call: the hardware's exp / log / reciprocal approximations, 2 ulp, are ample for
+        //  a term of a sum checked at 1e-5 relative)
+        const float u = fminf(fmaxf(__fdividef(1.0f, 1.0f + __expf(-ul)), FLT_MIN), 1.0f - FLT_EPSILON);
+        const float rho = 2.0f * u - 1.0f, s2 = fmaf(-rho, rho, 1.0f), inv_s2 = __fdividef(1.0f, s2);
         const float e = zd - rho * za, es = e * inv_s2;
-        lp_acc += -0.5f * (za * za + e * es) + 0.5f * logf(inv_s2) + 2.0f * logf(u) + 4.0f * logf(1.0f - u);
+        lp_acc += -0.5f * (za * za + e * es) + kLn2 * (-0.5f * lg2_approx(s2) + 2.0f * lg2_approx(u) + 4.0f * lg2_approx(1.0f - u));
         const float a_rho = es * za - rho * es * es + rho * inv_s2;
         if (ln.active) {
           st_stream(ln.g(o.u + jt), 2.0f - 6.0f * u + a_rho * 2.0f * u * (1.0f - u));
@@ -436,7 +463,7 @@ __global__ void __launch_bounds__(kMaxWarpsDyn * 32, 1) logdensity_dynamic_kerne
   }
   red_gc[warp * 32 + lane] = gc;
   __syncthreads();  // partials of gameweek 0, the suffix sums of every team and every gradient entry are written
-  if (warp == 0) reduce_hyper(0);
+  reduce_hyper(0);
   gc = 0.0f;
   for (int w = 0; w < W; w++) gc += red_gc[w * 32 + lane];
   {  // the 1-1 matches: tau = 1 - c for all of them

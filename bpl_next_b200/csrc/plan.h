@@ -138,8 +138,11 @@ struct KernelParams {
   uint32_t smem_red_cl;          // [kMaxSplit][32] d/d corr_coef partials of a cluster (rank 0)
   uint32_t smem_p2;              // 0, or [2 sides][T][2 + ndec][32] f32: phase-2 slot sums when the split-1 plan deals a
                                  // team's home-side and away-side tau lists to different warps (small T, one CTA)
-  uint32_t dyn_state, dyn_part, dyn_hyp;  // DYNAMIC: [T][2][32] f32 walk state, [2][W][10][32] f32 hyper partials, [2][10][32] f32
+  uint32_t dyn_state, dyn_part, dyn_hyp, dyn_fin;  // DYNAMIC: [T][2][32] f32 walk state, [2][W][10][32] f32 hyper partials,
+                                                   // [G][16][32] f32 per-gameweek hyper-parameters, [T][8][32] f32 site stash
   int dyn_nbuf;                           // DYNAMIC: table buffers (2: gameweek j+1 is built while j is still read)
+  int dyn_hyp_ws;                         // DYNAMIC: the hyper-parameter table lives in the workspace ([G][16][Cpad] behind the
+                                          // prefix sums) because it does not fit in shared memory
   int split_hint;                // largest cluster size worth using (small plans are latency-bound: 1)
   int force_clip_forms;          // testing (env BPLX_CLIP_FORMS at create): bit 0 / bit 1 = phase 1 / phase 2 always take the
                                  // clipping form of the arithmetic, even when no rate of the chains is near the clip
