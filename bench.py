@@ -158,7 +158,7 @@ def parity_sample(arr, theta_dc, lp, grad, cc, nsample=8, seed=0):
             "tolerance": {"lp_rel": 1e-5, "grad_scaled": 1e-4}, "ok": bool(e_lp < 1e-5 and e_g < 1e-4)}
 
 
-def time_logdensity(problem, C, steps, warmup, radius, seed, use_graph=True, target_s=1.0, arr=None):
+def time_logdensity(problem, C, steps, warmup, radius, seed, use_graph=True, target_s=1.0, arr=None, pad_rows=False):
     """Median device time of a K-step region (ms) over several repetitions; inputs rotate through buffer sets whose
     total size exceeds the L2 whatever K is."""
     import torch
@@ -169,8 +169,11 @@ def time_logdensity(problem, C, steps, warmup, radius, seed, use_graph=True, tar
     set_bytes = 2 * C * D * 4
     nb = max(2, int(math.ceil(1.5 * L2_BYTES / set_bytes)))
     g = torch.Generator(device="cuda").manual_seed(seed)
-    thetas = [(torch.rand((D, C), generator=g, device="cuda", dtype=torch.float32) * 2 - 1) * radius for _ in range(nb)]
-    grads = [torch.empty((D, C), device="cuda", dtype=torch.float32) for _ in range(nb)]
+    # row pitch of the [D, C] arrays (the C ABI's `ld` argument): dense by default; --pad-rows adds one 128-byte line to a
+    # pitch that is a multiple of 4 KB (measured: no difference on B200 for K1, K1d or the NUTS step)
+    ld = C + 32 if (pad_rows and (C * 4) % 4096 == 0) else C
+    thetas = [((torch.rand((D, ld), generator=g, device="cuda", dtype=torch.float32) * 2 - 1) * radius)[:, :C] for _ in range(nb)]
+    grads = [torch.empty((D, ld), device="cuda", dtype=torch.float32)[:, :C] for _ in range(nb)]
     lps = [torch.empty(C, device="cuda", dtype=torch.float32) for _ in range(nb)]
     ccs = [torch.empty(C, device="cuda", dtype=torch.float32) for _ in range(nb)]
     problem.workspace(C)
@@ -220,7 +223,7 @@ def time_logdensity(problem, C, steps, warmup, radius, seed, use_graph=True, tar
             if time.perf_counter() - t_start > target_s or len(times) >= 400:
                 break
     finite = bool(torch.isfinite(lps[0]).all().item())
-    return {"ms": float(np.median(times)), "reps": len(times), "nb": nb, "set_bytes": set_bytes, "finite": finite,
+    return {"ms": float(np.median(times)), "reps": len(times), "nb": nb, "set_bytes": set_bytes, "finite": finite, "ld": ld,
             "launches": launches, "parity": parity}
 
 
@@ -549,13 +552,15 @@ def main():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-subrecords", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--pad-rows", action="store_true", help="row pitch of theta / grad C + 32 floats instead of C")
     ap.add_argument("--fit-chains", type=int, default=32768)
-    ap.add_argument("--fit-warmup", type=int, default=150)
-    ap.add_argument("--fit-samples", type=int, default=100)
-    ap.add_argument("--fit-thin", type=int, default=10)
-    ap.add_argument("--fit-tree-depth", type=int, default=6,
-                    help="max_tree_depth of the fit sub-record (numpyro's default is 10; 6 bounds the bench's wall time: "
-                         "before the mass matrix is adapted every transition of this 1,339-parameter posterior runs to the cap)")
+    ap.add_argument("--fit-warmup", type=int, default=100)
+    ap.add_argument("--fit-samples", type=int, default=50)
+    ap.add_argument("--fit-thin", type=int, default=5)
+    ap.add_argument("--fit-tree-depth", type=int, default=5,
+                    help="max_tree_depth of the fit sub-record (numpyro's default is 10; 5 bounds the bench's wall time: "
+                         "before the mass matrix is adapted every transition of this 1,339-parameter posterior runs to the "
+                         "cap, so the sub-record is a timing of the sharded fit path, not a converged posterior -- see rhat_max)")
     ap.add_argument("--fit-max-launches", type=int, default=0, help="cap on log-density launches of the fit sub-record (0: none)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -603,7 +608,7 @@ def main():
     barrier()
     with ClockSampler(local) as clk:
         r = time_logdensity(problem, C, args.steps, args.warmup, args.radius, args.seed + 1 + rank,
-                            use_graph=not args.no_graph, arr=arr if rank == 0 else None)
+                            use_graph=not args.no_graph, arr=arr if rank == 0 else None, pad_rows=args.pad_rows)
     barrier()
     ms = max_over_ranks(r["ms"])
     value = units_total * arr.num_matches * args.steps / (ms * 1e-3)
@@ -670,7 +675,7 @@ def main():
             "config": {"workload": desc + f", {C_total} chains " + (f"partitioned over {world} GPU(s)" if args.scaling == "strong" else "per GPU"),
                        "chains_total": units_total, "chains_per_gpu": C, "matches": arr.num_matches,
                        "teams": arr.num_teams, "params": problem.D, "theta": f"U(-{args.radius},{args.radius})",
-                       "layout": "chain-minor [D, C] resident in HBM",
+                       "layout": f"chain-minor [D, C] resident in HBM, row pitch {r['ld']} floats",
                        "l2": f"inputs rotate through {r['nb']} buffer sets of {r['set_bytes'] / 1e6:.1f} MB each "
                              f"({r['nb'] * r['set_bytes'] / 1e6:.0f} MB > 126 MB L2)",
                        "timing": f"{'CUDA graph of' if not args.no_graph else ''} {args.steps} launches, CUDA events on "

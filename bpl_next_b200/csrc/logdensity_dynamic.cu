@@ -195,11 +195,13 @@ __global__ void __launch_bounds__(kMaxWarpsDyn * 32, 1) logdensity_dynamic_kerne
     ex[eA0] = att;
     ex[eB0] = -def;
     const uint32_t row = (uint32_t)t * kRowBytes;
+    // (the hardware exponential, 2 ulp: both passes build the rows with the same instructions, so the arg-max search
+    //  still finds the very product the forward pass saw)
     if (kp.has1) {
-      sts64(tab + kp.tabP1 + row, expf(ex[eAh1]), expf(ex[eBh1]));
-      sts64(tab + kp.tabQ1 + row, expf(ex[eBa1]), expf(ex[eAa1]));
+      sts64(tab + kp.tabP1 + row, __expf(ex[eAh1]), __expf(ex[eBh1]));
+      sts64(tab + kp.tabQ1 + row, __expf(ex[eBa1]), __expf(ex[eAa1]));
     }
-    if (kp.has0) sts64(tab + kp.tabP0 + row, expf(ex[eA0]), expf(ex[eB0]));
+    if (kp.has0) sts64(tab + kp.tabP0 + row, __expf(ex[eA0]), __expf(ex[eB0]));
     if (with_lp) {
 #pragma unroll
       for (int e = 0; e < 6; e++) lp_acc = fmaf(__ldg(kp.yexp + (size_t)jt * 6 + e), ex[e], lp_acc);

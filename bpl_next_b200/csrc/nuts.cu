@@ -138,31 +138,87 @@ __global__ void __launch_bounds__(32 * kNutsMaxY) nuts_step_kernel(const bplx_nu
   }
   const float eps = st.going_right ? st.step_size : -st.step_size;
   const Vec zE = st.going_right ? zR : zL, rE = st.going_right ? rR : rL, gE = st.going_right ? gR : gL;
-  float acc1[1] = {0.0f};
+  // checkpoints for the iterative U-turn test (numpyro `_leaf_idx_to_ckpt_idxs`, `_is_iterative_turning`): the levels
+  // idx_min .. idx_max this leaf is tested against, and the level an even leaf is stored at
+  const unsigned leaf = (unsigned)st.sub_num;
+  int idx_min = 1, idx_max = 0;
   if (pending) {
+    idx_max = __popc(leaf >> 1);
+    idx_min = idx_max - (__ffs(~leaf) - 1) + 1;  // minus the number of trailing one bits
+  }
+  const unsigned my_lvls = (pending && idx_max >= idx_min) ? (((2u << idx_max) - 1u) & ~((1u << idx_min) - 1u)) : 0u;
+  const bool ckpt = pending && (leaf & 1u) == 0u;
+  // ONE pass over the parameters does everything that does not depend on the accept / take decisions: the new leaf
+  // (momentum, position, gradient of the extended end), the kinetic energy, the subtree's momentum sum, the checkpoint
+  // an even leaf leaves behind and the U-turn dot products of every level the leaf is tested against -- each vector is
+  // read once (the stage-by-stage form re-read the leaf's momentum, the sum and the inverse mass once per level).
+  constexpr int kLv = 12;  // max_tree_depth <= 12
+  bool spec = false;
+  float acc1[1] = {0.0f};
+  float dt0[kLv], dt1[kLv];
+#pragma unroll
+  for (int i = 0; i < kLv; i++) dt0[i] = dt1[i] = 0.0f;
+  if (pending) {
+    const Vec ckw = vec_k(P.r_ckpts, idx_max), cksw = vec_k(P.r_sum_ckpts, idx_max);
+    const bool first = st.sub_num == 0;
+    // a leaf that is not the last of its subtree is followed by a leapfrog from the same end, unless the subtree turns or
+    // diverges: its start (stage F) is computed here, from registers, and redone below in the rare other case
+    spec = st.sub_num + 1 < (1 << st.depth);
     BPLX_FOR_BATCH(d0) {
-      float g[kNutsBatch], p[kNutsBatch], m[kNutsBatch], t[kNutsBatch];
+      float g[kNutsBatch], p[kNutsBatch], m[kNutsBatch], t[kNutsBatch], q[kNutsBatch], r1[kNutsBatch], rs[kNutsBatch];
       BPLX_IN_BATCH(u, d, d0) {
         const bool ok = d < D;
         g[u] = ok ? gr[d] : 0.0f;
         p[u] = ok ? ph[d] : 0.0f;
         m[u] = ok ? imm[d] : 0.0f;
         t[u] = ok ? th[d] : 0.0f;
+        q[u] = (ok && !first) ? rSq[d] : 0.0f;
+      }
+      BPLX_IN_BATCH(u, d, d0) {
+        r1[u] = fmaf(0.5f * eps, g[u], p[u]);
+        rs[u] = first ? r1[u] : q[u] + r1[u];
+      }
+#pragma unroll
+      for (int i = 0; i < kLv; i++) {
+        if (my_lvls & (1u << i)) {
+          const Vec ck = vec_k(P.r_ckpts, i), cks = vec_k(P.r_sum_ckpts, i);
+          float a[kNutsBatch], k2[kNutsBatch];
+          BPLX_IN_BATCH(u, d, d0) {
+            const bool ok = d < D;
+            a[u] = ok ? ck[d] : 0.0f;
+            k2[u] = ok ? cks[d] : 0.0f;
+          }
+          BPLX_IN_BATCH(u, d, d0) {
+            if (d < D) {
+              const float sm = (rs[u] - k2[u] + a[u]) - 0.5f * (a[u] + r1[u]);  // momentum sum of the subtree that starts at checkpoint i
+              dt0[i] = fmaf(m[u] * a[u], sm, dt0[i]);
+              dt1[i] = fmaf(m[u] * r1[u], sm, dt1[i]);
+            }
+          }
+        }
       }
       BPLX_IN_BATCH(u, d, d0) {
         if (d < D) {
-          const float r1 = fmaf(0.5f * eps, g[u], p[u]);
-          acc1[0] = fmaf(m[u] * r1, r1, acc1[0]);
-          rE[d] = r1;
+          acc1[0] = fmaf(m[u] * r1[u], r1[u], acc1[0]);
+          rE[d] = r1[u];
           zE[d] = t[u];
           gE[d] = g[u];
+          rSq[d] = rs[u];
+          if (ckpt) {
+            ckw[d] = r1[u];
+            cksw[d] = rs[u];
+          }
+          if (spec) {
+            const float rh = fmaf(0.5f * eps, g[u], r1[u]);
+            ph[d] = rh;
+            th[d] = fmaf(eps * m[u], rh, t[u]);
+          }
         }
       }
     }
   }
   reduce_y(acc1, red);
   bool sub_done = false;
-  int idx_min = 1, idx_max = 0;
   if (pending) {
     const float pe1 = -lp_new;
     float delta = pe1 + 0.5f * acc1[0] - st.energy_current;
@@ -179,67 +235,33 @@ __global__ void __launch_bounds__(32 * kNutsMaxY) nuts_step_kernel(const bplx_nu
       take = uniform() < pr;
       st.sub_weight = log_add_exp(st.sub_weight, w_leaf);
     }
-    // checkpoints for the iterative U-turn test (numpyro `_leaf_idx_to_ckpt_idxs`, `_is_iterative_turning`)
-    const unsigned leaf = (unsigned)st.sub_num;
-    idx_max = __popc(leaf >> 1);
-    idx_min = idx_max - (__ffs(~leaf) - 1) + 1;  // minus the number of trailing one bits
-    const bool ckpt = (leaf & 1u) == 0u;
-    const Vec ck = vec_k(P.r_ckpts, idx_max), cks = vec_k(P.r_sum_ckpts, idx_max);
-    BPLX_FOR_BATCH(d0) {
-      float r1[kNutsBatch], q[kNutsBatch], t[kNutsBatch], g[kNutsBatch];
-      BPLX_IN_BATCH(u, d, d0) {
-        const bool ok = d < D;
-        r1[u] = ok ? rE[d] : 0.0f;
-        q[u] = (ok && st.sub_num != 0) ? rSq[d] : 0.0f;
-        t[u] = (ok && take) ? th[d] : 0.0f;
-        g[u] = (ok && take) ? gr[d] : 0.0f;
-      }
-      BPLX_IN_BATCH(u, d, d0) {
-        if (d < D) {
-          const float rs = st.sub_num == 0 ? r1[u] : q[u] + r1[u];
-          rSq[d] = rs;
-          if (take) {
+    if (take) {  // the subtree's proposal moves to the new leaf (its position: the copy just made, theta may have moved on)
+      BPLX_FOR_BATCH(d0) {
+        float t[kNutsBatch], g[kNutsBatch];
+        BPLX_IN_BATCH(u, d, d0) {
+          const bool ok = d < D;
+          t[u] = ok ? zE[d] : 0.0f;
+          g[u] = ok ? gr[d] : 0.0f;
+        }
+        BPLX_IN_BATCH(u, d, d0) {
+          if (d < D) {
             zQ[d] = t[u];
             gQ[d] = g[u];
           }
-          if (ckpt) {
-            ck[d] = r1[u];
-            cks[d] = rs;
-          }
         }
       }
+      st.sub_pe = pe1;
     }
-    if (take) st.sub_pe = pe1;
     st.sub_div = delta > P.max_delta_energy;
     st.sub_sum_accept += acc;
   }
   // ======== B. iterative U-turn test against the checkpoints (levels idx_max .. idx_min, stop at the first turn) =======
   bool turning = false;
-  for (int i = P.max_tree_depth - 1; i >= 0; i--) {
-    const bool need = pending && i <= idx_max && i >= idx_min && !turning;
+#pragma unroll
+  for (int i = kLv - 1; i >= 0; i--) {
+    const bool need = ((my_lvls >> i) & 1u) && !turning;
     if (!__syncthreads_or(need)) continue;
-    float dots[2] = {0.0f, 0.0f};
-    if (need) {
-      const Vec ck = vec_k(P.r_ckpts, i), cks = vec_k(P.r_sum_ckpts, i);
-      BPLX_FOR_BATCH(d0) {
-        float a[kNutsBatch], b[kNutsBatch], m[kNutsBatch], q[kNutsBatch], k2[kNutsBatch];
-        BPLX_IN_BATCH(u, d, d0) {
-          const bool ok = d < D;
-          a[u] = ok ? ck[d] : 0.0f;
-          b[u] = ok ? rE[d] : 0.0f;
-          m[u] = ok ? imm[d] : 0.0f;
-          q[u] = ok ? rSq[d] : 0.0f;
-          k2[u] = ok ? cks[d] : 0.0f;
-        }
-        BPLX_IN_BATCH(u, d, d0) {
-          if (d < D) {
-            const float s = (q[u] - k2[u] + a[u]) - 0.5f * (a[u] + b[u]);  // momentum sum of the subtree that starts at checkpoint i
-            dots[0] = fmaf(m[u] * a[u], s, dots[0]);
-            dots[1] = fmaf(m[u] * b[u], s, dots[1]);
-          }
-        }
-      }
-    }
+    float dots[2] = {dt0[i], dt1[i]};
     reduce_y(dots, red);
     if (need) turning = dots[0] <= 0.0f || dots[1] <= 0.0f;
   }
@@ -407,6 +429,7 @@ __global__ void __launch_bounds__(32 * kNutsMaxY) nuts_step_kernel(const bplx_nu
     }
     const float e2 = st.going_right ? st.step_size : -st.step_size;
     const Vec zF = st.going_right ? zR : zL, rF = st.going_right ? rR : rL, gF = st.going_right ? gR : gL;
+    if (!(spec && !sub_done))  // (else: computed in the pass above, same arithmetic)
     BPLX_FOR_BATCH(d0) {
       float g[kNutsBatch], r0[kNutsBatch], m[kNutsBatch], z[kNutsBatch];
       BPLX_IN_BATCH(u, d, d0) {

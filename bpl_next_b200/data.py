@@ -22,13 +22,20 @@ DTYPES = {"goals": np.uint8, "teams": np.uint16, "conferences": np.uint8, "venue
 
 def parse_teams(home_team, away_team):
     """``bpl/_util.py:115-135``: sorted unique names, name->index dict, index arrays."""
-    teams = np.array(sorted(set(home_team) | set(away_team)))
-    teams_dict = {t: i for i, t in enumerate(teams)}
+    h, a = np.asarray(home_team), np.asarray(away_team)
+    if h.dtype.kind in "USiuf" and a.dtype.kind == h.dtype.kind and h.ndim == 1:
+        # one sort of the 2M names instead of 2M dictionary look-ups: same sorted unique names, same indices
+        teams, inv = np.unique(np.concatenate([h, a]), return_inverse=True)
+        home_ind, away_ind = inv[:len(h)], inv[len(h):]
+    else:  # names numpy cannot order as one array (mixed types): the reference's own loop
+        teams = np.array(sorted(set(home_team) | set(away_team)))
+        lut = {t: i for i, t in enumerate(teams)}
+        home_ind = np.array([lut[t] for t in home_team])
+        away_ind = np.array([lut[t] for t in away_team])
     if len(teams) > np.iinfo(DTYPES["teams"]).max:
         raise ValueError("too many teams for the uint16 team index")
-    home_ind = np.array([teams_dict[t] for t in home_team], DTYPES["teams"])
-    away_ind = np.array([teams_dict[t] for t in away_team], DTYPES["teams"])
-    return teams, teams_dict, home_ind, away_ind
+    teams_dict = {t: i for i, t in enumerate(teams)}
+    return teams, teams_dict, home_ind.astype(DTYPES["teams"]), away_ind.astype(DTYPES["teams"])
 
 
 def _goals(x):

@@ -77,8 +77,9 @@ class Problem:
     def logdensity(self, theta: torch.Tensor, chain_minor: bool = False, lp=None, grad=None, corr_coef=None,
                    stream=None):
         """Enqueue log-density + gradient.  ``theta`` is ``[C, D]`` (chain-major) or ``[D, C]``
-        (``chain_minor=True``), float32, contiguous, on the GPU.  Returns ``(lp, grad, corr_coef)``."""
-        assert theta.is_cuda and theta.dtype == torch.float32 and theta.is_contiguous()
+        (``chain_minor=True``), float32, on the GPU; rows may be padded (a view with unit inner stride: the row pitch is
+        passed as the leading dimension, and ``grad`` must have the same pitch).  Returns ``(lp, grad, corr_coef)``."""
+        assert theta.is_cuda and theta.dtype == torch.float32 and theta.dim() == 2 and theta.stride(1) == 1
         if chain_minor:
             D, Cn = theta.shape
         else:
@@ -86,11 +87,13 @@ class Problem:
         if D != self.D:
             raise ValueError(f"theta has {D} parameters, the model has {self.D}")
         lp = torch.empty(Cn, dtype=torch.float32, device=theta.device) if lp is None else lp
-        grad = torch.empty_like(theta) if grad is None else grad
+        grad = torch.empty_strided(theta.shape, theta.stride(), dtype=torch.float32, device=theta.device) if grad is None else grad
+        assert grad.shape == theta.shape and grad.stride() == theta.stride()
         corr_coef = torch.empty(Cn, dtype=torch.float32, device=theta.device) if corr_coef is None else corr_coef
         ws = self.workspace(Cn)
+        ld = int(theta.stride(0)) if theta.shape[0] > 1 else 0
         _abi.check(self._lib.bplx_logdensity_fwdbwd(
-            self._h, Cn, _abi.CHAIN_MINOR if chain_minor else _abi.CHAIN_MAJOR, 0,
+            self._h, Cn, _abi.CHAIN_MINOR if chain_minor else _abi.CHAIN_MAJOR, ld,
             _dptr(theta), _dptr(lp), _dptr(grad), _dptr(corr_coef),
             _dptr(ws), 0 if ws is None else ws.numel(), _stream_ptr(stream)))
         return lp, grad, corr_coef

@@ -1,5 +1,5 @@
-"""Per-launch cost of one leapfrog of a configs[2] fit: the log-density kernel (K1) and the NUTS step kernel, timed with
-CUDA events over a fixed number of (K1, step) pairs (no CUDA graph, so that ncu can pick single launches)."""
+"""Per-launch cost of one leapfrog of a configs[2] fit in steady state: (log-density kernel + NUTS step kernel) pairs timed
+as the difference of two runs of different length (no CUDA graph), next to the log-density kernel alone."""
 import json, sys, time
 import numpy as np, torch
 sys.path.insert(0, '.')
@@ -7,25 +7,31 @@ from bpl_next_b200 import Problem, nuts as bn, data as bdata
 from oracle import datasets
 
 C = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
-pairs = int(sys.argv[2]) if len(sys.argv) > 2 else 96
+n1 = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+n2 = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
+PAD = (sys.argv[4] != "nopad") if len(sys.argv) > 4 else True
 arr, _ = bdata.prepare("neutral_wc", datasets.config_3(), epsilon=0.1)
 p = Problem(arr)
 g = torch.Generator(device="cuda").manual_seed(1)
 theta0 = (torch.rand((p.D, C), generator=g, device="cuda") * 4 - 2).contiguous()
-t_k1 = []
 
 
 def potential(theta, lp, grad):
     p.logdensity(theta, chain_minor=True, lp=lp, grad=grad)
 
 
-torch.cuda.synchronize()
-t0 = time.perf_counter()
-run = bn.sample(potential, theta0, num_warmup=1000, num_samples=10, max_tree_depth=6, max_launches=pairs, use_graph=False,
-                check_every=32, diag_lags=8)
-torch.cuda.synchronize()
-wall = time.perf_counter() - t0
-# K1 alone on the same shapes
+def run(n):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    r = bn.sample(potential, theta0, num_warmup=1000, num_samples=10, max_tree_depth=6, max_launches=n, use_graph=False, pad_rows=PAD,
+                  check_every=32, diag_lags=8)
+    torch.cuda.synchronize()
+    return time.perf_counter() - t0, r.launches
+
+
+run(64)
+t1, l1 = run(n1)
+t2, l2 = run(n2)
 lp = torch.empty(C, device="cuda"); grad = torch.empty_like(theta0)
 for _ in range(3):
     potential(theta0, lp, grad)
@@ -36,5 +42,6 @@ for _ in range(10):
     potential(theta0, lp, grad)
 e1.record(); e1.synchronize()
 k1 = e0.elapsed_time(e1) / 10
-print(json.dumps({"chains": C, "D": p.D, "pairs": run.launches, "wall_s": wall, "ms_per_pair": 1e3 * wall / run.launches,
-                  "k1_ms": k1, "step_ms_est": 1e3 * wall / run.launches - k1}))
+pair = 1e3 * (t2 - t1) / (l2 - l1)
+print(json.dumps({"chains": C, "D": p.D, "launches": [l1, l2], "ms_per_pair_steady": pair, "k1_ms": k1, "step_ms": pair - k1,
+                  "ms_per_pair_first": 1e3 * t1 / l1}))
