@@ -92,6 +92,8 @@ def declare(lib):
     lib.bplx_score_grid_workspace_bytes.restype = sz
     lib.bplx_score_grid.argtypes = [C.POINTER(Samples), C.POINTER(Fixtures), i, C.c_float, vp, vp, vp, sz, vp]
     lib.bplx_score_grid.restype = i
+    lib.bplx_score_grid_ex.argtypes = [C.POINTER(Samples), C.POINTER(Fixtures), i, C.c_float, vp, vp, vp, sz, vp, C.c_uint]
+    lib.bplx_score_grid_ex.restype = i
     lib.bplx_score_grid_host.argtypes = [C.POINTER(Samples), C.POINTER(Fixtures), i, C.c_float, vp, vp]
     lib.bplx_score_grid_host.restype = i
     lib.bplx_reload_env.argtypes = []

@@ -385,6 +385,11 @@ size_t bplx_score_grid_workspace_bytes(const bplx_samples* s, const bplx_fixture
 
 int bplx_score_grid(const bplx_samples* s, const bplx_fixtures* f, int max_goals, float scale, float* grid,
                     float* outcome, void* workspace, size_t workspace_bytes, void* stream) {
+  return bplx_score_grid_ex(s, f, max_goals, scale, grid, outcome, workspace, workspace_bytes, stream, 0u);
+}
+
+int bplx_score_grid_ex(const bplx_samples* s, const bplx_fixtures* f, int max_goals, float scale, float* grid,
+                       float* outcome, void* workspace, size_t workspace_bytes, void* stream, unsigned flags) {
   int rc = check_grid_args(s, f, max_goals);
   if (rc != BPLX_OK) return rc;
   BPLX_REQUIRE(grid != nullptr, BPLX_E_INVALID, "grid is NULL");
@@ -414,6 +419,7 @@ int bplx_score_grid(const bplx_samples* s, const bplx_fixtures* f, int max_goals
                                         ((size_t)gp.S * gp.row_floats * 4 + 255) / 256 * 256);
   gp.grid = grid;
   gp.outcome = outcome;
+  gp.reuse_tables = (flags & BPLX_GRID_REUSE_TABLES) ? 1 : 0;
   return launch_score_grid(gp, static_cast<cudaStream_t>(stream));
 }
 

@@ -397,7 +397,7 @@ int launch_score_grid(const GridParams& gp, cudaStream_t stream) {
   const size_t smem = 128 + (stage_bytes > epi_bytes ? stage_bytes : epi_bytes);
   BPLX_REQUIRE(smem <= 227 * 1024, BPLX_E_UNSUPPORTED, "score grid needs %zu bytes of shared memory per CTA (max %d)", smem,
                227 * 1024);
-  {
+  if (!gp.reuse_tables) {
     const long long n = (long long)gp.S * (gp.T + gp.Cf + 1);
     score_grid_tables<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(gp);
     BPLX_CUDA(cudaGetLastError());

@@ -15,6 +15,7 @@ struct GridParams {
   int ns_stage;    // samples per stage
   int ntab;        // per-team tables in a sample row: 2 (P1, Q1) or 3 (+ P0, models with neutral venues)
   int row_floats;  // floats per sample row of `table` (a multiple of 4: rows are 16-byte aligned for the bulk copies)
+  int reuse_tables;  // the table in the workspace is already built for these samples
   float scale;
   // posterior samples, [S, T] row-major (home_advantage of DIXON_COLES: [S])
   const float *attack, *defence, *ha, *aa, *hd, *ad, *conf, *corr;

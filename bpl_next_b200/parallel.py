@@ -99,7 +99,7 @@ class ShardedScoreGrid:
         a, b = self.ranges[i]
         kw = dict(scale=self.scale, want_outcome=True)
         if self.cuda:
-            kw.update(grid=self.grid[a:b], outcome=self.outcome[a:b], workspace=self.ws)
+            kw.update(grid=self.grid[a:b], outcome=self.outcome[a:b], workspace=self.ws, reuse_tables=i > 0)
             self.fn(self.model, self.samples, self.fx[i], self.max_goals, **kw)
         else:  # CPU stand-in of the tests
             gr, oc = self.fn(self.model, self.samples, self.fx[i], self.max_goals, **kw)

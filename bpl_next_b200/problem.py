@@ -179,9 +179,10 @@ def score_grid_workspace_bytes(model: str, samples: Dict[str, torch.Tensor], fix
 
 def score_grid(model: str, samples: Dict[str, torch.Tensor], fixtures: Dict[str, torch.Tensor], max_goals: int,
                scale: Optional[float] = None, want_outcome: bool = True, workspace=None, grid=None, outcome=None,
-               stream=None):
+               stream=None, reuse_tables: bool = False):
     """Device path: posterior arrays ``[S, T]`` float32 and fixture index tensors on the GPU.
-    Returns ``(grid [F, g, g], outcome [F, 3] or None)``; ``scale`` defaults to ``1/S``."""
+    Returns ``(grid [F, g, g], outcome [F, 3] or None)``; ``scale`` defaults to ``1/S``.  ``reuse_tables``: the
+    ``workspace`` passed in still holds the exponential tables a previous call built from these very samples."""
     lib = _abi.lib()
     keep = []
 
@@ -207,9 +208,9 @@ def score_grid(model: str, samples: Dict[str, torch.Tensor], fixtures: Dict[str,
     if want_outcome and outcome is None:
         outcome = torch.empty((f.num_fixtures, 3), dtype=torch.float32, device=dev)
     scale = 1.0 / s.num_samples if scale is None else scale
-    _abi.check(lib.bplx_score_grid(C.byref(s), C.byref(f), max_goals, C.c_float(scale), _dptr(grid),
-                                   _dptr(outcome) if want_outcome else None, _dptr(workspace), workspace.numel(),
-                                   _stream_ptr(stream)))
+    _abi.check(lib.bplx_score_grid_ex(C.byref(s), C.byref(f), max_goals, C.c_float(scale), _dptr(grid),
+                                      _dptr(outcome) if want_outcome else None, _dptr(workspace), workspace.numel(),
+                                      _stream_ptr(stream), 1 if reuse_tables else 0))
     return grid, (outcome if want_outcome else None)
 
 

@@ -200,6 +200,15 @@ int bplx_score_grid(const bplx_samples* s, const bplx_fixtures* f, int max_goals
                     float* outcome,  /* device [F, 3] or NULL */
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * Same, with flags.  BPLX_GRID_REUSE_TABLES: the workspace still holds the per-(sample, team) exponential tables a previous
+ * bplx_score_grid[_ex] call built from THESE samples (same arrays, same shapes, same workspace pointer): skip the table
+ * pre-pass.  For callers that cut the fixtures into ranges (e.g. to overlap a cross-GPU all-reduce with the next range).
+ */
+#define BPLX_GRID_REUSE_TABLES 1u
+int bplx_score_grid_ex(const bplx_samples* s, const bplx_fixtures* f, int max_goals, float scale, float* grid,
+                       float* outcome, void* workspace, size_t workspace_bytes, void* stream, unsigned flags);
+
 /* host-buffer variant: every pointer in s / f / grid / outcome is a HOST pointer. */
 int bplx_score_grid_host(const bplx_samples* s, const bplx_fixtures* f, int max_goals, float scale,
                          float* grid, float* outcome);

@@ -110,3 +110,22 @@ def test_grid_config5_sample_sharding_is_additive():
     sub = slice(0, 40)
     g_o, o_o = oracle_grid("neutral_wc", s, {k: v[sub] for k, v in fx.items()}, 10)
     np.testing.assert_allclose(full[sub].cpu().numpy(), g_o, rtol=0, atol=ATOL)
+
+
+def test_grid_fixture_ranges_reuse_the_tables():
+    """ShardedScoreGrid cuts the fixtures into ranges (to overlap the all-reduce of one range with the next range's
+    kernel); ranges after the first reuse the exponential tables in the workspace (BPLX_GRID_REUSE_TABLES): same grid."""
+    import torch
+    from bpl_next_b200 import parallel, score_grid
+
+    s, fx = datasets.config_5(S=640, F=3000)
+    ds = {k: torch.from_numpy(v).cuda() for k, v in s.items()}
+    dfx = {k: torch.from_numpy(v).cuda() for k, v in fx.items()}
+    full, out_full = score_grid("neutral_wc", ds, dfx, 10)
+    sg = parallel.ShardedScoreGrid("neutral_wc", ds, dfx, 10, num_samples_total=640, chunks=3)
+    grid, out = sg.run()
+    torch.cuda.synchronize()
+    assert len(sg.ranges) == 3
+    assert torch.equal(grid, full) and torch.equal(out, out_full)
+    t = sg.run(timed=True)
+    assert len(t) == 3 and t[0] > 0
