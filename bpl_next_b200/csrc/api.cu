@@ -31,7 +31,7 @@ void reload_env_switches() {
   EnvSwitches e;
   e.no_pdl = getenv("BPLX_NO_PDL") != nullptr;
   e.nuts_generic = getenv("BPLX_NUTS_GENERIC") != nullptr;
-  if (const char* v = getenv("BPLX_FEW_MAX")) e.few_max = atoi(v);
+  e.no_tail_split = getenv("BPLX_NO_TAIL_SPLIT") != nullptr;
   if (const char* v = getenv("BPLX_SPLIT")) e.split = atoi(v);
   if (const char* v = getenv("BPLX_HOST_CHUNKS")) e.host_chunks = atoi(v);
   g_env = e;
@@ -128,18 +128,6 @@ static int enqueue(const bplx_problem* p, int C, int layout, int ld, const float
     for (int i = 0; i < kNumSplits; i++)
       if ((1 << i) == want && p->s1[i] && (i == 0 || p->max_clusters[i] > 0)) si = i;
   }
-  // a handful of chains: one CTA per chain, lanes over the entries of a list piece (logdensity_few.cu)
-  {
-    const int few_max = env_switches().few_max >= 0 ? env_switches().few_max : p->few_max_default;
-    if (env_switches().split == 0 && C <= few_max && logdensity_few_supported(kp)) {
-      kp.split = 1;
-      kp.stream1 = p->s1[0];
-      kp.stream2 = p->s2[0];
-      kp.warp_b1 = p->wb1[0];
-      kp.warp_b2 = p->wb2[0];
-      return launch_logdensity_few(kp, p->wb[0], stream);
-    }
-  }
   kp.split = 1 << si;
   kp.stream1 = p->s1[si];
   kp.stream2 = p->s2[si];
@@ -226,11 +214,6 @@ int bplx_problem_create(const bplx_problem_desc* desc, bplx_problem** out) {
   p->max_clusters[0] = 1 << 30;
   if (kp.model != BPLX_DYNAMIC)
     for (int i = 1; i < kNumSplits; i++) p->max_clusters[i] = p->s1[i] ? logdensity_max_clusters(kp, 1 << i) : 0;
-  {  // K1s pays while its CTAs (one per chain) still find free SMs (measured crossover)
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
-    p->few_max_default = (kp.model != BPLX_DYNAMIC && hp.stream1.size() < (1u << 24)) ? kFewMaxPerSm * sms : 0;
-  }
   p->stats[0] = desc->num_matches;
   p->stats[1] = hp.n1;
   p->stats[2] = hp.n1_padded;

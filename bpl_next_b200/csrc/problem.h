@@ -24,7 +24,6 @@ struct bplx_problem {
   const uint32_t* wb2[bplx::kNumSplits] = {};
   bplx::WarpBounds wb[bplx::kNumSplits] = {};  // host copies of wb1 / wb2 (static models): passed by value at launch
   int max_clusters[bplx::kNumSplits] = {0, 0, 0, 0};
-  int few_max_default = 0;  // chain counts up to this take the one-CTA-per-chain kernel (K1s)
   std::vector<void*> dev_allocs;
   // host-variant staging (lazily grown, guarded by mu)
   std::mutex mu;
@@ -47,8 +46,5 @@ int launch_logdensity(const KernelParams& kp, const WarpBounds& wb, cudaStream_t
 int logdensity_set_attributes(const KernelParams& kp);
 int logdensity_max_clusters(const KernelParams& kp, int split);  // co-resident clusters of `split` CTAs, 0 if unsupported
 int launch_logdensity_dynamic(const KernelParams& kp, cudaStream_t stream);
-constexpr int kFewMaxPerSm = 0;  // K1s for C <= kFewMaxPerSm * SMs chains (0: only when BPLX_FEW_MAX asks for it)
-bool logdensity_few_supported(const KernelParams& kp);
-int launch_logdensity_few(const KernelParams& kp, const WarpBounds& wb, cudaStream_t stream);
 int logdensity_dynamic_set_attributes();
 }  // namespace bplx

@@ -318,75 +318,3 @@ def test_likelihood_only_entry_point(model, kw, chain_minor):
     np.testing.assert_allclose(cc.cpu().numpy(), cc_o.detach().numpy(), rtol=1e-4, atol=1e-6)
     err = np.abs(g - g_o.numpy()) / np.abs(g_o.numpy()).max(axis=1, keepdims=True)
     assert err.max() < GRAD_RTOL, err.max()
-
-
-FEW_CASES = [c for c in CASES if c[0] != "dynamic"] + [("dixon_coles", dict(T=21, M=500)), ("extended", dict(weighted=True, K=5, T=9, M=300))]
-
-
-@pytest.mark.parametrize("model,kw", FEW_CASES)
-@pytest.mark.parametrize("radius", [0.5, 2.0])
-def test_few_chain_kernel(model, kw, radius, bplx_env):
-    """K1s (csrc/logdensity_few.cu): one CTA per chain, lanes over the entries of a list piece -- the few-chain regime of
-    the same entry point.  Forced for every chain count here; chain-major and chain-minor; also the likelihood-only view."""
-    import torch
-    from bpl_next_b200 import Problem
-
-    bplx_env(BPLX_FEW_MAX=1000000)
-    arr = H.small_problem(model, seed=3, **kw)
-    p = Problem(arr)
-    for C, chain_minor in ((1, False), (45, True), (7, False)):
-        theta = H.random_theta(p.D, C, seed=11 + C, radius=radius, dtype=np.float32)
-        t = torch.from_numpy(theta).cuda()
-        if chain_minor:
-            t = t.t().contiguous()
-        lp, grad, cc = p.logdensity(t, chain_minor=chain_minor)
-        torch.cuda.synchronize()
-        g = grad.t().contiguous() if chain_minor else grad
-        _check(arr, theta.astype(np.float64), lp.cpu().numpy(), g.cpu().numpy(), cc.cpu().numpy())
-    # bit-reproducible, and the same numbers (to float32 rounding) as the many-chain kernel
-    theta = H.random_theta(p.D, 33, seed=5, radius=radius, dtype=np.float32)
-    t = torch.from_numpy(theta).cuda()
-    a = [x.clone() for x in p.logdensity(t)]
-    b = p.logdensity(t)
-    torch.cuda.synchronize()
-    assert all(torch.equal(x, y) for x, y in zip(a, b))
-    bplx_env(BPLX_FEW_MAX=0)
-    c = p.logdensity(t)
-    torch.cuda.synchronize()
-    np.testing.assert_allclose(a[0].cpu().numpy(), c[0].cpu().numpy(), rtol=2e-6)
-    scale = c[1].abs().max(dim=1, keepdim=True).values
-    assert float(((a[1] - c[1]).abs() / scale).max()) < 2e-5
-    p.close()
-
-
-def test_few_chain_kernel_reference_source_and_likelihood(bplx_env):
-    """K1s against the reference-source vectors of configs[2] (T = 220, M = 40,000, weighted, confederations) and through
-    the likelihood-only entry point."""
-    import os
-    import torch
-    from bpl_next_b200 import Problem
-
-    bplx_env(BPLX_FEW_MAX=1000000)
-    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_shim_config_3.npz"))
-    arr = H.from_training_data("neutral_wc", datasets.config_3(), epsilon=0.1)
-    p = Problem(arr)
-    lp, grad, _ = p.logdensity(torch.from_numpy(z["theta"].astype(np.float32)).cuda())
-    torch.cuda.synchronize()
-    np.testing.assert_allclose(lp.cpu().numpy(), z["lp"], rtol=1e-5)
-    scale = np.abs(z["grad"]).max(axis=1, keepdims=True)
-    assert (np.abs(grad.cpu().numpy() - z["grad"]) / scale).max() < 1e-4
-    p.close()
-    arr = H.small_problem("neutral_wc", seed=6, multi_conf=True, T=13, M=400)
-    p = Problem(arr)
-    lay = p.loglik_layout
-    Dl = sum(c for _, c, _ in lay.values())
-    rng = np.random.default_rng(12)
-    tabs = rng.normal(0, 0.5, (9, Dl)).astype(np.float32)
-    tabs[:, lay["corr_coef_raw"][0]] = rng.uniform(0.05, 0.95, 9)
-    t = torch.from_numpy(tabs).cuda()
-    a = p.loglik(t)
-    bplx_env(BPLX_FEW_MAX=0)
-    b = p.loglik(t)
-    torch.cuda.synchronize()
-    np.testing.assert_allclose(a[0].cpu().numpy(), b[0].cpu().numpy(), rtol=2e-6)
-    assert float(((a[1] - b[1]).abs() / b[1].abs().max(dim=1, keepdim=True).values).max()) < 2e-5
