@@ -506,33 +506,65 @@ __global__ void __launch_bounds__(kMaxWarpsDyn * 32, 1) logdensity_dynamic_kerne
     }
   }
   float fix_md = 0.0f;  // what the fix-up adds to sum_t d/d defence[0, t] (mean_defence) -- and per team for the coefficients
+  // the (which, side) items: team and what the fix-up adds to its raw (att, def, venue effect) gradients
+  float f_dra[4], f_drd[4], f_drx[4][4];
+#pragma unroll
+  for (int it = 0; it < 4; it++) {
+    f_dra[it] = f_drd[it] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) f_drx[it][i] = 0.0f;
+    if (f_gw[it >> 1] >= 0) fold_fixup(fx, it >> 1, it & 1, f_dra[it], f_drd[it], f_drx[it]);
+  }
   for (int j = warp; j < G; j += W) {
+    // all loads of the gameweek first (they are independent), then the updates: one round trip per gameweek instead of
+    // one per entry; the scale factors come from the hyper-parameter table
+    const float* hj = hyp + (size_t)j * 16 * hs;
+    const float sa = hj[8 * hs], sd = hj[9 * hs];
+    float za[4], zd[4], gza[4], gzd[4];
+    bool on[4];
 #pragma unroll
-    for (int which = 0; which < 2; which++) {
-      if (f_gw[which] < j) continue;  // (also: no fix-up for this chain)
+    for (int it = 0; it < 4; it++) {
+      on[it] = f_gw[it >> 1] >= j && !kp.as_written && ln.active;
+      const int jt = j * T + f_team[it >> 1][it & 1];
+      za[it] = on[it] ? ln.ld(o.za + jt) : 0.0f;
+      zd[it] = on[it] ? ln.ld(o.zd + jt) : 0.0f;
+      gza[it] = on[it] ? *ln.g(o.za + jt) : 0.0f;
+      gzd[it] = on[it] ? *ln.g(o.zd + jt) : 0.0f;
+    }
+    float d_lsa = 0.0f, d_lsd = 0.0f;
 #pragma unroll
-      for (int side = 0; side < 2; side++) {
-        float dra = 0.0f, drd = 0.0f, drx[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        fold_fixup(fx, which, side, dra, drd, drx);
-        const int t = f_team[which][side], jt = j * T + t;
-        if (j == f_gw[which]) {  // the venue effects of the match's own gameweek
+    for (int it = 0; it < 4; it++) {
+      if (!on[it]) continue;
+      // the two arg-max matches often share a team (the strongest attack is in both): one update per distinct team
+      float dra = f_dra[it], drd = f_drd[it];
 #pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const float sig = expf(ln.ld(o.log_std[i] + j));
-            if (ln.active) {
-              *ln.g(o.dec[i] + jt) += sig * drx[i];
-              *ln.g(o.mean[i] + j) += drx[i];
-              *ln.g(o.log_std[i] + j) += sig * ln.ld(o.dec[i] + jt) * drx[i];
-            }
-          }
+      for (int it2 = it + 1; it2 < 4; it2++) {
+        if (on[it2] && f_team[it2 >> 1][it2 & 1] == f_team[it >> 1][it & 1]) {
+          dra += f_dra[it2];
+          drd += f_drd[it2];
+          on[it2] = false;
         }
-        if (!kp.as_written && ln.active) {  // attack / defence of gameweek j <= the match's: every walk step up to it
-          const float sa = expf(ln.ld(o.log_std_attack + j)), sd = expf(ln.ld(o.log_std_defence + j));
-          *ln.g(o.za + jt) += sa * dra;
-          *ln.g(o.zd + jt) += sd * drd;
-          *ln.g(o.log_std_attack + j) += sa * ln.ld(o.za + jt) * dra;
-          *ln.g(o.log_std_defence + j) += sd * ln.ld(o.zd + jt) * drd;
-        }
+      }
+      const int jt = j * T + f_team[it >> 1][it & 1];
+      *ln.g(o.za + jt) = fmaf(sa, dra, gza[it]);
+      *ln.g(o.zd + jt) = fmaf(sd, drd, gzd[it]);
+      d_lsa = fmaf(sa * za[it], dra, d_lsa);
+      d_lsd = fmaf(sd * zd[it], drd, d_lsd);
+    }
+    if (d_lsa != 0.0f || d_lsd != 0.0f) {
+      *ln.g(o.log_std_attack + j) += d_lsa;
+      *ln.g(o.log_std_defence + j) += d_lsd;
+    }
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+      if (f_gw[it >> 1] != j || !ln.active) continue;  // the venue effects of the match's own gameweek
+      const int jt = j * T + f_team[it >> 1][it & 1];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const float sig = hj[(4 + i) * hs];
+        *ln.g(o.dec[i] + jt) += sig * f_drx[it][i];
+        *ln.g(o.mean[i] + j) += f_drx[it][i];
+        *ln.g(o.log_std[i] + j) += sig * ln.ld(o.dec[i] + jt) * f_drx[it][i];
       }
     }
   }
