@@ -76,6 +76,8 @@ def declare(lib):
     lib.bplx_problem_layout.restype = C.c_char_p
     lib.bplx_problem_stats.argtypes = [vp, C.POINTER(C.c_longlong), i]
     lib.bplx_problem_stats.restype = i
+    lib.bplx_problem_warp_stats.argtypes = [vp, C.POINTER(C.c_longlong), i]
+    lib.bplx_problem_warp_stats.restype = i
     lib.bplx_logdensity_workspace_bytes.argtypes = [vp, i]
     lib.bplx_logdensity_workspace_bytes.restype = sz
     lib.bplx_logdensity_fwdbwd.argtypes = [vp, i, i, i, vp, vp, vp, vp, vp, sz, vp]

@@ -128,12 +128,37 @@ static int enqueue(const bplx_problem* p, int C, int layout, int ld, const float
     for (int i = 0; i < kNumSplits; i++)
       if ((1 << i) == want && p->s1[i] && (i == 0 || p->max_clusters[i] > 0)) si = i;
   }
-  kp.split = 1 << si;
-  kp.stream1 = p->s1[si];
-  kp.stream2 = p->s2[si];
-  kp.warp_b1 = p->wb1[si];
-  kp.warp_b2 = p->wb2[si];
-  return kp.model == BPLX_DYNAMIC ? launch_logdensity_dynamic(kp, stream) : launch_logdensity(kp, p->wb[si], stream, pdl);
+  auto use_split = [&](int i) {
+    kp.split = 1 << i;
+    kp.stream1 = p->s1[i];
+    kp.stream2 = p->s2[i];
+    kp.warp_b1 = p->wb1[i];
+    kp.warp_b2 = p->wb2[i];
+  };
+  use_split(si);
+  kp.group0 = 0;
+  kp.ngroups = groups;
+  if (kp.model == BPLX_DYNAMIC) return launch_logdensity_dynamic(kp, stream);
+  // Tail split: the kernel holds one CTA per SM, so `groups` CTAs run in waves of `sm_count`; when the last, partial
+  // wave is small enough, its groups go to a second launch with 2, 4 or 8 CTAs (a cluster) per group, which fills the
+  // SMs the wave would leave idle and ends sooner (configs[2] at 16,384 chains: 512 groups = 3 waves + 68 groups).
+  int ti = 0;
+  const int rest = p->sm_count > 0 ? groups % p->sm_count : 0;
+  if (si == 0 && rest > 0 && rest < groups && !env_switches().split && !env_switches().no_tail_split) {
+    for (int i = kNumSplits - 1; i >= 1; i--)
+      if (p->s1[i] && (1 << i) <= kp.split_hint && rest <= p->max_clusters[i] && rest * (1 << i) <= p->sm_count) {
+        ti = i;
+        break;
+      }
+  }
+  if (ti == 0) return launch_logdensity(kp, p->wb[si], stream, pdl);
+  kp.ngroups = groups - rest;
+  int rc = launch_logdensity(kp, p->wb[0], stream, pdl);
+  if (rc != BPLX_OK) return rc;
+  use_split(ti);
+  kp.group0 = groups - rest;
+  kp.ngroups = rest;
+  return launch_logdensity(kp, p->wb[ti], stream, pdl);
 }
 
 }  // namespace bplx
@@ -211,6 +236,7 @@ int bplx_problem_create(const bplx_problem_desc* desc, bplx_problem** out) {
 #undef UP
   rc = kp.model == BPLX_DYNAMIC ? logdensity_dynamic_set_attributes() : logdensity_set_attributes(kp);
   if (rc != BPLX_OK) return fail(rc);
+  if (cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, p->device) != cudaSuccess) p->sm_count = 0;
   p->max_clusters[0] = 1 << 30;
   if (kp.model != BPLX_DYNAMIC)
     for (int i = 1; i < kNumSplits; i++) p->max_clusters[i] = p->s1[i] ? logdensity_max_clusters(kp, 1 << i) : 0;
@@ -222,6 +248,41 @@ int bplx_problem_create(const bplx_problem_desc* desc, bplx_problem** out) {
   p->stats[5] = kp.smem_total;
   p->stats[6] = kp.nwarps;
   p->stats[7] = kp.V;
+  if (kp.model != BPLX_DYNAMIC) {  // what each warp of the split-1 plan walks (plan tuning)
+    p->warp_stats.assign((size_t)kp.nwarps * 12, 0);
+    for (int phase = 0; phase < 2; phase++) {
+      const std::vector<unsigned char>& S = phase ? hp.stream2 : hp.stream1;
+      const std::vector<uint32_t>& wb = phase ? hp.warp_b2 : hp.warp_b1;
+      const size_t esz = (phase == 0 && kp.clip) ? sizeof(EntryClip) : sizeof(Entry);
+      const uint32_t minp = phase ? kp.min_piece2 : kp.min_piece1;
+      for (int w = 0; w < kp.nwarps && w + 1 < (int)wb.size(); w++) {
+        long long* o = &p->warp_stats[(size_t)w * 12 + phase * 6];
+        const uint32_t len = wb[w + 1] - wb[w];
+        o[5] = (len + kp.stage_bytes - 1) / kp.stage_bytes;
+        for (uint32_t st = 0; st < len; st += kp.stage_bytes) {
+          uint32_t a = wb[w] + st;
+          const uint32_t aend = wb[w] + std::min(len, st + kp.stage_bytes);
+          while (a + minp <= aend) {
+            ListHdr H;
+            memcpy(&H, &S[a], sizeof H);
+            if (H.n0 + H.n1 + H.n2 == 0) break;  // stage padding
+            const bool home = (H.kind & 1) == 0;
+            if (phase == 0) {
+              o[home ? 0 : 1]++;
+              o[home ? 2 : 3] += H.n0;
+            } else {
+              o[0]++;
+              o[1] += H.n0;
+              o[2] += H.n1;
+              o[3] += H.n2;
+            }
+            if (H.flags & kTeamFirst) o[4]++;
+            a += (uint32_t)sizeof(ListHdr) + (uint32_t)((H.n0 + H.n1 + H.n2) * esz);
+          }
+        }
+      }
+    }
+  }
   *out = p;
   return BPLX_OK;
 }
@@ -248,6 +309,13 @@ int bplx_problem_stats(const bplx_problem* p, long long* out, int n) {
   BPLX_REQUIRE(p && out, BPLX_E_INVALID, "problem / out is NULL");
   for (int i = 0; i < n && i < 8; i++) out[i] = p->stats[i];
   return n < 8 ? n : 8;
+}
+
+int bplx_problem_warp_stats(const bplx_problem* p, long long* out, int n) {
+  BPLX_REQUIRE(p && out, BPLX_E_INVALID, "problem / out is NULL");
+  const int have = (int)p->warp_stats.size();
+  for (int i = 0; i < n && i < have; i++) out[i] = p->warp_stats[i];
+  return n < have ? n : have;
 }
 
 size_t bplx_logdensity_workspace_bytes(const bplx_problem* p, int num_chains) {

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logdensity_kernel(const __g
   const ThetaOffsets& o = kp.off;
   const int S = kp.split;  // CTAs of the cluster that shares this group of chains (1: no cluster)
   const int crank = S > 1 ? (int)cg::this_cluster().block_rank() : 0;
-  const int group = (int)blockIdx.x / S;
+  const int group = kp.group0 + (int)blockIdx.x / S;
   const int vwarp = crank * W + warp, VW = S * W;  // virtual warp: owner of teams / streams across the cluster
   auto sync_all = [&]() {
     if (S > 1) cg::this_cluster().sync();
@@ -776,9 +776,8 @@ static int launch_t(const KernelParams& kp, const WarpBounds& wb, cudaStream_t s
     BPLX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return BPLX_OK;
   }
-  const int groups = (kp.C + kChains - 1) / kChains;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(groups * kp.split));
+  cfg.gridDim = dim3((unsigned)(kp.ngroups * kp.split));
   cfg.blockDim = dim3((unsigned)(kp.nwarps * 32));
   cfg.dynamicSmemBytes = kp.smem_total;
   cfg.stream = stream;

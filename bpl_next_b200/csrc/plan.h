@@ -144,6 +144,7 @@ struct KernelParams {
   int dyn_hyp_ws;                         // DYNAMIC: the hyper-parameter table lives in the workspace ([G][16][Cpad] behind the
                                           // prefix sums) because it does not fit in shared memory
   int split_hint;                // largest cluster size worth using (small plans are latency-bound: 1)
+  int group0, ngroups;           // chain groups of this launch: [group0, group0 + ngroups) (a call may take two launches)
   int force_clip_forms;          // testing (env BPLX_CLIP_FORMS at create): bit 0 / bit 1 = phase 1 / phase 2 always take the
                                  // clipping form of the arithmetic, even when no rate of the chains is near the clip
   ThetaOffsets off;

@@ -36,7 +36,9 @@ struct bplx_problem {
   cudaStream_t host_in = nullptr, host_out = nullptr;  // H2D / D2H copies of the host variant (pipelined by chunk)
   cudaEvent_t host_ev[16] = {};                     // [2 * chunk]: chunk uploaded, chunk computed
   // plan statistics (for DESIGN/bench reporting)
+  int sm_count = 0;
   long long stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  std::vector<long long> warp_stats;  // [warps][12], see bplx_problem_warp_stats
 };
 
 namespace bplx {

@@ -79,7 +79,8 @@ class Problem:
         """Enqueue log-density + gradient.  ``theta`` is ``[C, D]`` (chain-major) or ``[D, C]``
         (``chain_minor=True``), float32, on the GPU; rows may be padded (a view with unit inner stride: the row pitch is
         passed as the leading dimension, and ``grad`` must have the same pitch).  Returns ``(lp, grad, corr_coef)``."""
-        assert theta.is_cuda and theta.dtype == torch.float32 and theta.dim() == 2 and theta.stride(1) == 1
+        assert theta.is_cuda and theta.dtype == torch.float32 and theta.dim() == 2
+        assert theta.stride(1) == 1 or theta.shape[1] == 1  # (the stride of a one-element dimension means nothing)
         if chain_minor:
             D, Cn = theta.shape
         else:

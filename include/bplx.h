@@ -108,6 +108,14 @@ const char* bplx_problem_layout(const bplx_problem* p);
  */
 int bplx_problem_stats(const bplx_problem* p, long long* out, int n);
 
+/*
+ * What each warp of a CTA walks (static models, the plan for one CTA per group of 32 chains): out[w*12 + 0..5] =
+ * phase-1 {home-form pieces, away-form pieces, home-form entries, away-form entries, teams, stages}, out[w*12 + 6..11]
+ * = phase-2 {pieces, tau = 1 - c X Y entries, tau = 1 + c X entries, tau = 1 + c Y entries, teams, stages} (padded
+ * counts).  Returns the number of values written (<= n); 0 for BPLX_DYNAMIC.  For tuning the plan's cost model.
+ */
+int bplx_problem_warp_stats(const bplx_problem* p, long long* out, int n);
+
 /* ---- log-density + gradient: replaces value_and_grad(potential_fn) per leapfrog ---------- */
 /* (numpyro potential_energy of `_model`; the returned lp is the log JOINT density, i.e. MINUS
  * the potential energy, and grad is d lp / d theta.) */

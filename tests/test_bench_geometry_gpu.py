@@ -61,7 +61,8 @@ def test_config_1_at_4096_chains():
 
 
 def test_config_2_at_one_full_wave_and_more():
-    """configs[2]: NeutralWC, M = 40,000, T = 220; 4,768 chains = 149 CTAs > one wave of 148 SMs (split 1)."""
+    """configs[2]: NeutralWC, M = 40,000, T = 220; 4,768 chains = 149 groups > one wave of 148 SMs: 148 CTAs, then the
+    last group as a cluster (tail split)."""
     z = np.load(os.path.join(GOLDEN, "ref_shim_config_3.npz"))
     arr = H.from_training_data("neutral_wc", datasets.config_3(), epsilon=0.1)
     slots, idx, (th, lp, g, cc), st, fin = _run_batch(arr, 4768, z["theta"], seed=42)
@@ -118,3 +119,35 @@ def test_grid_config_4_full_size():
 def test_grid_config_4_default_max_goals():
     """The reference's default max_goals = 15 (bpl/base.py:15,78) at F = 10,000 (S reduced to keep the oracle fast)."""
     _grid_case(15, 2048, 10000, nfix=32)
+
+
+def test_tail_split_matches_the_single_launch(bplx_env):
+    """216 groups of configs[2] chains on 148 SMs: one full wave of single CTAs, then 68 groups as 2-CTA clusters in a
+    second launch.  Same numbers as the one-launch plan (BPLX_NO_TAIL_SPLIT=1), to the rounding of the different
+    cross-warp summation order; tail chains against the oracle."""
+    import torch
+    from bpl_next_b200 import Problem, _abi
+
+    arr = H.from_training_data("neutral_wc", datasets.config_3(), epsilon=0.1)
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    C = (sms + sms // 2 - 6) * 32 - 5  # (a ragged last group as well)
+    rng = np.random.default_rng(77)
+    outs = []
+    for env in ({"BPLX_NO_TAIL_SPLIT": None}, {"BPLX_NO_TAIL_SPLIT": "1"}):
+        bplx_env(**env)
+        p = Problem(arr)
+        theta = rng.uniform(-2, 2, (C, p.D)).astype(np.float32) if not outs else theta
+        t = torch.from_numpy(np.ascontiguousarray(theta.T)).cuda()
+        n0 = _abi.lib().bplx_launch_count()
+        lp, grad, cc = p.logdensity(t, chain_minor=True)
+        torch.cuda.synchronize()
+        outs.append((lp.cpu().numpy(), grad.cpu().numpy().T, cc.cpu().numpy(), _abi.lib().bplx_launch_count() - n0))
+        p.close()
+    assert outs[0][3] == 2 and outs[1][3] == 1  # two launches with the tail split, one without
+    np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=2e-6)
+    np.testing.assert_allclose(outs[0][2], outs[1][2], rtol=1e-5, atol=1e-7)
+    scale = np.abs(outs[1][1]).max(axis=1, keepdims=True)
+    assert (np.abs(outs[0][1] - outs[1][1]) / scale).max() < 1e-5
+    assert np.array_equal(outs[0][0][: sms * 32], outs[1][0][: sms * 32])  # the full wave is the same launch
+    idx = np.array([sms * 32, sms * 32 + 31, C - 40, C - 1])
+    _check(arr, theta[idx], outs[0][0][idx], outs[0][1][idx], outs[0][2][idx])
