@@ -32,6 +32,7 @@ void reload_env_switches() {
   e.no_pdl = getenv("BPLX_NO_PDL") != nullptr;
   e.nuts_generic = getenv("BPLX_NUTS_GENERIC") != nullptr;
   e.no_tail_split = getenv("BPLX_NO_TAIL_SPLIT") != nullptr;
+  e.no_host_transpose = getenv("BPLX_NO_HOST_TRANSPOSE") != nullptr;
   if (const char* v = getenv("BPLX_SPLIT")) e.split = atoi(v);
   if (const char* v = getenv("BPLX_HOST_CHUNKS")) e.host_chunks = atoi(v);
   g_env = e;
@@ -159,6 +160,31 @@ static int enqueue(const bplx_problem* p, int C, int layout, int ld, const float
   kp.group0 = groups - rest;
   kp.ngroups = rest;
   return launch_logdensity(kp, p->wb[ti], stream, pdl);
+}
+
+// out[c][r] = in[r][c] for an R x Cc matrix (row pitches ldi, ldo): the host entry point takes and returns [chains, D]
+// arrays (what the reference's vmapped potential sees), the kernel's native layout is [D, chains].
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int Cc,
+                                                        size_t ldi, size_t ldo) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < R && c < Cc) tile[j][threadIdx.x] = in[(size_t)r * ldi + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < R && c < Cc) out[(size_t)c * ldo + r] = tile[threadIdx.x][j];
+  }
+}
+static int launch_transpose(const float* in, float* out, int R, int Cc, size_t ldi, size_t ldo, cudaStream_t s) {
+  const dim3 grid((unsigned)((Cc + 31) / 32), (unsigned)((R + 31) / 32));
+  BPLX_REQUIRE(grid.y <= 65535u, BPLX_E_UNSUPPORTED, "transpose of %d rows", R);
+  transpose_kernel<<<grid, dim3(32, 8), 0, s>>>(in, out, R, Cc, ldi, ldo);
+  BPLX_CUDA(cudaGetLastError());
+  note_launch(1);
+  return BPLX_OK;
 }
 
 }  // namespace bplx
@@ -293,6 +319,8 @@ void bplx_problem_destroy(bplx_problem* p) {
   if (p->d_theta) cudaFree(p->d_theta);
   if (p->d_out) cudaFree(p->d_out);
   if (p->d_ws) cudaFree(p->d_ws);
+  if (p->d_tin) cudaFree(p->d_tin);
+  if (p->d_tout) cudaFree(p->d_tout);
   if (p->host_stream) cudaStreamDestroy(p->host_stream);
   if (p->host_in) cudaStreamDestroy(p->host_in);
   if (p->host_out) cudaStreamDestroy(p->host_out);
@@ -376,16 +404,39 @@ int bplx_logdensity_fwdbwd_host(bplx_problem* p, int C, const float* theta, floa
   float* d_cc = d_lp + C;
   // (only worth it when a chunk still fills the GPU: below ~16k chains K1 is latency-bound and chunking serialises it;
   //  measured on configs[1], 4,096 chains: 104 us in one piece, 138 us in four)
-  int nchunk = C >= 32768 ? 4 : (C >= 16384 ? 2 : 1);
-  if (const int want = env_switches().host_chunks)  // tuning: 1, 2 or 4 pipelined chunks
-    if (want == 1 || want == 2 || want == 4) nchunk = want;
+  int nchunk = C >= 32768 ? 8 : (C >= 16384 ? 4 : (C >= 8192 ? 2 : 1));
+  if (const int want = env_switches().host_chunks)  // tuning: 1, 2, 4, 8 or 16 pipelined chunks
+    if (want == 1 || want == 2 || want == 4 || want == 8 || want == 16) nchunk = want;
+  // Large batches go through the kernel's native chain-minor layout: a tiled transpose of theta before the kernel and of
+  // the gradient after it (two passes over HBM each, ~0.1 ms for configs[2] at 32,768 chains) instead of the kernel's
+  // strided per-chain reads (3.5 ms against 1.6 ms in the native layout).
+  const bool native = (size_t)C * D >= ((size_t)1 << 22) && !env_switches().no_host_transpose;
   if (nchunk == 1) {  // one piece: everything in order on one stream, no events (each costs microseconds at this scale)
     // lp and corr_coef are one coalesced 128-byte store per warp: when the caller's arrays are page-locked the kernel
     // writes them straight into host memory (posted PCIe writes) instead of two more copies of 6.6 us each
     float* k_lp = mapped_or(lp, d_lp);
     float* k_cc = corr_coef ? mapped_or(corr_coef, d_cc) : d_cc;
     BPLX_CUDA(cudaMemcpyAsync(p->d_theta, theta, (size_t)C * D * sizeof(float), cudaMemcpyHostToDevice, s));
-    int rc = enqueue(p, C, BPLX_CHAIN_MAJOR, (int)D, p->d_theta, k_lp, d_grad, k_cc, p->d_ws, p->d_ws_bytes, s);
+    int rc;
+    if (native) {
+      const int ldc = (C + 31) / 32 * 32;
+      if (ldc > p->tr_cap) {
+        if (p->d_tin) cudaFree(p->d_tin);
+        if (p->d_tout) cudaFree(p->d_tout);
+        p->d_tin = p->d_tout = nullptr;
+        p->tr_cap = 0;
+        BPLX_CUDA(cudaMalloc(&p->d_tin, (size_t)ldc * D * sizeof(float)));
+        BPLX_CUDA(cudaMalloc(&p->d_tout, (size_t)ldc * D * sizeof(float)));
+        p->tr_cap = ldc;
+      }
+      rc = launch_transpose(p->d_theta, p->d_tin, C, (int)D, D, (size_t)ldc, s);
+      if (rc != BPLX_OK) return rc;
+      rc = enqueue(p, C, BPLX_CHAIN_MINOR, ldc, p->d_tin, k_lp, p->d_tout, k_cc, p->d_ws, p->d_ws_bytes, s);
+      if (rc != BPLX_OK) return rc;
+      rc = launch_transpose(p->d_tout, d_grad, (int)D, C, (size_t)ldc, D, s);
+    } else {
+      rc = enqueue(p, C, BPLX_CHAIN_MAJOR, (int)D, p->d_theta, k_lp, d_grad, k_cc, p->d_ws, p->d_ws_bytes, s);
+    }
     if (rc != BPLX_OK) return rc;
     BPLX_CUDA(cudaMemcpyAsync(grad, d_grad, (size_t)C * D * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (k_lp == d_lp) BPLX_CUDA(cudaMemcpyAsync(lp, d_lp, (size_t)C * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -395,14 +446,49 @@ int bplx_logdensity_fwdbwd_host(bplx_problem* p, int C, const float* theta, floa
     return BPLX_OK;
   }
   const int per = ((C + nchunk - 1) / nchunk + 31) / 32 * 32;
-  for (int k = 0, c0 = 0; c0 < C; k++, c0 += per) {
-    const int n = C - c0 < per ? C - c0 : per;
+  if (native && per > p->tr_cap) {
+    if (p->d_tin) cudaFree(p->d_tin);
+    if (p->d_tout) cudaFree(p->d_tout);
+    p->d_tin = p->d_tout = nullptr;
+    p->tr_cap = 0;
+    BPLX_CUDA(cudaMalloc(&p->d_tin, (size_t)per * D * sizeof(float)));
+    BPLX_CUDA(cudaMalloc(&p->d_tout, (size_t)per * D * sizeof(float)));
+    p->tr_cap = per;
+  }
+  // chunk sizes: with four or more chunks the first and the last are cut in half -- while the first chunk uploads and the
+  // last downloads, the link runs in one direction only
+  int sizes[40], ns = 0, left = C;
+  auto push = [&](int n) {
+    n = n < left ? n : left;
+    if (n > 0) sizes[ns++] = n, left -= n;
+  };
+  if (nchunk >= 4) {
+    const int half = (per / 2 + 31) / 32 * 32;
+    push(half);
+    push(half);
+    while (left > per) push(per);
+    push((left / 2 + 31) / 32 * 32);
+    push(left);
+  } else {
+    while (left > 0) push(per);
+  }
+  for (int k = 0, c0 = 0; k < ns; c0 += sizes[k], k++) {
+    const int n = sizes[k];
     const size_t off = (size_t)c0 * D;
     BPLX_CUDA(cudaMemcpyAsync(p->d_theta + off, theta + off, (size_t)n * D * sizeof(float), cudaMemcpyHostToDevice, p->host_in));
     BPLX_CUDA(cudaEventRecord(p->host_ev[2 * k], p->host_in));
     BPLX_CUDA(cudaStreamWaitEvent(s, p->host_ev[2 * k], 0));
-    int rc = enqueue(p, n, BPLX_CHAIN_MAJOR, (int)D, p->d_theta + off, d_lp + c0, d_grad + off, d_cc + c0, p->d_ws,
-                     p->d_ws_bytes, s);
+    int rc;
+    if (native) {  // (the transposed buffers are shared by the chunks: everything that touches them is in order on `s`)
+      rc = launch_transpose(p->d_theta + off, p->d_tin, n, (int)D, D, (size_t)per, s);
+      if (rc != BPLX_OK) return rc;
+      rc = enqueue(p, n, BPLX_CHAIN_MINOR, per, p->d_tin, d_lp + c0, p->d_tout, d_cc + c0, p->d_ws, p->d_ws_bytes, s);
+      if (rc != BPLX_OK) return rc;
+      rc = launch_transpose(p->d_tout, d_grad + off, (int)D, n, (size_t)per, D, s);
+    } else {
+      rc = enqueue(p, n, BPLX_CHAIN_MAJOR, (int)D, p->d_theta + off, d_lp + c0, d_grad + off, d_cc + c0, p->d_ws,
+                   p->d_ws_bytes, s);
+    }
     if (rc != BPLX_OK) return rc;
     BPLX_CUDA(cudaEventRecord(p->host_ev[2 * k + 1], s));
     BPLX_CUDA(cudaStreamWaitEvent(p->host_out, p->host_ev[2 * k + 1], 0));

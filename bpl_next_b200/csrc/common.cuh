@@ -34,10 +34,11 @@ void note_launch(int n = 1);  // kernels enqueued by this library (bplx_launch_c
 
 // Testing / tuning switches from the environment, read ONCE (first use) and again only by bplx_reload_env() -- never per
 // launch:  BPLX_NO_PDL=1 (no programmatic dependent launch on the K1 / NUTS-step launches), BPLX_SPLIT=1|2|4|8 (CTAs
-// per chain group), BPLX_HOST_CHUNKS=1|2|4 (host entry point pipeline), BPLX_NUTS_GENERIC=1 (stage-by-stage step kernel),
-// BPLX_NO_TAIL_SPLIT=1 (no second, cluster-split launch for the last partial wave of chain groups).
+// per chain group), BPLX_HOST_CHUNKS=1|2|4|8|16 (host entry point pipeline), BPLX_NUTS_GENERIC=1 (stage-by-stage step kernel),
+// BPLX_NO_TAIL_SPLIT=1 (no second, cluster-split launch for the last partial wave of chain groups),
+// BPLX_NO_HOST_TRANSPOSE=1 (the host entry point runs the kernel on [chains, D] buffers as they come).
 struct EnvSwitches {
-  bool no_pdl = false, nuts_generic = false, no_tail_split = false;
+  bool no_pdl = false, nuts_generic = false, no_tail_split = false, no_host_transpose = false;
   int split = 0, host_chunks = 0;
 };
 const EnvSwitches& env_switches();

@@ -30,11 +30,13 @@ struct bplx_problem {
   int host_cap = 0;
   float *h_theta = nullptr, *h_out = nullptr;  // pinned
   float *d_theta = nullptr, *d_out = nullptr;
+  float *d_tin = nullptr, *d_tout = nullptr;    // one chunk of theta / grad in the kernel's native chain-minor layout
+  int tr_cap = 0;                               // ... their capacity in chains
   void* d_ws = nullptr;
   size_t d_ws_bytes = 0;
   cudaStream_t host_stream = nullptr;            // compute
   cudaStream_t host_in = nullptr, host_out = nullptr;  // H2D / D2H copies of the host variant (pipelined by chunk)
-  cudaEvent_t host_ev[16] = {};                     // [2 * chunk]: chunk uploaded, chunk computed
+  cudaEvent_t host_ev[48] = {};                     // [2 * chunk]: chunk uploaded, chunk computed
   // plan statistics (for DESIGN/bench reporting)
   int sm_count = 0;
   long long stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};

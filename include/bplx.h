@@ -223,7 +223,7 @@ int bplx_score_grid_host(const bplx_samples* s, const bplx_fixtures* f, int max_
 
 /* ---- misc --------------------------------------------------------------------------------- */
 /* The library reads its testing / tuning switches (BPLX_NO_PDL, BPLX_SPLIT, BPLX_HOST_CHUNKS, BPLX_NUTS_GENERIC,
- * BPLX_NO_TAIL_SPLIT) from the environment once, at first use -- never on a launch path; call this after changing them. */
+ * BPLX_NO_TAIL_SPLIT, BPLX_NO_HOST_TRANSPOSE) from the environment once, at first use -- never on a launch path; call this after changing them. */
 void bplx_reload_env(void);
 const char* bplx_last_error(void);
 int bplx_version(void);

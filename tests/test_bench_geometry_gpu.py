@@ -151,3 +151,32 @@ def test_tail_split_matches_the_single_launch(bplx_env):
     assert np.array_equal(outs[0][0][: sms * 32], outs[1][0][: sms * 32])  # the full wave is the same launch
     idx = np.array([sms * 32, sms * 32 + 31, C - 40, C - 1])
     _check(arr, theta[idx], outs[0][0][idx], outs[0][1][idx], outs[0][2][idx])
+
+
+def test_host_entry_point_through_the_native_layout(bplx_env):
+    """Large batches through bplx_logdensity_fwdbwd_host are transposed on the device to the kernel's [D, chains] layout
+    (and chunked so that copies and kernels overlap): same bits as the kernel run on the [chains, D] buffers directly,
+    in one piece and in two chunks, ragged chain counts included; eight small chunks (each few enough chains for the
+    cluster plans, which sum in another order) to rounding; a sample against the oracle."""
+    from bpl_next_b200 import Problem
+
+    arr = H.from_training_data("neutral_wc", datasets.config_3(), epsilon=0.1)
+    rng = np.random.default_rng(91)
+    for C, chunks in ((4101, None), (8200, None), (4101, 8)):
+        p = Problem(arr)
+        theta = rng.uniform(-2, 2, (C, p.D)).astype(np.float32)
+        outs = []
+        for env in ({"BPLX_NO_HOST_TRANSPOSE": None, "BPLX_HOST_CHUNKS": chunks},
+                    {"BPLX_NO_HOST_TRANSPOSE": "1", "BPLX_HOST_CHUNKS": 1}):
+            bplx_env(**env)
+            outs.append([x.copy() for x in p.logdensity_host(theta)])
+        if chunks is None:
+            for a, b in zip(outs[0], outs[1]):
+                assert np.array_equal(a, b)
+        else:
+            np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=2e-6)
+            np.testing.assert_allclose(outs[0][2], outs[1][2], rtol=1e-5, atol=1e-7)
+            assert (np.abs(outs[0][1] - outs[1][1]) / np.abs(outs[1][1]).max(axis=1, keepdims=True)).max() < 1e-5
+        idx = np.array([0, 31, 32, C // 2, C - 1])
+        _check(arr, theta[idx], outs[0][0][idx], outs[0][1][idx], outs[0][2][idx])
+        p.close()
