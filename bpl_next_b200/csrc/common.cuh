@@ -36,9 +36,9 @@ void note_launch(int n = 1);  // kernels enqueued by this library (bplx_launch_c
 // launch:  BPLX_NO_PDL=1 (no programmatic dependent launch on the K1 / NUTS-step launches), BPLX_SPLIT=1|2|4|8 (CTAs
 // per chain group), BPLX_HOST_CHUNKS=1|2|4|8|16 (host entry point pipeline), BPLX_NUTS_GENERIC=1 (stage-by-stage step kernel),
 // BPLX_NO_TAIL_SPLIT=1 (no second, cluster-split launch for the last partial wave of chain groups),
-// BPLX_NO_HOST_TRANSPOSE=1 (the host entry point runs the kernel on [chains, D] buffers as they come).
+// BPLX_NO_TRANSPOSE=1 (large [chains, D] batches are computed as they come, not through the native [D, chains] layout).
 struct EnvSwitches {
-  bool no_pdl = false, nuts_generic = false, no_tail_split = false, no_host_transpose = false;
+  bool no_pdl = false, nuts_generic = false, no_tail_split = false, no_transpose = false;
   int split = 0, host_chunks = 0;
 };
 const EnvSwitches& env_switches();

@@ -119,6 +119,11 @@ int bplx_problem_warp_stats(const bplx_problem* p, long long* out, int n);
 /* ---- log-density + gradient: replaces value_and_grad(potential_fn) per leapfrog ---------- */
 /* (numpyro potential_energy of `_model`; the returned lp is the log JOINT density, i.e. MINUS
  * the potential energy, and grad is d lp / d theta.) */
+/* Workspace for num_chains chains.  For large batches (num_chains x D >= 2^22 elements) this includes room for one
+ * transposed copy of theta and of the gradient: BPLX_CHAIN_MAJOR calls are then computed in the kernel's native
+ * BPLX_CHAIN_MINOR layout (two tiled transposes around the kernel; the kernel alone is 2.2x slower on [chains, D] buffers
+ * of configs[2] size).  A smaller workspace (the kernel's own need) is accepted: the call then runs on the buffers as
+ * they are. */
 size_t bplx_logdensity_workspace_bytes(const bplx_problem* p, int num_chains);
 
 /*
@@ -223,7 +228,7 @@ int bplx_score_grid_host(const bplx_samples* s, const bplx_fixtures* f, int max_
 
 /* ---- misc --------------------------------------------------------------------------------- */
 /* The library reads its testing / tuning switches (BPLX_NO_PDL, BPLX_SPLIT, BPLX_HOST_CHUNKS, BPLX_NUTS_GENERIC,
- * BPLX_NO_TAIL_SPLIT, BPLX_NO_HOST_TRANSPOSE) from the environment once, at first use -- never on a launch path; call this after changing them. */
+ * BPLX_NO_TAIL_SPLIT, BPLX_NO_TRANSPOSE) from the environment once, at first use -- never on a launch path; call this after changing them. */
 void bplx_reload_env(void);
 const char* bplx_last_error(void);
 int bplx_version(void);

@@ -166,8 +166,8 @@ def test_host_entry_point_through_the_native_layout(bplx_env):
         p = Problem(arr)
         theta = rng.uniform(-2, 2, (C, p.D)).astype(np.float32)
         outs = []
-        for env in ({"BPLX_NO_HOST_TRANSPOSE": None, "BPLX_HOST_CHUNKS": chunks},
-                    {"BPLX_NO_HOST_TRANSPOSE": "1", "BPLX_HOST_CHUNKS": 1}):
+        for env in ({"BPLX_NO_TRANSPOSE": None, "BPLX_HOST_CHUNKS": chunks},
+                    {"BPLX_NO_TRANSPOSE": "1", "BPLX_HOST_CHUNKS": 1}):
             bplx_env(**env)
             outs.append([x.copy() for x in p.logdensity_host(theta)])
         if chunks is None:
@@ -180,3 +180,38 @@ def test_host_entry_point_through_the_native_layout(bplx_env):
         idx = np.array([0, 31, 32, C // 2, C - 1])
         _check(arr, theta[idx], outs[0][0][idx], outs[0][1][idx], outs[0][2][idx])
         p.close()
+
+
+def test_chain_major_device_call_through_the_native_layout(bplx_env):
+    """A large [chains, D] batch on the device (what a vmapped jax.ffi call hands over) is transposed into the kernel's
+    native layout when the workspace has the room bplx_logdensity_workspace_bytes asks for: same bits as the chain-minor
+    call and as the untransposed chain-major call; the likelihood-only entry point takes the same route."""
+    import torch
+    from bpl_next_b200 import Problem, _abi
+
+    arr = H.from_training_data("neutral_wc", datasets.config_3(), epsilon=0.1)
+    p = Problem(arr)
+    C = 4101
+    theta = np.random.default_rng(92).uniform(-2, 2, (C, p.D)).astype(np.float32)
+    tM = torch.from_numpy(theta).cuda()
+    n0 = _abi.lib().bplx_launch_count()
+    a = [x.clone() for x in p.logdensity(tM)]
+    assert _abi.lib().bplx_launch_count() - n0 == 3  # transpose, kernel, transpose
+    b = [x.clone() for x in p.logdensity(tM.t().contiguous(), chain_minor=True)]
+    bplx_env(BPLX_NO_TRANSPOSE=1)
+    n0 = _abi.lib().bplx_launch_count()
+    c = [x.clone() for x in p.logdensity(tM)]
+    assert _abi.lib().bplx_launch_count() - n0 == 1
+    torch.cuda.synchronize()
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1].t()) and torch.equal(a[2], b[2])
+    assert torch.equal(a[0], c[0]) and torch.equal(a[1], c[1]) and torch.equal(a[2], c[2])
+    bplx_env(BPLX_NO_TRANSPOSE=None)
+    Dl = int(_abi.lib().bplx_loglik_num_inputs(p._h))
+    tab = torch.from_numpy(np.random.default_rng(93).uniform(0.2, 0.9, (C, Dl)).astype(np.float32)).cuda()
+    n0 = _abi.lib().bplx_launch_count()
+    la = [x.clone() for x in p.loglik(tab)]
+    assert _abi.lib().bplx_launch_count() - n0 == 3
+    lb = [x.clone() for x in p.loglik(tab.t().contiguous(), chain_minor=True)]
+    torch.cuda.synchronize()
+    assert torch.equal(la[0], lb[0]) and torch.equal(la[1], lb[1].t()) and torch.equal(la[2], lb[2])
+    p.close()
