@@ -42,6 +42,16 @@ __device__ __forceinline__ float log_add_exp(float a, float b) {
   return m + log1pf(expf(-fabsf(a - b)));
 }
 
+// chain-major state: the 32 lanes of a warp are the slices of ONE chain -- a butterfly gives every lane the same sum
+template <int N>
+__device__ __forceinline__ void reduce_lanes(float (&v)[N]) {
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], m);
+  }
+}
+
 // sum over the threadIdx.y slices of every chain of the block (all threads of the block must call it)
 template <int N>
 __device__ __forceinline__ void reduce_y(float (&v)[N], float* red) {
@@ -101,18 +111,35 @@ constexpr int kNutsBatch = 4;
 
 // block = (32 chains, Y slices).  Thread (x, y) owns parameters d = y, y+Y, ... of chain x; the scalar state machine
 // is replicated in the Y threads of a chain (same inputs, same random numbers -> same decisions); only y == 0 writes it.
+//
+// CM = true (bplx_nuts_params::state_layout == 1, chain-major state): block = (32 lanes, chains), a WARP per chain; lane
+// y owns d = y, y + 32, ... of the chain's contiguous vectors.  Chains are not in lock step, so in the chain-minor
+// layout the lanes of a warp sit in different stages, extend different ends and test different checkpoint levels:
+// every 128-byte line is touched for a few of its 32 chains, stores fill sectors partially (read-modify-write in L2)
+// -- measured 11.2 GB of DRAM traffic per step on configs[2] against ~2.8 GB of vectors actually used.  With a warp
+// per chain every branch is warp-uniform and every access a full line of one chain's vector; the reductions over the
+// parameters are warp butterflies and the block never synchronises.
+template <bool CM>
 __global__ void __launch_bounds__(32 * kNutsMaxY) nuts_step_kernel(const bplx_nuts_params P) {
-  __shared__ float red[2 * kNutsMaxY * 32];
+  __shared__ float red[CM ? 1 : 2 * kNutsMaxY * 32];
   pdl_wait();  // (launched with programmatic stream serialization: nothing here may run ahead of the log-density kernel)
   pdl_launch_dependents();
-  const int Y = blockDim.y, y = threadIdx.y;
-  const int c_raw = blockIdx.x * 32 + threadIdx.x;
+  const int Y = CM ? 32 : blockDim.y, y = CM ? threadIdx.x : threadIdx.y;
+  const int c_raw = CM ? blockIdx.x * blockDim.y + threadIdx.y : blockIdx.x * 32 + threadIdx.x;
   const bool valid = c_raw < P.C;
   const int c = valid ? c_raw : P.C - 1;
   const int D = P.D;
-  const size_t ld = (size_t)P.ld;
-  auto vec = [&](float* base) { return Vec{base + c, ld}; };
-  auto vec_k = [&](float* base, int k) { return Vec{base + (size_t)k * D * ld + c, ld}; };
+  // element (k, d) of chain c in a stack of vectors: chain-minor [k][D][ld] + c, chain-major [k][C][ld_state] + d
+  const size_t ld = CM ? (size_t)1 : (size_t)P.ld;
+  const size_t plane = CM ? (size_t)P.C * (size_t)P.ld_state : (size_t)D * (size_t)P.ld;
+  const size_t cbase = CM ? (size_t)c * (size_t)P.ld_state : (size_t)c;
+  auto vec = [&](float* base) { return Vec{base + cbase, ld}; };
+  auto vec_k = [&](float* base, int k) { return Vec{base + (size_t)k * plane + cbase, ld}; };
+  auto reduce = [&](auto& v) {
+    if (CM) reduce_lanes(v);
+    else reduce_y(v, red);
+  };
+  auto block_or = [&](bool x) { return CM ? x : (bool)__syncthreads_or(x); };  // (chain-major: a chain's warp decides alone)
   const Vec th = vec(P.theta_eval), gr = vec(P.grad), ph = vec(P.p_half), imm = vec(P.inv_mass);
   const Vec zL = vec(P.zL), rL = vec(P.rL), gL = vec(P.gL), zR = vec(P.zR), rR = vec(P.rR), gR = vec(P.gR);
   const Vec zP = vec(P.zP), gP = vec(P.gP), rS = vec(P.r_sum);
@@ -217,7 +244,7 @@ __global__ void __launch_bounds__(32 * kNutsMaxY) nuts_step_kernel(const bplx_nu
       }
     }
   }
-  reduce_y(acc1, red);
+  reduce(acc1);
   bool sub_done = false;
   if (pending) {
     const float pe1 = -lp_new;
@@ -260,9 +287,9 @@ __global__ void __launch_bounds__(32 * kNutsMaxY) nuts_step_kernel(const bplx_nu
 #pragma unroll
   for (int i = kLv - 1; i >= 0; i--) {
     const bool need = ((my_lvls >> i) & 1u) && !turning;
-    if (!__syncthreads_or(need)) continue;
+    if (!block_or(need)) continue;
     float dots[2] = {dt0[i], dt1[i]};
-    reduce_y(dots, red);
+    reduce(dots);
     if (need) turning = dots[0] <= 0.0f || dots[1] <= 0.0f;
   }
   // ======== C. subtree complete: merge into the trajectory (biased progressive sampling, numpyro `_combine_tree`) =======
@@ -308,7 +335,7 @@ __global__ void __launch_bounds__(32 * kNutsMaxY) nuts_step_kernel(const bplx_nu
         }
       }
     }
-    if (__syncthreads_or(sub_done)) reduce_y(dots, red);
+    if (block_or(sub_done)) reduce(dots);
     if (sub_done) {
       if (move) st.pe = st.sub_pe;
       st.turning = st.sub_turning || dots[0] <= 0.0f || dots[1] <= 0.0f;
@@ -366,14 +393,14 @@ __global__ void __launch_bounds__(32 * kNutsMaxY) nuts_step_kernel(const bplx_nu
     } else {
       const int k = st.t - P.num_warmup;
       if (P.diag_lags > 0)
-        for (int d = y; d < D; d += Y) diag_collect(P, k, (size_t)d * ld + c, (size_t)D * ld, zP[d]);
+        for (int d = y; d < D; d += Y) diag_collect(P, k, (size_t)d * ld + cbase, plane, zP[d]);
       if (k % P.thin == 0 && k / P.thin < P.num_keep) {
         const int slot = k / P.thin;
-        float* out = P.samples + (size_t)slot * D * ld + c;
+        float* out = P.samples + (size_t)slot * plane + cbase;
         for (int d = y; d < D; d += Y) out[(size_t)d * ld] = zP[d];
         if (y == 0) {
-          P.sample_lp[(size_t)slot * ld + c] = -st.pe;
-          P.sample_accept[(size_t)slot * ld + c] = accept;
+          P.sample_lp[(size_t)slot * P.ld + c] = -st.pe;
+          P.sample_accept[(size_t)slot * P.ld + c] = accept;
         }
       }
     }
@@ -404,7 +431,7 @@ __global__ void __launch_bounds__(32 * kNutsMaxY) nuts_step_kernel(const bplx_nu
         gR[d] = g;
       }
     }
-    if (__syncthreads_or(fresh)) reduce_y(ke, red);
+    if (block_or(fresh)) reduce(ke);
     if (fresh) {
       draws += 64u + 2u * (unsigned)D + 8u;
       st.energy_current = st.pe + 0.5f * ke[0];
@@ -877,9 +904,10 @@ __global__ void nuts_init_kernel(const bplx_nuts_params P) {
   st.rng_offset = 0;
   static_cast<NutsChain*>(P.chain)[c] = st;
   for (int d = 0; d < P.D; d++) {
-    P.inv_mass[(size_t)d * P.ld + c] = 1.0f;
-    P.wf_mean[(size_t)d * P.ld + c] = 0.0f;
-    P.wf_m2[(size_t)d * P.ld + c] = 0.0f;
+    const size_t o = P.state_layout == 1 ? (size_t)c * P.ld_state + d : (size_t)d * P.ld + c;
+    P.inv_mass[o] = 1.0f;
+    P.wf_mean[o] = 0.0f;
+    P.wf_m2[o] = 0.0f;
   }
 }
 
@@ -893,6 +921,8 @@ size_t bplx_nuts_chain_bytes(void) { return sizeof(NutsChain); }
 
 int bplx_nuts_init(const bplx_nuts_params* p, void* stream) {
   BPLX_REQUIRE(p && p->C > 0 && p->D > 0 && p->ld >= p->C, BPLX_E_INVALID, "nuts: bad C / D / ld");
+  BPLX_REQUIRE(p->state_layout == 0 || (p->state_layout == 1 && p->ld_state >= p->D), BPLX_E_INVALID,
+               "nuts: state_layout must be 0 (chain-minor) or 1 (chain-major, ld_state >= D)");
   nuts_init_kernel<<<(p->C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(*p);
   BPLX_CUDA(cudaGetLastError());
   note_launch(1);
@@ -921,6 +951,8 @@ int bplx_nuts_step(const bplx_nuts_params* p, void* stream) {
                "nuts: max_tree_depth must be in [1, 12] and thin >= 1");
   BPLX_REQUIRE(p->diag_lags >= 0 && (p->diag_lags == 0 || (p->dg_ref && p->dg_sums && p->dg_lag && p->dg_ring && p->dg_head)),
                BPLX_E_INVALID, "nuts: diag_lags > 0 needs the dg_* accumulators");
+  BPLX_REQUIRE(p->state_layout == 0 || (p->state_layout == 1 && p->ld_state >= p->D), BPLX_E_INVALID,
+               "nuts: state_layout must be 0 (chain-minor) or 1 (chain-major, ld_state >= D)");
   int Y = (p->D + 3) / 4;  // about four parameters per thread, at most kNutsMaxY slices per chain
   Y = Y < 1 ? 1 : (Y > kNutsMaxY ? kNutsMaxY : Y);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -937,14 +969,16 @@ int bplx_nuts_step(const bplx_nuts_params* p, void* stream) {
     cfg.blockDim = block;
     return cudaLaunchKernelEx(&cfg, fn, *p);
   };
-  if (!generic && p->D <= 4 * kNutsMaxY)  // same geometry as the generic kernel: identical bits
+  if (p->state_layout == 1)  // chain-major state: a warp per chain, eight chains per block
+    BPLX_CUDA(launch(&nuts_step_kernel<true>, 8, dim3(32, 8)));
+  else if (!generic && p->D <= 4 * kNutsMaxY)  // same geometry as the generic kernel: identical bits
     BPLX_CUDA(launch(&nuts_step_fast_kernel<32, 4>, 32, dim3(32, Y)));
   else if (!generic && p->D <= 128)
     BPLX_CUDA(launch(&nuts_step_fast_kernel<16, 4>, 16, dim3(16, 32)));
   else if (!generic && p->D <= 256)
     BPLX_CUDA(launch(&nuts_step_fast_kernel<8, 4>, 8, dim3(8, 64)));
   else
-    BPLX_CUDA(launch(&nuts_step_kernel, 32, dim3(32, Y)));
+    BPLX_CUDA(launch(&nuts_step_kernel<false>, 32, dim3(32, Y)));
   BPLX_CUDA(cudaGetLastError());
   note_launch(1);
   return BPLX_OK;

@@ -4,7 +4,9 @@
     run = sample(potential, theta0, num_warmup=500, num_samples=1000)
 
 ``potential(theta_eval, lp, grad)`` evaluates log density and gradient in place on chain-minor ``[D, C]`` tensors
-(for the models: ``Problem.logdensity(..., chain_minor=True)``).  torch provides device memory and streams only.
+(for the models: ``Problem.logdensity(..., chain_minor=True)``).  For large models the sampler keeps its state
+chain-major (a warp per chain, see ``csrc/nuts.cu``) and calls ``potential_cm`` on ``[C, D]`` tensors instead
+(``Problem.logdensity(..., chain_minor=False)``).  torch provides device memory and streams only.
 """
 from __future__ import annotations
 
@@ -36,7 +38,9 @@ class NutsParams(C.Structure):
                                    "gQ", "r_sum_sub", "r_ckpts", "r_sum_ckpts", "wf_mean", "wf_m2", "samples",
                                    "sample_lp", "sample_accept", "active_count")] + [
         ("diag_lags", C.c_int32),
-    ] + [(n, C.c_void_p) for n in ("dg_ref", "dg_sums", "dg_lag", "dg_ring", "dg_head")]
+    ] + [(n, C.c_void_p) for n in ("dg_ref", "dg_sums", "dg_lag", "dg_ring", "dg_head")] + [
+        ("state_layout", C.c_int32), ("ld_state", C.c_int32),
+    ]
 
 
 def adaptation_schedule(num_steps: int):
@@ -98,29 +102,45 @@ def sample(potential: Callable[[torch.Tensor, torch.Tensor, torch.Tensor], None]
            num_warmup: int = 500, num_samples: int = 1000, thin: int = 1, seed: int = 42, max_tree_depth: int = 10,
            target_accept: float = 0.8, step_size: float = 1.0, chain_offset: int = 0, check_every: int = 32,
            max_launches: Optional[int] = None, use_graph: bool = True, diag_lags: int = 0,
-           pad_rows: bool = False) -> NutsRun:
+           pad_rows: bool = False, potential_cm: Optional[Callable[[torch.Tensor, torch.Tensor, torch.Tensor], None]] = None,
+           state_layout: str = "auto") -> NutsRun:
     """``theta0``: ``[D, C]`` float32 CUDA tensor (chain-minor) of initial unconstrained positions.
 
     ``thin`` stores every thin-th post-warm-up draw only; ``diag_lags > 0`` keeps per-chain streaming accumulators of
     ALL post-warm-up draws (moments of the whole chain and of its halves, lagged products up to ``diag_lags``) inside
-    the step kernel, so split R-hat and ESS need no stored draws (``diagnostics.streaming_summary``)."""
+    the step kernel, so split R-hat and ESS need no stored draws (``diagnostics.streaming_summary``).
+
+    ``state_layout``: ``"chain_minor"`` (every array ``[D, C]``), ``"chain_major"`` (``[C, D]``, needs ``potential_cm``)
+    or ``"auto"``: chain-major when ``potential_cm`` is given, the model is too large for the register-resident step
+    kernels (D > 256) and the batch is large enough for the log-density call to go through its transposing route
+    (C x D >= 2^22).  The returned tensors have the same logical shapes either way (views)."""
     if not theta0.is_cuda:
         raise RuntimeError("bpl_next_b200.nuts needs CUDA tensors: there is no CPU fallback")
     lib = _declare(_abi.lib())
     D, Cn = theta0.shape
     dev = theta0.device
     f32 = dict(dtype=torch.float32, device=dev)
+    if state_layout not in ("auto", "chain_minor", "chain_major"):
+        raise ValueError(f"state_layout {state_layout!r}")
+    cm = state_layout == "chain_major" or (state_layout == "auto" and potential_cm is not None and D > 256
+                                            and Cn * D >= (1 << 22))
+    if cm and potential_cm is None:
+        raise ValueError("state_layout='chain_major' needs potential_cm (the log-density on [C, D] tensors)")
     # row pitch of every [D, C] array (the kernels take any pitch >= C; measured on B200: padding a 4 KB-multiple pitch
     # by one line changes nothing -- 3.03 vs 3.10 ms per step at 32,768 chains -- so the default is the dense layout)
     ld = Cn + 32 if (Cn * 4) % 4096 == 0 and pad_rows else Cn
+    ldD = (D + 31) // 32 * 32  # chain-major: pitch of a chain's vector (whole 128-byte lines)
 
     def zeros(*lead):
+        """A zeroed stack of per-(chain, parameter) vectors, as its logical ``[..., D, C]`` view."""
+        if cm:
+            return torch.zeros(lead + (Cn, ldD), **f32)[..., :D].transpose(-1, -2)
         return torch.zeros(lead + (D, ld), **f32)[..., :Cn]
 
     num_keep = (num_samples + thin - 1) // thin
     # state: 18 + 2 * max_tree_depth vectors of [D, C]; output: num_keep of them.  Fail early and say what to change.
     diag_lags = max(0, min(int(diag_lags), max(num_samples - 1, 0)))
-    need = 4 * D * (Cn + 32) * (18 + 2 * max_tree_depth + num_keep + ((7 + 3 * diag_lags) if diag_lags else 0)) + 8 * num_keep * Cn
+    need = 4 * (D + 31) * (Cn + 32) * (18 + 2 * max_tree_depth + num_keep + ((7 + 3 * diag_lags) if diag_lags else 0)) + 8 * num_keep * Cn
     free, _total = torch.cuda.mem_get_info(dev)
     if need > 0.95 * free:
         raise MemoryError(
@@ -158,6 +178,12 @@ def sample(potential: Callable[[torch.Tensor, torch.Tensor, torch.Tensor], None]
     p.active_count = active.data_ptr()
     diag = None
     p.diag_lags = diag_lags
+    p.state_layout, p.ld_state = (1, ldD) if cm else (0, 0)
+    # what the potential sees: [D, C] views, or the chain-major [C, D] views of the same storage
+    if cm:
+        th_arg, gr_arg, call = theta_eval.transpose(0, 1), grad.transpose(0, 1), potential_cm
+    else:
+        th_arg, gr_arg, call = theta_eval, grad, potential
     if diag_lags:
         diag = {"ref": zeros(), "sums": zeros(6), "lag": zeros(diag_lags), "ring": zeros(diag_lags),
                 "head": zeros(diag_lags), "lags": diag_lags, "n": num_samples}
@@ -169,7 +195,7 @@ def sample(potential: Callable[[torch.Tensor, torch.Tensor, torch.Tensor], None]
     def block():  # check_every x (log-density, NUTS step); the last step counts the chains that are not finished
         st = torch.cuda.current_stream().cuda_stream
         for k in range(check_every):
-            potential(theta_eval, lp, grad)
+            call(th_arg, lp, gr_arg)
             if k == check_every - 1:
                 active.zero_()
             _abi.check(lib.bplx_nuts_step(C.byref(p), st))

@@ -60,6 +60,10 @@ def _run_chains(p: Problem, num_chains: int, random_state: int, num_warmup: int,
     def potential(theta, lp, grad):
         p.logdensity(theta, chain_minor=True, lp=lp, grad=grad)
 
+    def potential_cm(theta, lp, grad):  # [chains, D] tensors: large models keep the sampler state chain-major
+        p.logdensity(theta, chain_minor=False, lp=lp, grad=grad)
+
+    kw.setdefault("potential_cm", potential_cm)
     run = bnuts.sample(potential, theta0, num_warmup=num_warmup, num_samples=num_samples, thin=thin,
                        seed=int(random_state), chain_offset=c0, **kw)
     owner.nuts_run = run
@@ -105,7 +109,7 @@ class _BplxPredictor:
     def fit_streaming(self, training_data, epsilon=None, rescale_weights: bool = False, random_state: int = 42,
                       num_warmup: int = 500, num_samples: int = 1000, num_chains: int = 1024, thin: int = 10,
                       diag_lags: int = 24, max_tree_depth: int = 10, max_launches: Optional[int] = None,
-                      set_posterior: bool = False) -> Dict[str, Any]:
+                      set_posterior: bool = False, state_layout: str = "auto") -> Dict[str, Any]:
         """Many-chain ``fit`` that never stores all draws: the chains are partitioned over the ``torch.distributed`` ranks
         (no collective while sampling); every chain keeps streaming moment / lagged-product accumulators in the step
         kernel and only every ``thin``-th draw is stored.  At the end the R-hat / ESS moments are all-reduced
@@ -133,11 +137,15 @@ class _BplxPredictor:
         def potential(theta, lp, grad):
             p.logdensity(theta, chain_minor=True, lp=lp, grad=grad)
 
+        def potential_cm(theta, lp, grad):  # [chains, D] tensors: large models keep the sampler state chain-major
+            p.logdensity(theta, chain_minor=False, lp=lp, grad=grad)
+
         torch.cuda.synchronize()
         t0 = _time.perf_counter()
         run = bnuts.sample(potential, theta0, num_warmup=num_warmup, num_samples=num_samples, thin=thin,
                            seed=int(random_state), chain_offset=c0, max_tree_depth=max_tree_depth,
-                           max_launches=max_launches, diag_lags=diag_lags)
+                           max_launches=max_launches, diag_lags=diag_lags, potential_cm=potential_cm,
+                           state_layout=state_layout)
         torch.cuda.synchronize()
         t_sample = _time.perf_counter() - t0
         self.nuts_run = run

@@ -6,7 +6,7 @@
  * bpl/neutral_dixon_coles_WC.py:281-300, bpl/dynamic_dixon_coles.py:279-296): numpyro defaults (target accept 0.8,
  * max tree depth 10, diagonal mass, step size 1.0 adapted by dual averaging, Stan windows, divergence at dH > 1000).
  *
- * Protocol (all buffers caller-owned DEVICE memory, chain-minor [D][ld] unless stated, float32):
+ * Protocol (all buffers caller-owned DEVICE memory, float32, chain-minor [D][ld] unless stated or state_layout == 1):
  *     bplx_nuts_init(&p)                          chains start at stage "evaluate the initial position"
  *     copy the initial positions into theta_eval
  *     repeat { potential: lp, grad <- log-density(theta_eval);  bplx_nuts_step(&p) }  until *active_count == 0
@@ -61,6 +61,13 @@ typedef struct bplx_nuts_params {
   float* dg_ref;                 /* [D][ld]              x_0 */
   float* dg_sums;                /* [6][D][ld]           zero-initialised by the caller */
   float *dg_lag, *dg_ring, *dg_head; /* [diag_lags][D][ld] each, zero-initialised by the caller */
+  /* Layout of every per-(chain, parameter) array above -- theta_eval and grad included:
+   *   0  chain-minor [..][D][ld] (lane = chain; what the register-resident kernels for D <= 256 use)
+   *   1  chain-major [..][C][ld_state], ld_state >= D (a warp per chain: for large D, where chains that are not in lock
+   *      step make the chain-minor step touch every line for a few chains at a time -- 11.2 -> ~3 GB of DRAM traffic per
+   *      step on configs[2]).  The log-density call then takes BPLX_CHAIN_MAJOR buffers with ld = ld_state.
+   * The per-chain scalars (lp, sample_lp, sample_accept) keep the pitch ld in both. */
+  int32_t state_layout, ld_state;
 } bplx_nuts_params;
 
 size_t bplx_nuts_chain_bytes(void);

@@ -9,7 +9,7 @@ from oracle import datasets
 C = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
 n1 = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 n2 = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
-PAD = (sys.argv[4] != "nopad") if len(sys.argv) > 4 else True
+LAYOUT = sys.argv[4] if len(sys.argv) > 4 else "auto"  # auto | chain_minor | chain_major
 arr, _ = bdata.prepare("neutral_wc", datasets.config_3(), epsilon=0.1)
 p = Problem(arr)
 g = torch.Generator(device="cuda").manual_seed(1)
@@ -20,11 +20,15 @@ def potential(theta, lp, grad):
     p.logdensity(theta, chain_minor=True, lp=lp, grad=grad)
 
 
+def potential_cm(theta, lp, grad):
+    p.logdensity(theta, chain_minor=False, lp=lp, grad=grad)
+
+
 def run(n):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    r = bn.sample(potential, theta0, num_warmup=1000, num_samples=10, max_tree_depth=6, max_launches=n, use_graph=False, pad_rows=PAD,
-                  check_every=32, diag_lags=8)
+    r = bn.sample(potential, theta0, num_warmup=1000, num_samples=10, max_tree_depth=6, max_launches=n, use_graph=False, check_every=32, diag_lags=8,
+                  potential_cm=potential_cm, state_layout=LAYOUT)
     torch.cuda.synchronize()
     return time.perf_counter() - t0, r.launches
 
@@ -32,16 +36,20 @@ def run(n):
 run(64)
 t1, l1 = run(n1)
 t2, l2 = run(n2)
-lp = torch.empty(C, device="cuda"); grad = torch.empty_like(theta0)
+lp = torch.empty(C, device="cuda")
+cm = LAYOUT == "chain_major" or (LAYOUT == "auto" and p.D > 256 and C * p.D >= (1 << 22))
+th = theta0.t().contiguous() if cm else theta0
+grad = torch.empty_like(th)
+f = potential_cm if cm else potential
 for _ in range(3):
-    potential(theta0, lp, grad)
+    f(th, lp, grad)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(10):
-    potential(theta0, lp, grad)
+    f(th, lp, grad)
 e1.record(); e1.synchronize()
 k1 = e0.elapsed_time(e1) / 10
 pair = 1e3 * (t2 - t1) / (l2 - l1)
-print(json.dumps({"chains": C, "D": p.D, "launches": [l1, l2], "ms_per_pair_steady": pair, "k1_ms": k1, "step_ms": pair - k1,
+print(json.dumps({"chains": C, "D": p.D, "state_layout": "chain_major" if cm else "chain_minor", "launches": [l1, l2], "ms_per_pair_steady": pair, "k1_ms": k1, "step_ms": pair - k1,
                   "ms_per_pair_first": 1e3 * t1 / l1}))

@@ -251,3 +251,97 @@ def test_posterior_matches_independent_cpu_sampler(model):
         assert z.max() < 5.0, (k, z.max(), mean, gold[k + "_mean"])
         np.testing.assert_allclose(sd, gold[k + "_sd"], rtol=0.08, err_msg=k)
     p.close()
+
+
+def _gauss(D, seed):
+    import torch
+
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    mu = torch.randn((D, 1), generator=g, device="cuda") * 2
+    sd = torch.exp(0.7 * torch.randn((D, 1), generator=g, device="cuda"))
+
+    def potential(theta, lp, grad):  # [D, C]
+        z = (theta - mu) / sd
+        lp.copy_(-0.5 * (z * z).sum(0))
+        grad.copy_(-z / sd)
+
+    def potential_cm(theta, lp, grad):  # [C, D] (padded row pitch)
+        z = (theta - mu[:, 0]) / sd[:, 0]
+        lp.copy_(-0.5 * (z * z).sum(1))
+        grad.copy_(-z / sd[:, 0])
+
+    return mu, sd, potential, potential_cm, g
+
+
+def test_chain_major_state_samples_the_same_target():
+    """state_layout='chain_major' (a warp per chain, [C, D] vectors): means / sds of independent normals within Monte-Carlo
+    error, the adapted inverse mass is the variance, streaming accumulators equal their specification."""
+    import torch
+    from bpl_next_b200 import diagnostics as dg
+
+    D, C = 300, 256
+    mu, sd, potential, potential_cm, g = _gauss(D, 11)
+    theta0 = torch.rand((D, C), generator=g, device="cuda") * 4 - 2
+    run = bn.sample(potential, theta0, num_warmup=300, num_samples=120, seed=4, potential_cm=potential_cm,
+                    state_layout="chain_major", diag_lags=12)
+    assert run.samples.shape == (120, D, C) and run.inv_mass.shape == (D, C)
+    assert run.num_divergent.sum() == 0 and (run.transitions == 420).all()
+    x = run.samples.double()
+    ess = dg.effective_sample_size(run.samples).cpu().numpy()
+    mean = x.mean(dim=(0, 2)).cpu().numpy()
+    std = x.permute(1, 0, 2).reshape(D, -1).std(dim=1).cpu().numpy()
+    mcse = sd[:, 0].cpu().numpy() / np.sqrt(ess)
+    assert np.all(np.abs(mean - mu[:, 0].cpu().numpy()) < 5 * mcse)
+    np.testing.assert_allclose(std, sd[:, 0].cpu().numpy(), rtol=0.05)
+    assert dg.split_rhat(run.samples).max().item() < 1.03
+    np.testing.assert_allclose(run.inv_mass.mean(dim=1).cpu().numpy(), (sd[:, 0] ** 2).cpu().numpy(), rtol=0.4)
+    assert 0.6 < run.accept.mean().item() < 0.95
+    ref = dg.accumulate_reference(run.samples, 12)
+    for k in ("ref", "sums", "lag", "ring", "head"):
+        want = ref[k].cpu().numpy()
+        np.testing.assert_allclose(run.diag[k].cpu().numpy(), want, rtol=2e-5, atol=2e-6 * max(1.0, np.abs(want).max()), err_msg=k)
+
+
+def test_chain_major_and_chain_minor_state_take_the_same_first_transitions():
+    """Same seeds, same per-chain random streams: with a fixed step size the first draws of the two layouts agree to
+    rounding for (nearly) every chain -- the two kernels differ only in the order of the sums over parameters."""
+    import torch
+
+    D, C = 300, 192
+    mu, sd, potential, potential_cm, g = _gauss(D, 12)
+    theta0 = torch.rand((D, C), generator=g, device="cuda") * 2 - 1
+    runs = [bn.sample(potential, theta0.clone(), num_warmup=0, num_samples=2, seed=9, step_size=0.05, max_tree_depth=4,
+                      potential_cm=potential_cm, state_layout=lay) for lay in ("chain_minor", "chain_major")]
+    a, b = runs[0].samples[0], runs[1].samples[0]  # [D, C]
+    same = ((a - b).abs().max(dim=0).values < 1e-3).float().mean().item()
+    assert same > 0.95, same
+    assert torch.allclose(runs[0].lp[0], runs[1].lp[0], rtol=1e-3, atol=1e-2) or same > 0.95
+    assert (runs[0].num_leapfrog == runs[1].num_leapfrog).mean() > 0.9
+
+
+def test_chain_major_state_on_the_wc_model():
+    """NeutralWC at a size where 'auto' picks the chain-major state and the log-density call goes through its transposing
+    route (C x D >= 2^22): a short run ends with every chain done, finite draws, acceptance in range."""
+    import torch
+    from bpl_next_b200 import Problem
+    from oracle import datasets
+    from tests import helpers as H
+
+    arr = H.from_training_data("neutral_wc", datasets.config_3(), epsilon=0.1)
+    p = Problem(arr)
+    C = 3200
+    assert C * p.D >= (1 << 22)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    theta0 = torch.rand((p.D, C), generator=g, device="cuda") * 0.2 - 0.1
+
+    def potential(theta, lp, grad):
+        p.logdensity(theta, chain_minor=True, lp=lp, grad=grad)
+
+    def potential_cm(theta, lp, grad):
+        p.logdensity(theta, chain_minor=False, lp=lp, grad=grad)
+
+    run = bn.sample(potential, theta0, num_warmup=20, num_samples=6, seed=5, max_tree_depth=4, potential_cm=potential_cm)
+    assert (run.transitions == 26).all()
+    assert torch.isfinite(run.samples).all() and torch.isfinite(run.lp).all()
+    assert 0.3 < run.accept.mean().item() <= 1.0
+    p.close()
