@@ -104,7 +104,10 @@ __device__ __forceinline__ void diag_collect(const bplx_nuts_params& P, int k, s
 // round trip to L2 / HBM per parameter (the vectors may alias as far as the compiler knows, so it does not hoist the loads
 // itself; measured on configs[2], 32,768 chains x 1,339 parameters: the step was 4x the log-density kernel).  The
 // arithmetic and its order are unchanged: same bits as before, and as the register-resident kernel.
-constexpr int kNutsBatch = 4;
+// (chain-major, measured on configs[2] at 32,768 chains: 4 blocks of 8 warps per SM at 64 registers -- cold chain-state
+//  fields spill -- with batches of 4: 0.76 ms per step; batches of 2: 0.85, of 6: 0.82, of 8: 0.89; 2 blocks per SM at
+//  128 registers: 1.07; 5 / 6 blocks per SM: 0.91 / 0.98)
+constexpr int kNutsBatchCMinor = 4, kNutsBatchCMajor = 4;
 #define BPLX_FOR_BATCH(d0) for (int d0 = y; d0 < D; d0 += kNutsBatch * Y)
 #define BPLX_IN_BATCH(u, d, d0) \
   _Pragma("unroll") for (int u = 0, d = d0; u < kNutsBatch; u++, d += Y)
@@ -120,7 +123,8 @@ constexpr int kNutsBatch = 4;
 // per chain every branch is warp-uniform and every access a full line of one chain's vector; the reductions over the
 // parameters are warp butterflies and the block never synchronises.
 template <bool CM>
-__global__ void __launch_bounds__(32 * kNutsMaxY) nuts_step_kernel(const bplx_nuts_params P) {
+__global__ void __launch_bounds__(CM ? 256 : 32 * kNutsMaxY, CM ? 4 : 1) nuts_step_kernel(const bplx_nuts_params P) {
+  constexpr int kNutsBatch = CM ? kNutsBatchCMajor : kNutsBatchCMinor;
   __shared__ float red[CM ? 1 : 2 * kNutsMaxY * 32];
   pdl_wait();  // (launched with programmatic stream serialization: nothing here may run ahead of the log-density kernel)
   pdl_launch_dependents();
@@ -173,18 +177,20 @@ __global__ void __launch_bounds__(32 * kNutsMaxY) nuts_step_kernel(const bplx_nu
     idx_max = __popc(leaf >> 1);
     idx_min = idx_max - (__ffs(~leaf) - 1) + 1;  // minus the number of trailing one bits
   }
-  const unsigned my_lvls = (pending && idx_max >= idx_min) ? (((2u << idx_max) - 1u) & ~((1u << idx_min) - 1u)) : 0u;
+  const int nlv = (pending && idx_max >= idx_min) ? idx_max - idx_min + 1 : 0;  // levels idx_min .. idx_max
   const bool ckpt = pending && (leaf & 1u) == 0u;
   // ONE pass over the parameters does everything that does not depend on the accept / take decisions: the new leaf
   // (momentum, position, gradient of the extended end), the kinetic energy, the subtree's momentum sum, the checkpoint
   // an even leaf leaves behind and the U-turn dot products of every level the leaf is tested against -- each vector is
   // read once (the stage-by-stage form re-read the leaf's momentum, the sum and the inverse mass once per level).
-  constexpr int kLv = 12;  // max_tree_depth <= 12
+  // (the dot products of kSlots levels at a time live in registers: a leaf is tested against as many levels as its index
+  //  has trailing one bits plus one -- more than four for one leaf in sixteen, which then takes another pass below)
+  constexpr int kSlots = 4;
   bool spec = false;
   float acc1[1] = {0.0f};
-  float dt0[kLv], dt1[kLv];
+  float dt0[kSlots], dt1[kSlots];
 #pragma unroll
-  for (int i = 0; i < kLv; i++) dt0[i] = dt1[i] = 0.0f;
+  for (int j = 0; j < kSlots; j++) dt0[j] = dt1[j] = 0.0f;
   if (pending) {
     const Vec ckw = vec_k(P.r_ckpts, idx_max), cksw = vec_k(P.r_sum_ckpts, idx_max);
     const bool first = st.sub_num == 0;
@@ -206,9 +212,9 @@ __global__ void __launch_bounds__(32 * kNutsMaxY) nuts_step_kernel(const bplx_nu
         rs[u] = first ? r1[u] : q[u] + r1[u];
       }
 #pragma unroll
-      for (int i = 0; i < kLv; i++) {
-        if (my_lvls & (1u << i)) {
-          const Vec ck = vec_k(P.r_ckpts, i), cks = vec_k(P.r_sum_ckpts, i);
+      for (int j = 0; j < kSlots; j++) {
+        if (j < nlv) {
+          const Vec ck = vec_k(P.r_ckpts, idx_min + j), cks = vec_k(P.r_sum_ckpts, idx_min + j);
           float a[kNutsBatch], k2[kNutsBatch];
           BPLX_IN_BATCH(u, d, d0) {
             const bool ok = d < D;
@@ -217,9 +223,9 @@ __global__ void __launch_bounds__(32 * kNutsMaxY) nuts_step_kernel(const bplx_nu
           }
           BPLX_IN_BATCH(u, d, d0) {
             if (d < D) {
-              const float sm = (rs[u] - k2[u] + a[u]) - 0.5f * (a[u] + r1[u]);  // momentum sum of the subtree that starts at checkpoint i
-              dt0[i] = fmaf(m[u] * a[u], sm, dt0[i]);
-              dt1[i] = fmaf(m[u] * r1[u], sm, dt1[i]);
+              const float sm = (rs[u] - k2[u] + a[u]) - 0.5f * (a[u] + r1[u]);  // momentum sum of the subtree that starts at the checkpoint
+              dt0[j] = fmaf(m[u] * a[u], sm, dt0[j]);
+              dt1[j] = fmaf(m[u] * r1[u], sm, dt1[j]);
             }
           }
         }
@@ -283,14 +289,51 @@ __global__ void __launch_bounds__(32 * kNutsMaxY) nuts_step_kernel(const bplx_nu
     st.sub_sum_accept += acc;
   }
   // ======== B. iterative U-turn test against the checkpoints (levels idx_max .. idx_min, stop at the first turn) =======
+  // (the subtree turns if it turns against ANY of its levels: the order of the tests does not matter)
   bool turning = false;
+  for (int j0 = 0; block_or(j0 < nlv && !turning); j0 += kSlots) {
+    if (j0 > 0) {  // the next kSlots levels of a leaf with many: the new leaf's momentum and the sum are read back
 #pragma unroll
-  for (int i = kLv - 1; i >= 0; i--) {
-    const bool need = ((my_lvls >> i) & 1u) && !turning;
-    if (!block_or(need)) continue;
-    float dots[2] = {dt0[i], dt1[i]};
-    reduce(dots);
-    if (need) turning = dots[0] <= 0.0f || dots[1] <= 0.0f;
+      for (int j = 0; j < kSlots; j++) dt0[j] = dt1[j] = 0.0f;
+      if (j0 < nlv && !turning) {
+        BPLX_FOR_BATCH(d0) {
+          float m[kNutsBatch], r1[kNutsBatch], rs[kNutsBatch];
+          BPLX_IN_BATCH(u, d, d0) {
+            const bool ok = d < D;
+            m[u] = ok ? imm[d] : 0.0f;
+            r1[u] = ok ? rE[d] : 0.0f;
+            rs[u] = ok ? rSq[d] : 0.0f;
+          }
+#pragma unroll
+          for (int j = 0; j < kSlots; j++) {
+            if (j0 + j < nlv) {
+              const Vec ck = vec_k(P.r_ckpts, idx_min + j0 + j), cks = vec_k(P.r_sum_ckpts, idx_min + j0 + j);
+              float a[kNutsBatch], k2[kNutsBatch];
+              BPLX_IN_BATCH(u, d, d0) {
+                const bool ok = d < D;
+                a[u] = ok ? ck[d] : 0.0f;
+                k2[u] = ok ? cks[d] : 0.0f;
+              }
+              BPLX_IN_BATCH(u, d, d0) {
+                if (d < D) {
+                  const float sm = (rs[u] - k2[u] + a[u]) - 0.5f * (a[u] + r1[u]);
+                  dt0[j] = fmaf(m[u] * a[u], sm, dt0[j]);
+                  dt1[j] = fmaf(m[u] * r1[u], sm, dt1[j]);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kSlots; j++) {
+      const bool need = j0 + j < nlv && !turning;
+      if (!block_or(need)) continue;
+      float dots[2] = {dt0[j], dt1[j]};
+      reduce(dots);
+      if (need) turning = dots[0] <= 0.0f || dots[1] <= 0.0f;
+    }
   }
   // ======== C. subtree complete: merge into the trajectory (biased progressive sampling, numpyro `_combine_tree`) =======
   bool move = false;

@@ -96,6 +96,7 @@ class NutsRun:
     inv_mass: torch.Tensor       # [D, C]
     transitions: Optional[np.ndarray] = None  # [C] transitions completed (== num_warmup + num_samples unless cut short)
     diag: Optional[dict] = None  # streaming accumulators (diagnostics.streaming_summary): ref, sums, lag, ring, head, lags, n
+    block_ms: Optional[list] = None  # with time_blocks: CUDA-event time of every block of `check_every` (potential, step) pairs
 
 
 def sample(potential: Callable[[torch.Tensor, torch.Tensor, torch.Tensor], None], theta0: torch.Tensor,
@@ -103,7 +104,7 @@ def sample(potential: Callable[[torch.Tensor, torch.Tensor, torch.Tensor], None]
            target_accept: float = 0.8, step_size: float = 1.0, chain_offset: int = 0, check_every: int = 32,
            max_launches: Optional[int] = None, use_graph: bool = True, diag_lags: int = 0,
            pad_rows: bool = False, potential_cm: Optional[Callable[[torch.Tensor, torch.Tensor, torch.Tensor], None]] = None,
-           state_layout: str = "auto") -> NutsRun:
+           state_layout: str = "auto", time_blocks: bool = False) -> NutsRun:
     """``theta0``: ``[D, C]`` float32 CUDA tensor (chain-minor) of initial unconstrained positions.
 
     ``thin`` stores every thin-th post-warm-up draw only; ``diag_lags > 0`` keeps per-chain streaming accumulators of
@@ -211,11 +212,17 @@ def sample(potential: Callable[[torch.Tensor, torch.Tensor, torch.Tensor], None]
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=side):
                 block()
+        events = []
         while launches < limit and int(active.item()) != 0:
+            if time_blocks:
+                events.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+                events[-1][0].record(side)
             if graph is not None:
                 graph.replay()
             else:
                 block()
+            if time_blocks:
+                events[-1][1].record(side)
             launches += check_every
     torch.cuda.current_stream().wait_stream(side)
     summ = np.zeros((Cn, 8), dtype=np.float32)
@@ -223,4 +230,5 @@ def sample(potential: Callable[[torch.Tensor, torch.Tensor, torch.Tensor], None]
     _abi.check(lib.bplx_nuts_summary(C.byref(p), summ.ctypes.data))
     return NutsRun(samples=samples, lp=sample_lp, accept=sample_accept, step_size=summ[:, 1].copy(),
                    num_divergent=summ[:, 2].astype(np.int64), num_leapfrog=summ[:, 3].astype(np.int64),
-                   launches=launches, inv_mass=vecs["inv_mass"], transitions=summ[:, 0].astype(np.int64), diag=diag)
+                   launches=launches, inv_mass=vecs["inv_mass"], transitions=summ[:, 0].astype(np.int64), diag=diag,
+                   block_ms=[a.elapsed_time(b) for a, b in events] if time_blocks else None)

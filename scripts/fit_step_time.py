@@ -1,8 +1,13 @@
-"""Per-launch cost of one leapfrog of a configs[2] fit in steady state: (log-density kernel + NUTS step kernel) pairs timed
-as the difference of two runs of different length (no CUDA graph), next to the log-density kernel alone."""
+"""Per-launch cost of one leapfrog of a configs[2] fit in steady state: CUDA-event times of the blocks of 32 (log-density
+kernel + NUTS step kernel) pairs of one run (CUDA graph replays), next to the log-density kernel alone.
+usage: python scripts/fit_step_time.py [chains] [launches] [unused] [auto|chain_minor|chain_major]"""
 import json, sys, time
 import numpy as np, torch
 sys.path.insert(0, '.')
+import os
+from bpl_next_b200 import _abi
+if os.environ.get("BPLX_LIB"):  # a library variant built for an experiment
+    _abi.LIB_PATH = os.path.join(os.path.dirname(_abi.LIB_PATH), os.environ["BPLX_LIB"])
 from bpl_next_b200 import Problem, nuts as bn, data as bdata
 from oracle import datasets
 
@@ -24,18 +29,10 @@ def potential_cm(theta, lp, grad):
     p.logdensity(theta, chain_minor=False, lp=lp, grad=grad)
 
 
-def run(n):
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    r = bn.sample(potential, theta0, num_warmup=1000, num_samples=10, max_tree_depth=6, max_launches=n, use_graph=False, check_every=32, diag_lags=8,
-                  potential_cm=potential_cm, state_layout=LAYOUT)
-    torch.cuda.synchronize()
-    return time.perf_counter() - t0, r.launches
-
-
-run(64)
-t1, l1 = run(n1)
-t2, l2 = run(n2)
+torch.cuda.synchronize()
+r = bn.sample(potential, theta0, num_warmup=1000, num_samples=10, max_tree_depth=6, max_launches=n1, check_every=32, diag_lags=8,
+              potential_cm=potential_cm, state_layout=LAYOUT, time_blocks=True)
+blocks = np.array(r.block_ms) / 32.0
 lp = torch.empty(C, device="cuda")
 cm = LAYOUT == "chain_major" or (LAYOUT == "auto" and p.D > 256 and C * p.D >= (1 << 22))
 th = theta0.t().contiguous() if cm else theta0
@@ -50,6 +47,8 @@ for _ in range(10):
     f(th, lp, grad)
 e1.record(); e1.synchronize()
 k1 = e0.elapsed_time(e1) / 10
-pair = 1e3 * (t2 - t1) / (l2 - l1)
-print(json.dumps({"chains": C, "D": p.D, "state_layout": "chain_major" if cm else "chain_minor", "launches": [l1, l2], "ms_per_pair_steady": pair, "k1_ms": k1, "step_ms": pair - k1,
-                  "ms_per_pair_first": 1e3 * t1 / l1}))
+half = blocks[len(blocks) // 2:]
+pair = float(np.median(half))
+print(json.dumps({"chains": C, "D": p.D, "state_layout": "chain_major" if cm else "chain_minor", "launches": r.launches,
+                  "ms_per_pair_steady": pair, "pair_min_max": [float(half.min()), float(half.max())], "k1_ms": k1,
+                  "step_ms": pair - k1, "ms_per_pair_first_blocks": [float(x) for x in blocks[:3]]}))
