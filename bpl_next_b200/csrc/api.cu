@@ -74,20 +74,32 @@ static float* mapped_or(float* host, float* fallback) {
 // arrays (what the reference's vmapped potential sees), the kernel's native layout is [D, chains].
 __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int Cc,
                                                         size_t ldi, size_t ldo) {
-  __shared__ float tile[32][33];
-  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-  for (int j = threadIdx.y; j < 32; j += 8) {
-    const int r = r0 + j, c = c0 + threadIdx.x;
-    if (r < R && c < Cc) tile[j][threadIdx.x] = in[(size_t)r * ldi + c];
-  }
+  // a block moves 128 rows x 32 columns: its 16 loads per thread are all issued before the first store
+  __shared__ float tile[4][32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 128;
+  float v[4][4];
+#pragma unroll
+  for (int s = 0; s < 4; s++)
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int r = r0 + s * 32 + threadIdx.y + 8 * k, c = c0 + threadIdx.x;
+      v[s][k] = (r < R && c < Cc) ? in[(size_t)r * ldi + c] : 0.0f;
+    }
+#pragma unroll
+  for (int s = 0; s < 4; s++)
+#pragma unroll
+    for (int k = 0; k < 4; k++) tile[s][threadIdx.y + 8 * k][threadIdx.x] = v[s][k];
   __syncthreads();
-  for (int j = threadIdx.y; j < 32; j += 8) {
-    const int c = c0 + j, r = r0 + threadIdx.x;
-    if (r < R && c < Cc) out[(size_t)c * ldo + r] = tile[threadIdx.x][j];
-  }
+#pragma unroll
+  for (int s = 0; s < 4; s++)
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int c = c0 + threadIdx.y + 8 * k, r = r0 + s * 32 + threadIdx.x;
+      if (r < R && c < Cc) out[(size_t)c * ldo + r] = tile[s][threadIdx.x][threadIdx.y + 8 * k];
+    }
 }
 static int launch_transpose(const float* in, float* out, int R, int Cc, size_t ldi, size_t ldo, cudaStream_t s) {
-  const dim3 grid((unsigned)((Cc + 31) / 32), (unsigned)((R + 31) / 32));
+  const dim3 grid((unsigned)((Cc + 31) / 32), (unsigned)((R + 127) / 128));
   BPLX_REQUIRE(grid.y <= 65535u, BPLX_E_UNSUPPORTED, "transpose of %d rows", R);
   transpose_kernel<<<grid, dim3(32, 8), 0, s>>>(in, out, R, Cc, ldi, ldo);
   BPLX_CUDA(cudaGetLastError());
