@@ -31,7 +31,8 @@ def potential_cm(theta, lp, grad):
 
 torch.cuda.synchronize()
 r = bn.sample(potential, theta0, num_warmup=1000, num_samples=10, max_tree_depth=6, max_launches=n1, check_every=32, diag_lags=8,
-              potential_cm=potential_cm, state_layout=LAYOUT, time_blocks=True)
+              potential_cm=potential_cm, state_layout=LAYOUT, time_blocks=True,
+              use_graph=not os.environ.get("BPLX_NO_GRAPH"))  # (plain launches for an ncu capture)
 blocks = np.array(r.block_ms) / 32.0
 lp = torch.empty(C, device="cuda")
 cm = LAYOUT == "chain_major" or (LAYOUT == "auto" and p.D > 256 and C * p.D >= (1 << 22))
