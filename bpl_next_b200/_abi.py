@@ -104,6 +104,9 @@ def declare(lib):
     lib.bplx_last_error.restype = C.c_char_p
     lib.bplx_version.argtypes = []
     lib.bplx_version.restype = i
+    lib.bplx_peer_sum.argtypes = [C.POINTER(vp), i, i, C.c_size_t, C.c_size_t, C.c_size_t, vp, C.c_size_t, C.c_size_t, vp,
+                                  C.c_uint, vp]
+    lib.bplx_peer_sum.restype = i
     lib.bplx_launch_count.argtypes = []
     lib.bplx_launch_count.restype = C.c_ulonglong
     return lib

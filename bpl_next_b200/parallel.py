@@ -66,11 +66,18 @@ class ShardedScoreGrid:
     side stream, so only the last range's exchange is exposed.  Buffers are allocated once; ``run()`` is re-entrant.
 
     ``run(timed=True)`` returns ``(total_ms, compute_ms, exposed_exchange_ms)`` from CUDA events on the launch stream.
+
+    On GPUs the exchange is NOT an NCCL call: the ranks keep their partial grids in symmetric memory
+    (``torch.distributed._symmetric_memory``: every rank's buffer mapped into every rank over NVLink) and one kernel per
+    range and rank (``bplx_peer_sum``, ``csrc/peer_sum.cu``) exchanges flags with the peers and sums the range of every
+    rank's buffer in rank order -- same bits on every rank, no staging, latency of one kernel.  The buffers are
+    double-buffered by run so that a rank never overwrites a range a slower peer may still be reading.  ``peer=False``
+    (or a failed rendezvous, reported in ``exchange_kind``) falls back to ``all_reduce``.
     """
 
     def __init__(self, model: str, local_samples: Dict[str, torch.Tensor], fixtures: Dict[str, torch.Tensor],
                  max_goals: int, num_samples_total: int, group=None, chunks: Optional[int] = None,
-                 local_fn: Optional[Callable] = None):
+                 local_fn: Optional[Callable] = None, peer: bool = True):
         if local_fn is None:
             from .problem import score_grid as local_fn
         self.fn, self.model, self.samples, self.group = local_fn, model, local_samples, group
@@ -84,22 +91,63 @@ class ShardedScoreGrid:
         n = chunks if chunks is not None else (4 if self.dist and F >= 2048 else 1)
         n = max(1, min(n, F))
         edges = [F * i // n for i in range(n + 1)]
+        if F >= 16 * n:  # range starts at multiples of four fixtures: 16-byte aligned rows for the vector loads of the exchange
+            edges = [min(F, (e + 3) // 4 * 4) for e in edges[:-1]] + [F]
         self.ranges = [(a, b) for a, b in zip(edges[:-1], edges[1:]) if b > a]
         self.fx = [{k: (None if v is None else v[a:b]) for k, v in fixtures.items()} for a, b in self.ranges]
         self.ws = None
         self.cuda = dev.type == "cuda"
         self.exchange_kind = "none (one rank)" if not self.dist else \
             f"all_reduce(sum) of the partial grids, {len(self.ranges)} fixture ranges, range k-1 exchanged while range k computes"
+        self.peer = None
         if self.cuda:
-            self.side = torch.cuda.Stream(device=dev)
+            self.side = torch.cuda.Stream(device=dev, priority=-1)
             self.ev = [torch.cuda.Event() for _ in self.ranges]
             self.t = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            if self.dist and peer:
+                self._setup_peer(F, g, dev)
+
+    _FLAG_FLOATS = 64  # 256 bytes of flags in front of the data of every symmetric buffer
+
+    def _setup_peer(self, F, g, dev):
+        import ctypes as C
+
+        from . import _abi
+        try:
+            import torch.distributed._symmetric_memory as symm
+            grp = self.group if self.group is not None else dist.group.WORLD
+            n = dist.get_world_size(grp)
+            nd = (F * g * g + F * 3 + 3) // 4 * 4
+            bufs = [symm.empty(self._FLAG_FLOATS + nd, dtype=torch.float32, device=dev) for _ in range(2)]
+            handles = [symm.rendezvous(t, grp) for t in bufs]
+            for t in bufs:
+                t.zero_()
+            torch.cuda.synchronize(dev)
+            dist.barrier(group=grp)  # every rank's flags are zero before anyone publishes
+            ptrs = [(C.c_void_p * n)(*[int(p) for p in h.buffer_ptrs]) for h in handles]
+            self.peer = {
+                "n": n, "rank": dist.get_rank(grp), "bufs": bufs, "handles": handles, "ptrs": ptrs, "epoch": [0, 0],
+                "parity": 0, "lib": _abi.lib(), "F": F, "gg": g * g,
+                "grid": [t[self._FLAG_FLOATS:self._FLAG_FLOATS + F * g * g].view(F, g, g) for t in bufs],
+                "outcome": [t[self._FLAG_FLOATS + F * g * g:self._FLAG_FLOATS + F * g * g + F * 3].view(F, 3) for t in bufs],
+            }
+            self.exchange_kind = (f"peer-memory sum over NVLink (bplx_peer_sum per rank and fixture range: flag exchange, then "
+                                  f"every rank's partial grid read in rank order), {len(self.ranges)} fixture ranges, range k-1 "
+                                  f"exchanged while range k computes")
+        except Exception as e:  # no symmetric memory on this system: NCCL
+            self.peer = None
+            self.exchange_kind += f" [symmetric memory unavailable: {type(e).__name__}: {e}]"
 
     def _local(self, i):
         a, b = self.ranges[i]
         kw = dict(scale=self.scale, want_outcome=True)
         if self.cuda:
-            kw.update(grid=self.grid[a:b], outcome=self.outcome[a:b], workspace=self.ws, reuse_tables=i > 0)
+            if self.peer is not None:  # the partial sums go to this run's symmetric buffer
+                par = self.peer["parity"]
+                kw.update(grid=self.peer["grid"][par][a:b], outcome=self.peer["outcome"][par][a:b])
+            else:
+                kw.update(grid=self.grid[a:b], outcome=self.outcome[a:b])
+            kw.update(workspace=self.ws, reuse_tables=i > 0)
             self.fn(self.model, self.samples, self.fx[i], self.max_goals, **kw)
         else:  # CPU stand-in of the tests
             gr, oc = self.fn(self.model, self.samples, self.fx[i], self.max_goals, **kw)
@@ -108,6 +156,17 @@ class ShardedScoreGrid:
 
     def _exchange(self, i):
         a, b = self.ranges[i]
+        if self.peer is not None:
+            from . import _abi
+            P = self.peer
+            par = P["parity"]
+            P["epoch"][par] += 1
+            _abi.check(P["lib"].bplx_peer_sum(
+                P["ptrs"][par], P["n"], P["rank"], self._FLAG_FLOATS * 4,
+                a * P["gg"], (b - a) * P["gg"], self.grid[a:b].data_ptr(),
+                P["F"] * P["gg"] + a * 3, (b - a) * 3, self.outcome[a:b].data_ptr(),
+                P["epoch"][par], torch.cuda.current_stream().cuda_stream))
+            return
         dist.all_reduce(self.grid[a:b], op=dist.ReduceOp.SUM, group=self.group)
         dist.all_reduce(self.outcome[a:b], op=dist.ReduceOp.SUM, group=self.group)
 
@@ -123,6 +182,8 @@ class ShardedScoreGrid:
             need = max(_p.score_grid_workspace_bytes(self.model, self.samples, fx, self.max_goals) for fx in self.fx)
             self.ws = torch.empty(max(need, 1), dtype=torch.uint8, device=self.grid.device)
         main = torch.cuda.current_stream()
+        if self.peer is not None:
+            self.peer["parity"] ^= 1
         if timed:
             self.t[0].record(main)
         for i in range(len(self.ranges)):

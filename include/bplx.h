@@ -227,6 +227,25 @@ int bplx_score_grid_host(const bplx_samples* s, const bplx_fixtures* f, int max_
                          float* grid, float* outcome);
 
 /* ---- misc --------------------------------------------------------------------------------- */
+/* ---- predict over sample shards: the sum of the partial grids over the ranks, over peer memory ------------- */
+/*
+ * One-shot all-reduce(sum) of two element ranges of SYMMETRIC buffers (one per rank, same size, each mapped into every
+ * rank's address space -- e.g. torch.distributed._symmetric_memory): replaces the all_reduce that finishes the reference's
+ * `.mean(axis=0)` over posterior samples (bpl/base.py:94-110) when the samples are sharded over GPUs.
+ *   bufs[q]     device pointer (valid on THIS rank) to rank q's buffer, q = 0 .. nranks-1; bufs[rank] is this rank's own.
+ *               Layout of every buffer: `flag_bytes` of 32-bit flags (zero before the first call; flag p of rank q's
+ *               buffer = the last epoch rank p has published), then the float data.
+ *   off, cnt    element ranges of the data (grid rows, outcome rows of a fixture range); cnt1 may be 0
+ *   out0, out1  this rank's results (ordinary device memory): out[i] = sum over q, in rank order, of data_q[off + i] --
+ *               the same bits on every rank
+ *   epoch       a counter that every rank increases by one per call (all ranks make the same sequence of calls)
+ * The kernel publishes this rank's flag to all peers, waits for theirs, then reads every rank's range over NVLink.  A
+ * rank may overwrite a range of its own buffer again only after a later call on that rank has returned from its wait
+ * (double-buffer by call parity, as bpl_next_b200.parallel.ShardedScoreGrid does).
+ */
+int bplx_peer_sum(void* const* bufs, int nranks, int rank, size_t flag_bytes, size_t off0, size_t cnt0, float* out0,
+                  size_t off1, size_t cnt1, float* out1, unsigned epoch, void* stream);
+
 /* The library reads its testing / tuning switches (BPLX_NO_PDL, BPLX_SPLIT, BPLX_HOST_CHUNKS, BPLX_NUTS_GENERIC,
  * BPLX_NO_TAIL_SPLIT, BPLX_NO_TRANSPOSE) from the environment once, at first use -- never on a launch path; call this after changing them. */
 void bplx_reload_env(void);

@@ -31,6 +31,28 @@ torch.cuda.synchronize()
 out["grid_max_abs_diff"] = float((grid - ref).abs().max().item())
 out["outcome_max_abs_diff"] = float((outc - ref_out).abs().max().item())
 out["grid_sharded_ms_max_over_ranks"] = float(t.item())
+# ---- N1b: the overlapped, ranged variant; exchange over peer memory (bplx_peer_sum) against NCCL all_reduce -------------
+for name, peer in (("peer", True), ("nccl", False)):
+    sg = parallel.ShardedScoreGrid("neutral_wc", local_s, dfx, 10, S, peer=peer)
+    for _ in range(3):
+        sg.run()
+    torch.cuda.synchronize(); dist.barrier()
+    ts = []
+    for _ in range(10):
+        dist.barrier()
+        ts.append(sg.run(timed=True))
+    g2, o2 = sg.run()
+    torch.cuda.synchronize()
+    med = np.median(np.array(ts), axis=0)
+    tt = torch.tensor(med, device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    out[f"ranged_{name}"] = {"exchange": sg.exchange_kind, "uses_peer_memory": sg.peer is not None,
+                             "grid_max_abs_diff": float((g2 - ref).abs().max().item()),
+                             "outcome_max_abs_diff": float((o2 - ref_out).abs().max().item()),
+                             "total_ms": float(tt[0].item()), "compute_ms": float(tt[1].item()), "exposed_exchange_ms": float(tt[2].item())}
+    chk = torch.stack([g2.double().sum(), o2.double().sum()])
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    out[f"ranged_{name}"]["ranks_hold_identical_sums"] = bool(torch.equal(lo, hi))
 # ---- N2 --------------------------------------------------------------------------------------------------------
 arr = H.from_training_data("dixon_coles", datasets.dummy_data())
 p = Problem(arr)
