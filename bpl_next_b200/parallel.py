@@ -91,7 +91,11 @@ class ShardedScoreGrid:
         n = chunks if chunks is not None else (4 if self.dist and F >= 2048 else 1)
         n = max(1, min(n, F))
         edges = [F * i // n for i in range(n + 1)]
-        if F >= 16 * n:  # range starts at multiples of four fixtures: 16-byte aligned rows for the vector loads of the exchange
+        if F >= 16 * n:
+            # the LAST range's exchange is the exposed one: it gets a third of an equal share; range starts at multiples of
+            # four fixtures (16-byte aligned rows for the vector loads of the exchange)
+            last = F // (3 * n) if n > 1 else F
+            edges = [(F - last) * i // (n - 1) for i in range(n)] + [F] if n > 1 else [0, F]
             edges = [min(F, (e + 3) // 4 * 4) for e in edges[:-1]] + [F]
         self.ranges = [(a, b) for a, b in zip(edges[:-1], edges[1:]) if b > a]
         self.fx = [{k: (None if v is None else v[a:b]) for k, v in fixtures.items()} for a, b in self.ranges]
