@@ -96,7 +96,9 @@ class ShardedScoreGrid:
             # four fixtures (16-byte aligned rows for the vector loads of the exchange)
             last = F // (3 * n) if n > 1 else F
             edges = [(F - last) * i // (n - 1) for i in range(n)] + [F] if n > 1 else [0, F]
-            edges = [min(F, (e + 3) // 4 * 4) for e in edges[:-1]] + [F]
+            q = 256 if F >= 1024 * n else 4  # whole CTAs of the grid kernel (one thread per fixture, 256 per CTA)
+            edges = [min(F, (e + q // 2) // q * q) for e in edges[:-1]] + [F]
+            edges = sorted(set(edges))
         self.ranges = [(a, b) for a, b in zip(edges[:-1], edges[1:]) if b > a]
         self.fx = [{k: (None if v is None else v[a:b]) for k, v in fixtures.items()} for a, b in self.ranges]
         self.ws = None
