@@ -681,12 +681,16 @@ def main():
                        "timing": f"{'CUDA graph of' if not args.no_graph else ''} {args.steps} launches, CUDA events on "
                                  f"the launch stream, median of {r['reps']} repetitions, max over ranks",
                        "waves": {"chain_groups_per_gpu": groups, "sms": 148, "waves": groups / 148.0,
-                                 "quantisation_efficiency": groups / (148.0 * math.ceil(groups / 148.0))},
+                                 "quantisation_efficiency": groups / (148.0 * math.ceil(groups / 148.0)),
+                                 "launches_per_step": r["launches"] / max(args.steps, 1),
+                                 "tail_split": ("the last partial wave (%d groups) runs as thread-block clusters in a second launch"
+                                                % (groups % 148)) if r["launches"] > args.steps else "none"},
                        "plan": st},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps,
-                    "api": "bplx_logdensity_fwdbwd_host (pinned numpy in/out, chain-major [C, D])"},
+                    "api": "bplx_logdensity_fwdbwd_host (pinned numpy in/out, chain-major [C, D]; transposed on the device to "
+                           "the native layout, copies and kernels pipelined in chunks)"},
             "gpu_launches": r["launches"],
             "finite": r["finite"],
             "parity_max_err": r["parity"],
