@@ -3,6 +3,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <new>
@@ -33,6 +34,7 @@ void reload_env_switches() {
   e.nuts_generic = getenv("BPLX_NUTS_GENERIC") != nullptr;
   e.no_tail_split = getenv("BPLX_NO_TAIL_SPLIT") != nullptr;
   e.no_transpose = getenv("BPLX_NO_TRANSPOSE") != nullptr;
+  if (const char* v = getenv("BPLX_TRANSPOSE_MIN_ELEMS")) e.transpose_min_elems = (size_t)atoll(v);
   if (const char* v = getenv("BPLX_SPLIT")) e.split = atoi(v);
   if (const char* v = getenv("BPLX_HOST_CHUNKS")) e.host_chunks = atoi(v);
   g_env = e;
@@ -109,10 +111,9 @@ static int launch_transpose(const float* in, float* out, int R, int Cc, size_t l
 
 // Room behind the kernel's own workspace for one transposed copy of theta and of the gradient ([D][Cpad] each): large
 // [chains, D] batches are computed in the kernel's native [D, chains] layout (see enqueue).
-constexpr size_t kTransposeMinElems = (size_t)1 << 22;
 static size_t align256(size_t n) { return (n + 255) / 256 * 256; }
 static size_t transpose_room(const KernelParams& kp, int C) {
-  if ((size_t)C * (size_t)kp.D < kTransposeMinElems) return 0;
+  if ((size_t)C * (size_t)kp.D < env_switches().transpose_min_elems) return 0;
   return 2 * (((size_t)C + 31) / 32 * 32) * (size_t)kp.D * sizeof(float);
 }
 
@@ -130,9 +131,12 @@ static int enqueue(const bplx_problem* p, int C, int layout, int ld, const float
   BPLX_REQUIRE(C > 0, BPLX_E_INVALID, "num_chains must be positive (got %d)", C);
   BPLX_REQUIRE(theta && lp && grad, BPLX_E_INVALID, "theta, lp and grad must not be NULL");
   if (layout == BPLX_CHAIN_MAJOR && !env_switches().no_transpose) {
-    // A large [chains, D] batch (what a vmapped jax.ffi call hands over): tiled transposes of theta before and of the
-    // gradient after the kernel, which then runs in its native layout (configs[2], 32,768 chains: 1.6 + 0.2 ms instead
-    // of 3.5 ms of strided per-chain reads) -- when the caller's workspace has the room bplx_logdensity_workspace_bytes asks for.
+    // A [chains, D] batch (what a vmapped jax.ffi call hands over): tiled transposes of theta before and of the
+    // gradient after the kernel, which then runs in its native layout (configs[2], 32,768 chains: 1.6 + 0.14 ms instead
+    // of 3.5 ms of strided per-chain reads) -- when the caller's workspace has the room bplx_logdensity_workspace_bytes
+    // asks for.  From 2^17 elements: measured per leapfrog of a fit with chain-major sampler state, configs[1] at 4,096
+    // chains x 73 parameters 45 -> 40 us, configs[2] data at 256 chains x 1,339 231 -> 153 us; configs[0] at 1,024 x 45
+    // (below the threshold) 28.7 vs 29.5 us.
     const size_t base = align256(workspace_bytes(p->kp, C)), room = transpose_room(p->kp, C);
     if (room > 0 && ws != nullptr && ws_bytes >= base + room) {
       const int Dc = lik ? p->lik_D : p->kp.D;
@@ -450,7 +454,7 @@ int bplx_logdensity_fwdbwd_host(bplx_problem* p, int C, const float* theta, floa
   // Large batches go through the kernel's native chain-minor layout: a tiled transpose of theta before the kernel and of
   // the gradient after it (two passes over HBM each, ~0.1 ms for configs[2] at 32,768 chains) instead of the kernel's
   // strided per-chain reads (3.5 ms against 1.6 ms in the native layout).
-  const bool native = (size_t)C * D >= ((size_t)1 << 22) && !env_switches().no_transpose;
+  const bool native = (size_t)C * D >= std::max(env_switches().transpose_min_elems, (size_t)1 << 20) && !env_switches().no_transpose;
   if (nchunk == 1) {  // one piece: everything in order on one stream, no events (each costs microseconds at this scale)
     // lp and corr_coef are one coalesced 128-byte store per warp: when the caller's arrays are page-locked the kernel
     // writes them straight into host memory (posted PCIe writes) instead of two more copies of 6.6 us each

@@ -40,6 +40,7 @@ void note_launch(int n = 1);  // kernels enqueued by this library (bplx_launch_c
 struct EnvSwitches {
   bool no_pdl = false, nuts_generic = false, no_tail_split = false, no_transpose = false;
   int split = 0, host_chunks = 0;
+  size_t transpose_min_elems = (size_t)1 << 17;  // BPLX_TRANSPOSE_MIN_ELEMS: smallest chains x D device batch that is transposed
 };
 const EnvSwitches& env_switches();
 void reload_env_switches();

@@ -112,9 +112,9 @@ def sample(potential: Callable[[torch.Tensor, torch.Tensor, torch.Tensor], None]
     the step kernel, so split R-hat and ESS need no stored draws (``diagnostics.streaming_summary``).
 
     ``state_layout``: ``"chain_minor"`` (every array ``[D, C]``), ``"chain_major"`` (``[C, D]``, needs ``potential_cm``)
-    or ``"auto"``: chain-major when ``potential_cm`` is given, the model is too large for the register-resident step
-    kernels (D > 256) and the batch is large enough for the log-density call to go through its transposing route
-    (C x D >= 2^22).  The returned tensors have the same logical shapes either way (views)."""
+    or ``"auto"``: chain-major whenever ``potential_cm`` is given -- measured per leapfrog of a fit: configs[0] at 1,024
+    chains 29.8 -> 28.5 us, configs[1] at 4,096 chains 63 -> 40 us, configs[2] at 32,768 chains 4.57 -> 2.62 ms.  The
+    returned tensors have the same logical shapes either way (views)."""
     if not theta0.is_cuda:
         raise RuntimeError("bpl_next_b200.nuts needs CUDA tensors: there is no CPU fallback")
     lib = _declare(_abi.lib())
@@ -123,8 +123,7 @@ def sample(potential: Callable[[torch.Tensor, torch.Tensor, torch.Tensor], None]
     f32 = dict(dtype=torch.float32, device=dev)
     if state_layout not in ("auto", "chain_minor", "chain_major"):
         raise ValueError(f"state_layout {state_layout!r}")
-    cm = state_layout == "chain_major" or (state_layout == "auto" and potential_cm is not None and D > 256
-                                            and Cn * D >= (1 << 22))
+    cm = state_layout == "chain_major" or (state_layout == "auto" and potential_cm is not None)
     if cm and potential_cm is None:
         raise ValueError("state_layout='chain_major' needs potential_cm (the log-density on [C, D] tensors)")
     # row pitch of every [D, C] array (the kernels take any pitch >= C; measured on B200: padding a 4 KB-multiple pitch

@@ -119,7 +119,7 @@ int bplx_problem_warp_stats(const bplx_problem* p, long long* out, int n);
 /* ---- log-density + gradient: replaces value_and_grad(potential_fn) per leapfrog ---------- */
 /* (numpyro potential_energy of `_model`; the returned lp is the log JOINT density, i.e. MINUS
  * the potential energy, and grad is d lp / d theta.) */
-/* Workspace for num_chains chains.  For large batches (num_chains x D >= 2^22 elements) this includes room for one
+/* Workspace for num_chains chains.  For batches of num_chains x D >= 2^17 elements this includes room for one
  * transposed copy of theta and of the gradient: BPLX_CHAIN_MAJOR calls are then computed in the kernel's native
  * BPLX_CHAIN_MINOR layout (two tiled transposes around the kernel; the kernel alone is 2.2x slower on [chains, D] buffers
  * of configs[2] size).  A smaller workspace (the kernel's own need) is accepted: the call then runs on the buffers as

@@ -35,7 +35,7 @@ r = bn.sample(potential, theta0, num_warmup=1000, num_samples=10, max_tree_depth
               use_graph=not os.environ.get("BPLX_NO_GRAPH"))  # (plain launches for an ncu capture)
 blocks = np.array(r.block_ms) / 32.0
 lp = torch.empty(C, device="cuda")
-cm = LAYOUT == "chain_major" or (LAYOUT == "auto" and p.D > 256 and C * p.D >= (1 << 22))
+cm = LAYOUT in ("chain_major", "auto")
 th = theta0.t().contiguous() if cm else theta0
 grad = torch.empty_like(th)
 f = potential_cm if cm else potential
