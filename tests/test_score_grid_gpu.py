@@ -129,3 +129,28 @@ def test_grid_fixture_ranges_reuse_the_tables():
     assert torch.equal(grid, full) and torch.equal(out, out_full)
     t = sg.run(timed=True)
     assert len(t) == 3 and t[0] > 0
+
+
+@pytest.mark.parametrize("model", ["extended", "neutral_wc"])
+def test_grid_max_goals_63_with_large_rates_stays_finite(model):
+    """The largest grid the API accepts (max_goals = 63) at rates of 4-10 goals: the normalised pmf recurrence of the
+    tiled kernel must neither overflow (round 1's un-normalised powers did beyond 16 goals -- ADVICE r1) nor lose the tiny
+    cells' mass: every cell finite, the oracle's values to 1e-6 absolute, rows summing to the oracle's sums."""
+    import torch
+    from bpl_next_b200 import score_grid
+
+    S, T, F, Cf, mg = 48, 6, 21, 3, 63
+    s = make_samples(model, S, T, Cf, seed=5)
+    s["attack"] = (s["attack"] + 1.7).astype(np.float32)  # rates e^1.7 = 5.5 times larger
+    fx = make_fixtures(model, F, T, Cf, seed=6)
+    ds = {k: torch.from_numpy(v).cuda() for k, v in s.items()}
+    dfx = {k: torch.from_numpy(v).cuda() for k, v in fx.items()}
+    grid, outcome = score_grid(model, ds, dfx, mg)
+    torch.cuda.synchronize()
+    g, o = grid.cpu().numpy(), outcome.cpu().numpy()
+    assert np.isfinite(g).all() and np.isfinite(o).all()
+    g_o, o_o = oracle_grid(model, s, fx, mg)
+    assert g_o.sum(axis=(1, 2)).min() > 0.99  # (the rates are large enough to matter, small enough for a 64 x 64 grid)
+    np.testing.assert_allclose(g, g_o, rtol=0, atol=1e-6)
+    np.testing.assert_allclose(g.sum(axis=(1, 2)), g_o.sum(axis=(1, 2)), atol=2e-5)
+    np.testing.assert_allclose(o, o_o, rtol=0, atol=2e-5)
