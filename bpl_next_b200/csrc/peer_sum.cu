@@ -41,10 +41,22 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 // the (wide) sum kernel ever spins on a slower rank next to this rank's own grid kernel of the following range.
 __global__ void __launch_bounds__(32) peer_flag_kernel(const PeerArgs a) {
   const int lane = threadIdx.x;
+  // epoch 0: the call counter kept behind the per-rank flags of this rank's own buffer (slot kMaxPeers) -- every rank makes
+  // the same sequence of calls, so the counters agree, and a launch that needs no host argument can be replayed in a graph
+  uint32_t epoch = a.epoch;
+  if (epoch == 0u) {
+    uint32_t* counter = a.flags[a.rank] + kMaxPeers;
+    if (lane == 0) {
+      epoch = *counter + 1u;
+      if (epoch == 0u) epoch = 1u;
+      *counter = epoch;
+    }
+    epoch = __shfl_sync(0xffffffffu, epoch, 0);
+  }
   __threadfence_system();  // what this rank wrote before (its partial grid) is visible to whoever sees the flag
-  if (lane < a.n) st_release_sys(a.flags[lane] + a.rank, a.epoch);
+  if (lane < a.n) st_release_sys(a.flags[lane] + a.rank, epoch);
   if (lane < a.n)  // (epochs only grow; the difference is taken so that a wrapped counter still works)
-    while ((int32_t)(ld_acquire_sys(a.flags[a.rank] + lane) - a.epoch) < 0) {
+    while ((int32_t)(ld_acquire_sys(a.flags[a.rank] + lane) - epoch) < 0) {
     }
   __syncwarp();
   __threadfence_system();
@@ -92,8 +104,8 @@ extern "C" int bplx_peer_sum(void* const* bufs, int nranks, int rank, size_t fla
                              float* out0, size_t off1, size_t cnt1, float* out1, unsigned epoch, void* stream) {
   BPLX_REQUIRE(bufs && nranks >= 1 && nranks <= kMaxPeers && rank >= 0 && rank < nranks, BPLX_E_INVALID,
                "peer_sum: bad ranks (%d of %d, at most %d)", rank, nranks, kMaxPeers);
-  BPLX_REQUIRE(flag_bytes >= (size_t)nranks * sizeof(uint32_t) && flag_bytes % 16 == 0, BPLX_E_INVALID,
-               "peer_sum: the flag area must hold one 32-bit flag per rank and keep the data 16-byte aligned");
+  BPLX_REQUIRE(flag_bytes >= (size_t)(kMaxPeers + 1) * sizeof(uint32_t) && flag_bytes % 16 == 0, BPLX_E_INVALID,
+               "peer_sum: the flag area must hold %d 32-bit words and keep the data 16-byte aligned", kMaxPeers + 1);
   BPLX_REQUIRE((cnt0 == 0 || out0) && (cnt1 == 0 || out1), BPLX_E_INVALID, "peer_sum: output is NULL");
   PeerArgs a{};
   for (int q = 0; q < nranks; q++) {

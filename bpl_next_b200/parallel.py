@@ -77,7 +77,7 @@ class ShardedScoreGrid:
 
     def __init__(self, model: str, local_samples: Dict[str, torch.Tensor], fixtures: Dict[str, torch.Tensor],
                  max_goals: int, num_samples_total: int, group=None, chunks: Optional[int] = None,
-                 local_fn: Optional[Callable] = None, peer: bool = True):
+                 local_fn: Optional[Callable] = None, peer: bool = True, use_graph: bool = True):
         if local_fn is None:
             from .problem import score_grid as local_fn
         self.fn, self.model, self.samples, self.group = local_fn, model, local_samples, group
@@ -106,6 +106,8 @@ class ShardedScoreGrid:
         self.exchange_kind = "none (one rank)" if not self.dist else \
             f"all_reduce(sum) of the partial grids, {len(self.ranges)} fixture ranges, range k-1 exchanged while range k computes"
         self.peer = None
+        self.graphs = None
+        self.use_graph = use_graph
         if self.cuda:
             self.side = torch.cuda.Stream(device=dev, priority=-1)
             self.ev = [torch.cuda.Event() for _ in self.ranges]
@@ -132,10 +134,10 @@ class ShardedScoreGrid:
             dist.barrier(group=grp)  # every rank's flags are zero before anyone publishes
             ptrs = [(C.c_void_p * n)(*[int(p) for p in h.buffer_ptrs]) for h in handles]
             self.peer = {
-                "n": n, "rank": dist.get_rank(grp), "bufs": bufs, "handles": handles, "ptrs": ptrs, "epoch": [0, 0],
-                "parity": 0, "lib": _abi.lib(), "F": F, "gg": g * g,
+                "n": n, "rank": dist.get_rank(grp), "bufs": bufs, "handles": handles, "ptrs": ptrs, "parity": 0, "lib": _abi.lib(), "F": F, "gg": g * g,
                 "grid": [t[self._FLAG_FLOATS:self._FLAG_FLOATS + F * g * g].view(F, g, g) for t in bufs],
                 "outcome": [t[self._FLAG_FLOATS + F * g * g:self._FLAG_FLOATS + F * g * g + F * 3].view(F, 3) for t in bufs],
+                "scratch": (torch.empty((F, g, g), dtype=torch.float32, device=dev), torch.empty((F, 3), dtype=torch.float32, device=dev)),
             }
             self.exchange_kind = (f"peer-memory sum over NVLink (bplx_peer_sum per rank and fixture range: flag exchange, then "
                                   f"every rank's partial grid read in rank order), {len(self.ranges)} fixture ranges, range k-1 "
@@ -144,11 +146,13 @@ class ShardedScoreGrid:
             self.peer = None
             self.exchange_kind += f" [symmetric memory unavailable: {type(e).__name__}: {e}]"
 
-    def _local(self, i):
+    def _local(self, i, exchange=True):
         a, b = self.ranges[i]
         kw = dict(scale=self.scale, want_outcome=True)
         if self.cuda:
-            if self.peer is not None:  # the partial sums go to this run's symmetric buffer
+            if self.peer is not None and not exchange:  # (the compute-only pass of a timed run: private scratch)
+                kw.update(grid=self.peer["scratch"][0][a:b], outcome=self.peer["scratch"][1][a:b])
+            elif self.peer is not None:  # the partial sums go to this run's symmetric buffer
                 par = self.peer["parity"]
                 kw.update(grid=self.peer["grid"][par][a:b], outcome=self.peer["outcome"][par][a:b])
             else:
@@ -166,15 +170,52 @@ class ShardedScoreGrid:
             from . import _abi
             P = self.peer
             par = P["parity"]
-            P["epoch"][par] += 1
-            _abi.check(P["lib"].bplx_peer_sum(
+            _abi.check(P["lib"].bplx_peer_sum(  # (epoch 0: the kernel counts the calls itself -> replayable in a graph)
                 P["ptrs"][par], P["n"], P["rank"], self._FLAG_FLOATS * 4,
                 a * P["gg"], (b - a) * P["gg"], self.grid[a:b].data_ptr(),
                 P["F"] * P["gg"] + a * 3, (b - a) * 3, self.outcome[a:b].data_ptr(),
-                P["epoch"][par], torch.cuda.current_stream().cuda_stream))
+                0, torch.cuda.current_stream().cuda_stream))
             return
         dist.all_reduce(self.grid[a:b], op=dist.ReduceOp.SUM, group=self.group)
         dist.all_reduce(self.outcome[a:b], op=dist.ReduceOp.SUM, group=self.group)
+
+    def _body(self, exchange: bool):
+        """One pass over the fixture ranges on the current stream (+ the side stream for the exchanges)."""
+        main = torch.cuda.current_stream()
+        for i in range(len(self.ranges)):
+            self._local(i, exchange)
+            if self.dist and exchange:
+                self.ev[i].record(main)
+                self.side.wait_event(self.ev[i])
+                with torch.cuda.stream(self.side):
+                    self._exchange(i)
+        if self.dist and exchange:
+            main.wait_stream(self.side)
+
+    def _capture(self):
+        """With the peer-memory exchange a run has no argument that changes between runs: it is captured once per buffer
+        parity (plus once without the exchange, for the timed split) and replayed -- every rank's ~16 launches then start
+        without Python in between, which is most of the skew the flag wait would otherwise absorb."""
+        self.graphs = None
+        if self.peer is None or not self.use_graph:
+            return
+        try:
+            cap = torch.cuda.Stream(device=self.grid.device)
+            cap.wait_stream(torch.cuda.current_stream())
+            graphs = {}
+            with torch.cuda.stream(cap):
+                for key, par, ex in (("x0", 0, True), ("x1", 1, True), ("c0", 0, False)):
+                    self.peer["parity"] = par
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=cap):
+                        self._body(ex)
+                    graphs[key] = g
+            torch.cuda.current_stream().wait_stream(cap)
+            self.graphs = graphs
+            self.peer["parity"] = 1
+        except Exception as e:  # capture not possible here: plain launches
+            self.graphs = None
+            self.exchange_kind += f" [graph capture failed: {type(e).__name__}: {e}]"
 
     def run(self, timed: bool = False):
         if not self.cuda:
@@ -187,9 +228,27 @@ class ShardedScoreGrid:
             from . import problem as _p
             need = max(_p.score_grid_workspace_bytes(self.model, self.samples, fx, self.max_goals) for fx in self.fx)
             self.ws = torch.empty(max(need, 1), dtype=torch.uint8, device=self.grid.device)
+            self._body(False)  # (lazy allocations inside the kernels' wrappers happen here, outside any capture)
+            torch.cuda.current_stream().synchronize()
+            self._capture()
         main = torch.cuda.current_stream()
         if self.peer is not None:
             self.peer["parity"] ^= 1
+        if self.graphs is not None:
+            g = self.graphs["x%d" % self.peer["parity"]]
+            if not timed:
+                g.replay()
+                return self.grid, self.outcome
+            # total = the replayed run; compute = the same launches without the exchange; their difference is what the
+            # exchange exposes (events inside a graph cannot be timed)
+            self.t[0].record(main)
+            g.replay()
+            self.t[1].record(main)
+            self.graphs["c0"].replay()
+            self.t[2].record(main)
+            self.t[2].synchronize()
+            total, comp = self.t[0].elapsed_time(self.t[1]), self.t[1].elapsed_time(self.t[2])
+            return total, comp, max(total - comp, 0.0)
         if timed:
             self.t[0].record(main)
         for i in range(len(self.ranges)):

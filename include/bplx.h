@@ -238,7 +238,9 @@ int bplx_score_grid_host(const bplx_samples* s, const bplx_fixtures* f, int max_
  *   off, cnt    element ranges of the data (grid rows, outcome rows of a fixture range); cnt1 may be 0
  *   out0, out1  this rank's results (ordinary device memory): out[i] = sum over q, in rank order, of data_q[off + i] --
  *               the same bits on every rank
- *   epoch       a counter that every rank increases by one per call (all ranks make the same sequence of calls)
+ *   epoch       a counter that every rank increases by one per call (all ranks make the same sequence of calls); 0 = the
+ *               kernel keeps the counter itself, in word 16 of this rank's flag area (the call then has no argument that
+ *               changes from one call to the next and can be replayed in a CUDA graph).  flag_bytes >= 68, multiple of 16.
  * The kernel publishes this rank's flag to all peers, waits for theirs, then reads every rank's range over NVLink.  A
  * rank may overwrite a range of its own buffer again only after a later call on that rank has returned from its wait
  * (double-buffer by call parity, as bpl_next_b200.parallel.ShardedScoreGrid does).

@@ -14,7 +14,7 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 out = {"world": world}
 # ---- N1 --------------------------------------------------------------------------------------------------------
-S, F = 4096, 2000
+S, F = 4096, 4100
 s, fx = datasets.config_5(S=S, F=F)
 start, cnt = parallel.shard(S, rank, world)
 local_s = {k: torch.from_numpy(v[start:start + cnt]).cuda() for k, v in s.items()}
@@ -32,8 +32,8 @@ out["grid_max_abs_diff"] = float((grid - ref).abs().max().item())
 out["outcome_max_abs_diff"] = float((outc - ref_out).abs().max().item())
 out["grid_sharded_ms_max_over_ranks"] = float(t.item())
 # ---- N1b: the overlapped, ranged variant; exchange over peer memory (bplx_peer_sum) against NCCL all_reduce -------------
-for name, peer in (("peer", True), ("nccl", False)):
-    sg = parallel.ShardedScoreGrid("neutral_wc", local_s, dfx, 10, S, peer=peer)
+for name, peer, graph in (("peer_graph", True, True), ("peer", True, False), ("nccl", False, False)):
+    sg = parallel.ShardedScoreGrid("neutral_wc", local_s, dfx, 10, S, peer=peer, use_graph=graph)
     for _ in range(3):
         sg.run()
     torch.cuda.synchronize(); dist.barrier()
@@ -45,7 +45,8 @@ for name, peer in (("peer", True), ("nccl", False)):
     torch.cuda.synchronize()
     med = np.median(np.array(ts), axis=0)
     tt = torch.tensor(med, device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    out[f"ranged_{name}"] = {"exchange": sg.exchange_kind, "uses_peer_memory": sg.peer is not None,
+    out[f"ranged_{name}"] = {"exchange": sg.exchange_kind, "uses_peer_memory": sg.peer is not None, "replayed_as_graph": sg.graphs is not None,
+                             "ranges": len(sg.ranges),
                              "grid_max_abs_diff": float((g2 - ref).abs().max().item()),
                              "outcome_max_abs_diff": float((o2 - ref_out).abs().max().item()),
                              "total_ms": float(tt[0].item()), "compute_ms": float(tt[1].item()), "exposed_exchange_ms": float(tt[2].item())}
