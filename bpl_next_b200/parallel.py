@@ -145,6 +145,13 @@ class ShardedScoreGrid:
         except Exception as e:  # no symmetric memory on this system: NCCL
             self.peer = None
             self.exchange_kind += f" [symmetric memory unavailable: {type(e).__name__}: {e}]"
+        # every rank must take the same path: one that spins on peer flags next to one inside all_reduce would hang
+        ok = torch.tensor([1 if self.peer is not None else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0 and self.peer is not None:
+            self.peer = None
+            self.exchange_kind = (f"all_reduce(sum) of the partial grids, {len(self.ranges)} fixture ranges, range k-1 exchanged "
+                                  f"while range k computes [symmetric memory unavailable on another rank]")
 
     def _local(self, i, exchange=True):
         a, b = self.ranges[i]
