@@ -536,24 +536,28 @@ __global__ void __launch_bounds__(CM ? 256 : 32 * kNutsMaxY, CM ? 4 : 1) nuts_st
 // the Welford accumulators, the first checkpoint level of the U-turn test) in a second batch that arrives while the
 // first stages run; the stages then work on registers and store what they change.  Same arithmetic in the same order
 // as the kernel above: with the same (32, Y) geometry the two give identical bits (tests/test_nuts_gpu.py).
-template <int CPB, int NPT>
-__global__ void __launch_bounds__(512) nuts_step_fast_kernel(const bplx_nuts_params P) {
-  __shared__ float red[2 * 512];
+// CM = true (chain-major state, bplx_nuts_params::state_layout == 1): block = (32 lanes, CPB chains), a warp per chain,
+// lane y owns d = y + 32 j -- the reductions are warp butterflies, the U-turn levels a chain's own, no block barrier.
+template <int CPB, int NPT, bool CM>
+__global__ void __launch_bounds__(CM ? 32 * CPB : 512) nuts_step_fast_kernel(const bplx_nuts_params P) {
+  __shared__ float red[CM ? 1 : 2 * 512];
   __shared__ unsigned lvl_mask;
-  const int Y = blockDim.y, y = threadIdx.y, x = threadIdx.x;
+  const int Y = CM ? 32 : blockDim.y, y = CM ? threadIdx.x : threadIdx.y, x = CM ? threadIdx.y : threadIdx.x;
   const int c_raw = blockIdx.x * CPB + x;
   const bool valid = c_raw < P.C;
   const int c = valid ? c_raw : P.C - 1;
   const int D = P.D;
-  const size_t ld = (size_t)P.ld;
-  if (x == 0 && y == 0) lvl_mask = 0u;
+  const size_t ld = CM ? (size_t)1 : (size_t)P.ld;  // stride between a chain's consecutive parameters
+  const size_t plane = CM ? (size_t)P.C * (size_t)P.ld_state : (size_t)D * (size_t)P.ld;  // one vector of every chain
+  const size_t cbase = CM ? (size_t)c * (size_t)P.ld_state : (size_t)c;
+  if (!CM && x == 0 && y == 0) lvl_mask = 0u;
   bool has[NPT];
   size_t off[NPT];
 #pragma unroll
   for (int j = 0; j < NPT; j++) {
     const int d = y + j * Y;
     has[j] = d < D;
-    off[j] = (size_t)(has[j] ? d : 0) * ld + (size_t)c;
+    off[j] = (size_t)(has[j] ? d : 0) * ld + cbase;
   }
   auto ldv = [&](const float* base, float (&v)[NPT], bool on) {
 #pragma unroll
@@ -565,6 +569,11 @@ __global__ void __launch_bounds__(512) nuts_step_fast_kernel(const bplx_nuts_par
       if (has[j]) base[off[j]] = v[j];
   };
   auto reduce1 = [&](float& v) {  // sum over the slices of every chain (all threads of the block call it)
+    if (CM) {
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+      return;
+    }
     __syncthreads();
     red[y * CPB + x] = v;
     __syncthreads();
@@ -573,6 +582,14 @@ __global__ void __launch_bounds__(512) nuts_step_fast_kernel(const bplx_nuts_par
     v = s;
   };
   auto reduce2 = [&](float (&v)[2]) {
+    if (CM) {
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) {
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], m);
+        v[1] += __shfl_xor_sync(0xffffffffu, v[1], m);
+      }
+      return;
+    }
     __syncthreads();
     red[y * CPB + x] = v[0];
     red[(Y + y) * CPB + x] = v[1];
@@ -623,8 +640,8 @@ __global__ void __launch_bounds__(512) nuts_step_fast_kernel(const bplx_nuts_par
   ldv(P.wf_m2, w2, warm);
   {
     const int i0 = my_lvls ? 31 - __clz(my_lvls) : 0;
-    ldv(P.r_ckpts + (size_t)i0 * D * ld, ck, my_lvls != 0u);
-    ldv(P.r_sum_ckpts + (size_t)i0 * D * ld, cks, my_lvls != 0u);
+    ldv(P.r_ckpts + (size_t)i0 * plane, ck, my_lvls != 0u);
+    ldv(P.r_sum_ckpts + (size_t)i0 * plane, cks, my_lvls != 0u);
   }
   curandStatePhilox4_32_10_t rng;
   curand_init(P.seed, (unsigned long long)(P.chain_offset + c), st.rng_offset, &rng);
@@ -699,19 +716,21 @@ __global__ void __launch_bounds__(512) nuts_step_fast_kernel(const bplx_nuts_par
       stv(P.gQ, gQ);
     }
     if (ckpt) {
-      stv(P.r_ckpts + (size_t)idx_max * D * ld, r1);
-      stv(P.r_sum_ckpts + (size_t)idx_max * D * ld, rQ);
+      stv(P.r_ckpts + (size_t)idx_max * plane, r1);
+      stv(P.r_sum_ckpts + (size_t)idx_max * plane, rQ);
     }
     if (take) st.sub_pe = pe1;
     st.sub_div = delta > P.max_delta_energy;
     st.sub_sum_accept += acc;
   }
   // ======== B. iterative U-turn test against the checkpoints: only the levels some chain of the block needs ============
-  if (my_lvls && y == 0) atomicOr(&lvl_mask, my_lvls);
-  __syncthreads();
+  if (!CM) {
+    if (my_lvls && y == 0) atomicOr(&lvl_mask, my_lvls);
+    __syncthreads();
+  }
   bool turning = false;
   {
-    unsigned m = lvl_mask;
+    unsigned m = CM ? my_lvls : lvl_mask;
     // (the level prefetched in batch 2 is this chain's highest; the block's may be higher)
     int have = my_lvls ? 31 - __clz(my_lvls) : -1;
     while (m) {
@@ -719,8 +738,8 @@ __global__ void __launch_bounds__(512) nuts_step_fast_kernel(const bplx_nuts_par
       m &= ~(1u << i);
       const bool need = pending && ((my_lvls >> i) & 1u) && !turning;
       if (need && have != i) {
-        ldv(P.r_ckpts + (size_t)i * D * ld, ck, true);
-        ldv(P.r_sum_ckpts + (size_t)i * D * ld, cks, true);
+        ldv(P.r_ckpts + (size_t)i * plane, ck, true);
+        ldv(P.r_sum_ckpts + (size_t)i * plane, cks, true);
         have = i;
       }
       float dots[2] = {0.0f, 0.0f};
@@ -739,8 +758,8 @@ __global__ void __launch_bounds__(512) nuts_step_fast_kernel(const bplx_nuts_par
       const unsigned below = my_lvls & ((1u << i) - 1u);
       if (need && below) {
         const int inext = 31 - __clz(below);
-        ldv(P.r_ckpts + (size_t)inext * D * ld, ck, true);
-        ldv(P.r_sum_ckpts + (size_t)inext * D * ld, cks, true);
+        ldv(P.r_ckpts + (size_t)inext * plane, ck, true);
+        ldv(P.r_sum_ckpts + (size_t)inext * plane, cks, true);
         have = inext;
       }
       reduce2(dots);
@@ -784,7 +803,7 @@ __global__ void __launch_bounds__(512) nuts_step_fast_kernel(const bplx_nuts_par
         stv(P.gP, gP);
       }
     }
-    if (__syncthreads_or(sub_done)) reduce2(dots);
+    if (CM ? sub_done : (bool)__syncthreads_or(sub_done)) reduce2(dots);
     if (sub_done) {
       if (move) st.pe = st.sub_pe;
       st.turning = st.sub_turning || dots[0] <= 0.0f || dots[1] <= 0.0f;
@@ -846,14 +865,14 @@ __global__ void __launch_bounds__(512) nuts_step_fast_kernel(const bplx_nuts_par
       if (P.diag_lags > 0) {
 #pragma unroll
         for (int j = 0; j < NPT; j++)
-          if (has[j]) diag_collect(P, k, off[j], (size_t)D * ld, zP[j]);
+          if (has[j]) diag_collect(P, k, off[j], plane, zP[j]);
       }
       if (k % P.thin == 0 && k / P.thin < P.num_keep) {
         const int slot = k / P.thin;
-        stv(P.samples + (size_t)slot * D * ld, zP);
+        stv(P.samples + (size_t)slot * plane, zP);
         if (y == 0) {
-          P.sample_lp[(size_t)slot * ld + c] = -st.pe;
-          P.sample_accept[(size_t)slot * ld + c] = accept;
+          P.sample_lp[(size_t)slot * P.ld + c] = -st.pe;
+          P.sample_accept[(size_t)slot * P.ld + c] = accept;
         }
       }
     }
@@ -889,7 +908,7 @@ __global__ void __launch_bounds__(512) nuts_step_fast_kernel(const bplx_nuts_par
       stv(P.gL, gP);
       stv(P.gR, gP);
     }
-    if (__syncthreads_or(fresh)) reduce1(ke);
+    if (CM ? fresh : (bool)__syncthreads_or(fresh)) reduce1(ke);
     if (fresh) {
       draws += 64u + 2u * (unsigned)D + 8u;
       st.energy_current = st.pe + 0.5f * ke;
@@ -1012,14 +1031,16 @@ int bplx_nuts_step(const bplx_nuts_params* p, void* stream) {
     cfg.blockDim = block;
     return cudaLaunchKernelEx(&cfg, fn, *p);
   };
-  if (p->state_layout == 1)  // chain-major state: a warp per chain, eight chains per block
+  if (p->state_layout == 1 && !generic && p->D <= 128)  // chain-major, small model: the chain's slices live in registers
+    BPLX_CUDA(launch(&nuts_step_fast_kernel<8, 4, true>, 8, dim3(32, 8)));
+  else if (p->state_layout == 1)  // chain-major state: a warp per chain, eight chains per block
     BPLX_CUDA(launch(&nuts_step_kernel<true>, 8, dim3(32, 8)));
   else if (!generic && p->D <= 4 * kNutsMaxY)  // same geometry as the generic kernel: identical bits
-    BPLX_CUDA(launch(&nuts_step_fast_kernel<32, 4>, 32, dim3(32, Y)));
+    BPLX_CUDA(launch(&nuts_step_fast_kernel<32, 4, false>, 32, dim3(32, Y)));
   else if (!generic && p->D <= 128)
-    BPLX_CUDA(launch(&nuts_step_fast_kernel<16, 4>, 16, dim3(16, 32)));
+    BPLX_CUDA(launch(&nuts_step_fast_kernel<16, 4, false>, 16, dim3(16, 32)));
   else if (!generic && p->D <= 256)
-    BPLX_CUDA(launch(&nuts_step_fast_kernel<8, 4>, 8, dim3(8, 64)));
+    BPLX_CUDA(launch(&nuts_step_fast_kernel<8, 4, false>, 8, dim3(8, 64)));
   else
     BPLX_CUDA(launch(&nuts_step_kernel<false>, 32, dim3(32, Y)));
   BPLX_CUDA(cudaGetLastError());

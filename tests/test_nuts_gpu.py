@@ -80,12 +80,17 @@ def test_dixon_coles_posterior_is_stationary_across_seeds():
     assert 0.1 < ha < 0.3, ha
 
 
-@pytest.mark.parametrize("D,C", [(6, 70), (44, 96), (64, 33)])
-def test_register_resident_step_matches_stage_by_stage_kernel(D, C, bplx_env):
+@pytest.mark.parametrize("layout", ["chain_minor", "chain_major"])
+@pytest.mark.parametrize("D,C", [(6, 70), (44, 96), (64, 33), (113, 21)])
+def test_register_resident_step_matches_stage_by_stage_kernel(D, C, layout, bplx_env):
     """Small models run the NUTS bookkeeping out of registers (nuts_step_fast_kernel); with the same block geometry it
     does the same arithmetic in the same order as the stage-by-stage kernel, so whole runs must agree bit for bit:
-    draws, acceptance statistics, leapfrog counts, adapted step sizes and mass matrices."""
+    draws, acceptance statistics, leapfrog counts, adapted step sizes and mass matrices.  Both state layouts (chain-minor:
+    lane = chain, up to 16 slices; chain-major: a warp per chain, D <= 128)."""
     import torch
+
+    if layout == "chain_minor" and D > 64:
+        pytest.skip("chain-minor: the two kernels share their geometry up to D = 64 only")
 
     g = torch.Generator(device="cuda").manual_seed(3)
     sd = torch.exp(torch.rand((D, 1), generator=g, device="cuda") * 3 - 1.5)
@@ -96,11 +101,17 @@ def test_register_resident_step_matches_stage_by_stage_kernel(D, C, bplx_env):
         lp.copy_(-0.5 * (z * z).sum(0))
         grad.copy_(-z / sd)
 
+    def potential_cm(theta, lp, grad):
+        z = (theta - mu[:, 0]) / sd[:, 0]
+        lp.copy_(-0.5 * (z * z).sum(1))
+        grad.copy_(-z / sd[:, 0])
+
     theta0 = torch.rand((D, C), generator=g, device="cuda") * 4 - 2
     runs = []
     for generic in (False, True):
         bplx_env(BPLX_NUTS_GENERIC="1" if generic else None)
-        runs.append(bn.sample(potential, theta0.clone(), num_warmup=120, num_samples=40, seed=7, use_graph=False))
+        runs.append(bn.sample(potential, theta0.clone(), num_warmup=120, num_samples=40, seed=7, use_graph=False,
+                              potential_cm=potential_cm, state_layout=layout))
     a, b = runs
     assert a.launches == b.launches
     assert torch.equal(a.samples, b.samples)
