@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(CM ? 256 : 32 * kNutsMaxY, CM ? 4 : 1) nuts_st
 // CM = true (chain-major state, bplx_nuts_params::state_layout == 1): block = (32 lanes, CPB chains), a warp per chain,
 // lane y owns d = y + 32 j -- the reductions are warp butterflies, the U-turn levels a chain's own, no block barrier.
 template <int CPB, int NPT, bool CM>
-__global__ void __launch_bounds__(CM ? 32 * CPB : 512) nuts_step_fast_kernel(const bplx_nuts_params P) {
+__global__ void __launch_bounds__(CM ? 32 * CPB : 512, CM ? 2 : 1) nuts_step_fast_kernel(const bplx_nuts_params P) {
   __shared__ float red[CM ? 1 : 2 * 512];
   __shared__ unsigned lvl_mask;
   const int Y = CM ? 32 : blockDim.y, y = CM ? threadIdx.x : threadIdx.y, x = CM ? threadIdx.y : threadIdx.x;
@@ -1031,7 +1031,9 @@ int bplx_nuts_step(const bplx_nuts_params* p, void* stream) {
     cfg.blockDim = block;
     return cudaLaunchKernelEx(&cfg, fn, *p);
   };
-  if (p->state_layout == 1 && !generic && p->D <= 128)  // chain-major, small model: the chain's slices live in registers
+  if (p->state_layout == 1 && !generic && p->D <= 64)  // chain-major, small model: the chain's slices live in registers
+    BPLX_CUDA(launch(&nuts_step_fast_kernel<8, 2, true>, 8, dim3(32, 8)));
+  else if (p->state_layout == 1 && !generic && p->D <= 128)
     BPLX_CUDA(launch(&nuts_step_fast_kernel<8, 4, true>, 8, dim3(32, 8)));
   else if (p->state_layout == 1)  // chain-major state: a warp per chain, eight chains per block
     BPLX_CUDA(launch(&nuts_step_kernel<true>, 8, dim3(32, 8)));
