@@ -215,3 +215,28 @@ def test_chain_major_device_call_through_the_native_layout(bplx_env):
     torch.cuda.synchronize()
     assert torch.equal(la[0], lb[0]) and torch.equal(la[1], lb[1].t()) and torch.equal(la[2], lb[2])
     p.close()
+
+
+def test_dynamic_model_chain_major_call_through_the_native_layout(bplx_env):
+    """The dynamic model takes the same route: a [chains, D] batch above the transposing threshold gives the bits of the
+    [D, chains] call, and of the untransposed call; a few chains against the oracle."""
+    import torch
+    from bpl_next_b200 import Problem, _abi
+
+    arr = H.small_problem("dynamic", seed=4, Cf=12, T=9, M=700, neutral_frac=0.2)
+    p = Problem(arr)
+    C = (1 << 17) // p.D + 37
+    theta = np.random.default_rng(94).uniform(-0.4, 0.4, (C, p.D)).astype(np.float32)
+    tM = torch.from_numpy(theta).cuda()
+    n0 = _abi.lib().bplx_launch_count()
+    a = [x.clone() for x in p.logdensity(tM)]
+    assert _abi.lib().bplx_launch_count() - n0 == 3
+    b = [x.clone() for x in p.logdensity(tM.t().contiguous(), chain_minor=True)]
+    bplx_env(BPLX_NO_TRANSPOSE=1)
+    c = [x.clone() for x in p.logdensity(tM)]
+    torch.cuda.synchronize()
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1].t()) and torch.equal(a[2], b[2])
+    assert torch.equal(a[0], c[0]) and torch.equal(a[1], c[1]) and torch.equal(a[2], c[2])
+    idx = np.array([0, 31, 32, C - 1])
+    _check(arr, theta[idx], a[0].cpu().numpy()[idx], a[1].cpu().numpy()[idx], a[2].cpu().numpy()[idx])
+    p.close()
