@@ -448,7 +448,11 @@ int bplx_logdensity_fwdbwd_host(bplx_problem* p, int C, const float* theta, floa
   float* d_cc = d_lp + C;
   // (only worth it when a chunk still fills the GPU: below ~16k chains K1 is latency-bound and chunking serialises it;
   //  measured on configs[1], 4,096 chains: 104 us in one piece, 138 us in four)
-  int nchunk = C >= 32768 ? 8 : (C >= 16384 ? 4 : (C >= 8192 ? 2 : 1));
+  // by payload (measured on configs[2] data, ms per call for 1 / 2 / 4 / 8 chunks: 22 MB each way 1.07 / 0.82 / 0.78 / 1.01,
+  // 44 MB 2.10 / 1.53 / 1.32 / 1.41, 88 MB 4.08 / 2.97 / 2.48 / 2.39; 175 MB: 8 chunks)
+  const size_t payload = (size_t)C * D * sizeof(float);
+  int nchunk = payload >= ((size_t)80 << 20) ? 8 : (payload >= ((size_t)16 << 20) ? 4 : (payload >= ((size_t)6 << 20) ? 2 : 1));
+  while (nchunk > 1 && C / nchunk < 256) nchunk /= 2;
   if (const int want = env_switches().host_chunks)  // tuning: 1, 2, 4, 8 or 16 pipelined chunks
     if (want == 1 || want == 2 || want == 4 || want == 8 || want == 16) nchunk = want;
   // Large batches go through the kernel's native chain-minor layout: a tiled transpose of theta before the kernel and of

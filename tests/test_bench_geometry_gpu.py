@@ -156,13 +156,14 @@ def test_tail_split_matches_the_single_launch(bplx_env):
 def test_host_entry_point_through_the_native_layout(bplx_env):
     """Large batches through bplx_logdensity_fwdbwd_host are transposed on the device to the kernel's [D, chains] layout
     (and chunked so that copies and kernels overlap): same bits as the kernel run on the [chains, D] buffers directly,
-    in one piece and in two chunks, ragged chain counts included; eight small chunks (each few enough chains for the
-    cluster plans, which sum in another order) to rounding; a sample against the oracle."""
+    in one piece and in two chunks, ragged chain counts included; the default chunking of a 22 MB batch and eight small
+    chunks (each few enough chains for the cluster plans, which sum in another order) to rounding; a sample against the
+    oracle."""
     from bpl_next_b200 import Problem
 
     arr = H.from_training_data("neutral_wc", datasets.config_3(), epsilon=0.1)
     rng = np.random.default_rng(91)
-    for C, chunks in ((4101, None), (8200, None), (4101, 8)):
+    for C, chunks, exact in ((4101, 1, True), (8200, 2, True), (4101, None, False), (4101, 8, False)):
         p = Problem(arr)
         theta = rng.uniform(-2, 2, (C, p.D)).astype(np.float32)
         outs = []
@@ -170,7 +171,7 @@ def test_host_entry_point_through_the_native_layout(bplx_env):
                     {"BPLX_NO_TRANSPOSE": "1", "BPLX_HOST_CHUNKS": 1}):
             bplx_env(**env)
             outs.append([x.copy() for x in p.logdensity_host(theta)])
-        if chunks is None:
+        if exact:
             for a, b in zip(outs[0], outs[1]):
                 assert np.array_equal(a, b)
         else:
